@@ -1,0 +1,87 @@
+"""ctypes binding of libapgk.so (the C ABI in include/apgk.h).
+
+The shared library is built in-tree by __graft_entry__.build() / `make -C allpathslg_b200/csrc`.
+There is no fallback: if the library is missing, import of the symbols fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libapgk.so")
+
+APGK_OK = 0
+E_ARG, E_CUDA, E_NOMEM, E_STATE, E_RANGE = -1, -2, -3, -4, -5
+WANT_SPECTRUM, WANT_COUNTS = 1, 2
+N_STAGES = 12
+MAX_K = 96
+
+
+class Config(C.Structure):
+    _fields_ = [("K", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("prefix_bits", C.c_int32),
+                ("reserve_bases", C.c_uint64)]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("genome_len", C.c_uint64), ("seed_g", C.c_uint64), ("seed_p", C.c_uint64), ("seed_q", C.c_uint64),
+                ("seed_r", C.c_uint64), ("seed_e", C.c_uint64), ("read_len", C.c_uint32), ("err_per_200", C.c_uint32)]
+
+
+# every symbol include/apgk.h declares: name -> (restype, argtypes)
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+SYMBOLS = {
+    "apgk_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
+    "apgk_destroy": (None, [_vp]),
+    "apgk_last_error": (C.c_char_p, [_vp]),
+    "apgk_words_per_kmer": (C.c_int, [C.c_int]),
+    "apgk_reset": (C.c_int, [_vp]),
+    "apgk_add_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+    "apgk_add_reads_uniform": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32]),
+    "apgk_synth_reads": (C.c_int, [_vp, C.POINTER(SynthParams), C.c_uint64, C.c_uint64]),
+    "apgk_export_reads": (C.c_int, [_vp, _vp]),
+    "apgk_read_store_info": (C.c_int, [_vp, _u64p, _u64p]),
+    "apgk_finish": (C.c_int, [_vp]),
+    "apgk_totals": (C.c_int, [_vp, _u64p, _u64p]),
+    "apgk_spectrum": (C.c_int, [_vp, C.POINTER(_u64p), _u64p]),
+    "apgk_spectrum_sparse": (C.c_int, [_vp, C.POINTER(_u64p), C.POINTER(_u64p), _u64p]),
+    "apgk_counts_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
+    "apgk_counts_copy": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "apgk_lookup": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp]),
+    "apgk_read_freqs": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "apgk_owner_plan": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "apgk_owner_scatter": (C.c_int, [_vp, _vp]),
+    "apgk_owner_of": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, _vp]),
+    "apgk_finish_keys_device": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "apgk_spectrum_device": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
+    "apgk_spectrum_reload": (C.c_int, [_vp]),
+    "apgk_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "apgk_stage_name": (C.c_char_p, [C.c_int]),
+    "apgk_kernel_launches": (C.c_uint64, [_vp]),
+    "apgk_reset_counters": (None, [_vp]),
+    "apgk_geometry": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "apgk_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "apgk_host_free": (C.c_int, [_vp]),
+    "apgk_debug_host_extract": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp]),
+    "apgk_debug_host_canonical": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
+    "apgk_debug_host_synth": (C.c_int, [C.POINTER(SynthParams), C.c_uint64, C.c_uint64, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libapgk.so.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libapgk.so is missing at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C allpathslg_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)  # AttributeError if the symbol is not exported
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib

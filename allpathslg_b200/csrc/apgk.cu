@@ -1,0 +1,1062 @@
+// apgk.cu -- context, host orchestration and the C ABI (include/apgk.h) of libapgk.so.
+//
+// Pipeline of apgk_finish (one GPU):
+//   level 0   k_hist_reads -> column scan -> k_scatter_reads   reads  -> A (full keys, bucketed by D0 bits)
+//   level 1   k_hist_keys  -> column scan -> k_scatter_keys    A      -> B (remainders or full keys, D1 bits)
+//   local     k_local (+ k_big for oversize buckets)           B      -> temp records in A/B + spectrum
+//   table     scan of per-bucket record counts -> k_compact    temp   -> sorted (k-mer, count) table + index
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/apgk.h"
+#include "table.cuh"
+
+using namespace apgk;
+
+namespace {
+
+enum Stage { ST_HIST0, ST_SCAN0, ST_SCATTER0, ST_HIST1, ST_SCAN1, ST_SCATTER1, ST_LOCAL, ST_BIG, ST_TABLE, ST_SPECTRUM,
+             ST_OWNER, ST_TOTAL };
+const char* kStageNames[APGK_N_STAGES] = {"hist0", "scan0", "scatter0", "hist1", "scan1", "scatter1",
+                                          "local", "big", "table", "spectrum", "owner", "total"};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  // NOTE: cudaMemset / cudaMemcpy(D2D) on the legacy stream do not order with the context's
+  // non-blocking stream, so zeroing synchronises the device before returning.
+  cudaError_t ensure(size_t bytes, bool zero_new = false) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + (bytes >> 5) + 4096;  // a little slack so small growth does not realloc
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    if (zero_new) {
+      e = cudaMemset(p, 0, cap);
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+struct apgk_ctx {
+  apgk_config cfg{};
+  int W = 1;
+  int device = 0;
+  int n_sm = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // ---- read store
+  DevBuf bases, starts, staging, off_dev;
+  uint64_t total_bases = 0, n_reads = 0;
+  // ---- pipeline buffers
+  DevBuf A, B, cnt16, base32, chunksum, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
+      scratch, stacks, spec_dense, spec_ovf, misc;
+  // ---- results
+  DevBuf out_keys, out_cnt;
+  bool finished = false, have_table = false;
+  uint64_t n_instances = 0, n_distinct = 0;
+  KeyGeom geom{};
+  uint32_t nb1 = 0;          // number of level-1 buckets
+  uint32_t elem_bytes = 0;   // level-1 element size
+  uint64_t n_big = 0;
+  std::vector<uint64_t> spec_host, sparse_f, sparse_n;
+  bool spec_loaded = false;
+  // ---- owner partition state
+  uint32_t owner_ranks = 0;
+  uint32_t owner_tiles = 0;
+  std::vector<uint64_t> owner_counts;
+  // ---- instrumentation
+  cudaEvent_t ev[APGK_N_STAGES][2]{};
+  bool ev_used[APGK_N_STAGES]{};
+  float stage_ms[APGK_N_STAGES]{};
+  uint64_t launches = 0;
+};
+
+namespace {
+
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      char b__[512];                                                                                     \
+      snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      c->err = b__;                                                                                      \
+      return (e__ == cudaErrorMemoryAllocation) ? APGK_E_NOMEM : APGK_E_CUDA;                            \
+    }                                                                                                    \
+  } while (0)
+
+#define FAIL(code, ...)                        \
+  do {                                         \
+    char b__[512];                             \
+    snprintf(b__, sizeof b__, __VA_ARGS__);    \
+    c->err = b__;                              \
+    return (code);                             \
+  } while (0)
+
+#define LAUNCHED() do { c->launches++; CU(cudaGetLastError()); } while (0)
+
+void stage_begin(apgk_ctx* c, int s) { cudaEventRecord(c->ev[s][0], c->stream); c->ev_used[s] = true; }
+void stage_end(apgk_ctx* c, int s) { cudaEventRecord(c->ev[s][1], c->stream); }
+
+int words_for(int K) { return (2 * K + 63) / 64; }
+
+// tile geometry per key width
+template <int W> struct Geo;
+template <> struct Geo<1> { static constexpr int NT0 = 1024; static constexpr int NT1 = 1024; static constexpr uint32_t TILE1 = 16384; static constexpr int LM_KEY = 4096; };
+template <> struct Geo<2> { static constexpr int NT0 = 512;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 8192;  static constexpr int LM_KEY = 3072; };
+template <> struct Geo<3> { static constexpr int NT0 = 256;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 5120;  static constexpr int LM_KEY = 2048; };
+constexpr int LM_U32 = 4096;
+constexpr int COL_NT = 1024;
+
+// host-side description of a partition level, mirrored on the device in ctx->plan
+struct HostPlan {
+  std::vector<uint32_t> seg_tile0, seg_chunk0;
+  std::vector<uint64_t> seg_start;
+  LevelPlan lp{};
+};
+
+void build_plan(HostPlan& hp, const std::vector<uint64_t>& seg_sizes, uint32_t tile_elems, int bins) {
+  const int S = (int)seg_sizes.size();
+  hp.seg_tile0.assign(S + 1, 0); hp.seg_chunk0.assign(S + 1, 0); hp.seg_start.assign(S + 1, 0);
+  uint64_t max_tiles = 1;
+  for (int s = 0; s < S; s++) {
+    uint64_t t = (seg_sizes[s] + tile_elems - 1) / tile_elems;
+    hp.seg_tile0[s + 1] = hp.seg_tile0[s] + (uint32_t)t;
+    hp.seg_start[s + 1] = hp.seg_start[s] + seg_sizes[s];
+    max_tiles = std::max(max_tiles, t);
+  }
+  int ct = (int)std::ceil(std::sqrt((double)max_tiles));
+  ct = std::max(8, std::min(ct, 2048));
+  for (int s = 0; s < S; s++) {
+    uint32_t t = hp.seg_tile0[s + 1] - hp.seg_tile0[s];
+    hp.seg_chunk0[s + 1] = hp.seg_chunk0[s] + (t + ct - 1) / ct;
+  }
+  hp.lp.bins = bins; hp.lp.n_segments = S; hp.lp.chunk_tiles = ct;
+  hp.lp.n_tiles = hp.seg_tile0[S]; hp.lp.n_chunks = hp.seg_chunk0[S]; hp.lp.tile_elems = tile_elems;
+}
+
+// copy the plan arrays to the device (ctx->plan) and patch the pointers
+int upload_plan(apgk_ctx* c, HostPlan& hp) {
+  const size_t S1 = hp.seg_tile0.size();
+  const size_t bytes = S1 * (4 + 4 + 8) + 64;
+  CU(c->plan.ensure(bytes));
+  unsigned char* d = c->plan.as<unsigned char>();
+  CU(cudaMemcpyAsync(d, hp.seg_start.data(), S1 * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d + S1 * 8, hp.seg_tile0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d + S1 * 12, hp.seg_chunk0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // the host vectors may die before the copy otherwise
+  hp.lp.seg_start = (const uint64_t*)d;
+  hp.lp.seg_tile0 = (const uint32_t*)(d + S1 * 8);
+  hp.lp.seg_chunk0 = (const uint32_t*)(d + S1 * 12);
+  return APGK_OK;
+}
+
+// column scan: cnt16 -> base32 (+ segtot, bstart32, optional absolute bucket offsets)
+int column_scan(apgk_ctx* c, const HostPlan& hp, int fold, unsigned long long* bofs_out) {
+  const LevelPlan& lp = hp.lp;
+  if (lp.n_chunks == 0) return APGK_OK;
+  CU(c->chunksum.ensure((size_t)lp.n_chunks * lp.bins * 4));
+  CU(c->segtot.ensure((size_t)lp.n_segments * lp.bins * 8));
+  CU(c->bstart32.ensure((size_t)lp.n_segments * lp.bins * 4));
+  CU(c->base32.ensure((size_t)lp.n_tiles * lp.bins * 4));
+  k_colsum<COL_NT><<<lp.n_chunks, COL_NT, 0, c->stream>>>(lp, c->cnt16.as<uint16_t>(), c->chunksum.as<uint32_t>());
+  LAUNCHED();
+  k_segscan<COL_NT><<<lp.n_segments, COL_NT, 0, c->stream>>>(lp, c->chunksum.as<uint32_t>(),
+                                                            c->segtot.as<unsigned long long>(),
+                                                            c->bstart32.as<uint32_t>(), bofs_out);
+  LAUNCHED();
+  k_colapply<COL_NT><<<lp.n_chunks, COL_NT, 0, c->stream>>>(lp, c->cnt16.as<uint16_t>(), c->chunksum.as<uint32_t>(),
+                                                           c->bstart32.as<uint32_t>(), fold, c->base32.as<uint32_t>());
+  LAUNCHED();
+  return APGK_OK;
+}
+
+template <typename K>
+int set_smem(apgk_ctx* c, K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return APGK_OK;
+}
+
+ReadStore read_store(const apgk_ctx* c) {
+  ReadStore rs;
+  rs.bases32 = c->bases.as<uint32_t>();
+  rs.starts32 = c->starts.as<uint32_t>();
+  rs.total_bases = c->total_bases;
+  rs.K = c->cfg.K;
+  return rs;
+}
+
+int choose_prefix_bits(const apgk_ctx* c, uint64_t upper, int local_max) {
+  if (c->cfg.prefix_bits > 0) return std::max(2, std::min(24, (int)c->cfg.prefix_bits));
+  const char* env = getenv("APGK_PREFIX_BITS");
+  if (env && atoi(env) > 0) return std::max(2, std::min(24, atoi(env)));
+  double target = local_max / 3.0;
+  int P = 2;
+  while (P < 24 && (double)upper / (double)(1ull << P) > target) P++;
+  return P;
+}
+
+// geometry for this run
+void make_geom(apgk_ctx* c, int P) {
+  KeyGeom& g = c->geom;
+  g.K = c->cfg.K; g.W = c->W;
+  g.TB = std::max(2 * g.K, P);
+  g.pad = g.TB - 2 * g.K;
+  g.D0 = (P + 1) / 2; g.D1 = P - g.D0;
+  g.REM = g.TB - P;
+  g.topbits = 2 * g.K - 64 * (g.W - 1);
+}
+
+int ensure_store(apgk_ctx* c, uint64_t bases_needed) {
+  // bases: 2 bits each + 64 bytes of zero padding; starts: 1 bit each + padding.  Grow by copy.
+  const size_t bbytes = ((bases_needed + 31) / 32) * 8 + 256;
+  const size_t sbytes = ((bases_needed + 31) / 32) * 4 + 256;
+  if (bbytes > c->bases.cap) {
+    DevBuf nb, ns;
+    size_t grow = std::max(bbytes, c->bases.cap * 2);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(nb.ensure(grow, true));
+    CU(ns.ensure(grow / 2 + 256, true));
+    if (c->total_bases) {
+      CU(cudaMemcpyAsync(nb.p, c->bases.p, ((c->total_bases + 31) / 32) * 8 + 8, cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaMemcpyAsync(ns.p, c->starts.p, ((c->total_bases + 31) / 32) * 4 + 8, cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    c->bases.release(); c->starts.release();
+    c->bases = nb; c->starts = ns;
+  }
+  (void)sbytes;
+  return APGK_OK;
+}
+
+int append_bases(apgk_ctx* c, const uint8_t* packed, uint64_t first_base, uint64_t n_bases) {
+  if (!n_bases) return APGK_OK;
+  int rc = ensure_store(c, c->total_bases + n_bases);
+  if (rc) return rc;
+  const uint64_t dst_bit0 = 2 * c->total_bases, src_bit0 = 2 * first_base;
+  if ((dst_bit0 & 7) == 0 && (src_bit0 & 7) == 0) {
+    // byte aligned on both sides: copy straight into the store
+    const size_t nbytes = (size_t)((2 * n_bases + 7) / 8);
+    CU(cudaMemcpyAsync(c->bases.as<uint8_t>() + (dst_bit0 >> 3), packed + (src_bit0 >> 3), nbytes,
+                       cudaMemcpyHostToDevice, c->stream));
+    // bits of the last byte beyond n_bases must stay zero for later appends and for the window loads
+    if ((2 * n_bases) & 7) {
+      // clear the tail: re-write the final partial byte masked (tiny synchronous fix-up)
+      uint8_t last = packed[(src_bit0 >> 3) + nbytes - 1] & (uint8_t)((1u << ((2 * n_bases) & 7)) - 1u);
+      CU(cudaMemcpyAsync(c->bases.as<uint8_t>() + (dst_bit0 >> 3) + nbytes - 1, &last, 1, cudaMemcpyHostToDevice,
+                         c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+  } else {
+    const uint64_t sb_byte = src_bit0 >> 3;
+    const uint64_t sb_al = sb_byte & ~7ull;  // keep 8-byte alignment of the staged words
+    const size_t nbytes = (size_t)(((src_bit0 + 2 * n_bases + 7) >> 3) - sb_al);
+    CU(c->staging.ensure(nbytes + 32));
+    CU(cudaMemsetAsync((uint8_t*)c->staging.p + (nbytes & ~(size_t)7), 0, 24, c->stream));
+    CU(cudaMemcpyAsync(c->staging.p, packed + sb_al, nbytes, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t nbits = 2 * n_bases;
+    const uint64_t nwords = ((dst_bit0 + nbits + 63) >> 6) - (dst_bit0 >> 6);
+    k_append_bits<<<(unsigned)((nwords + 255) / 256), 256, 0, c->stream>>>(
+        c->staging.as<uint64_t>(), src_bit0 - sb_al * 8, c->bases.as<uint64_t>(), dst_bit0, nbits);
+    LAUNCHED();
+  }
+  return APGK_OK;
+}
+
+void invalidate_results(apgk_ctx* c) {
+  c->finished = false; c->have_table = false; c->spec_loaded = false;
+  c->n_instances = c->n_distinct = 0;
+  c->owner_ranks = 0;
+}
+
+// ---------------------------------------------------------------- the pipeline
+template <int W, typename ElemB>
+int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys);
+
+template <int W>
+int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
+  invalidate_results(c);
+  for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
+  const uint64_t upper = dev_keys ? n_keys : c->total_bases;
+  // decide element type of the level-1 buffer first (it fixes LOCAL_MAX, which fixes P)
+  int P = choose_prefix_bits(c, upper, LM_U32);
+  make_geom(c, P);
+  const bool u32 = (W == 1 && c->geom.REM <= 32);
+  if (!u32) {
+    P = choose_prefix_bits(c, upper, Geo<W>::LM_KEY);
+    make_geom(c, P);
+  }
+  stage_begin(c, ST_TOTAL);
+  int rc;
+  if constexpr (W == 1) {
+    if (c->geom.REM <= 32) rc = run_levels<W, uint32_t>(c, dev_keys, n_keys);
+    else rc = run_levels<W, Key<W>>(c, dev_keys, n_keys);
+  } else {
+    rc = run_levels<W, Key<W>>(c, dev_keys, n_keys);
+  }
+  if (rc) return rc;
+  stage_end(c, ST_TOTAL);
+  CU(cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < APGK_N_STAGES; s++)
+    if (c->ev_used[s]) cudaEventElapsedTime(&c->stage_ms[s], c->ev[s][0], c->ev[s][1]);
+  c->finished = true;
+  return APGK_OK;
+}
+
+template <typename ElemB, int W>
+struct ScatterSel {  // level-1 scatter kernel: Key<W> in, ElemB out
+  static auto kernel() { return k_scatter_keys<Key<W>, ElemB, Geo<W>::NT1>; }
+};
+
+template <int W, typename ElemB>
+int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
+  const KeyGeom g = c->geom;
+  const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
+  const int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : Geo<W>::LM_KEY;
+  c->elem_bytes = sizeof(ElemB);
+  c->nb1 = (uint32_t)bins0 * (uint32_t)bins1;
+  CU(c->spec_dense.ensure((size_t)SPEC_DENSE * 8));
+  CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
+
+  // ================= level 0
+  DigitSpec ds0{DIGIT_BITS, g.TB - g.D0, g.D0, g.pad, 0, 0u, (uint32_t)bins0};
+  HostPlan hp0;
+  const uint32_t tile0 = dev_keys ? Geo<W>::TILE1 : (uint32_t)Geo<W>::NT0 * POS_PER_THREAD;
+  {
+    std::vector<uint64_t> one{dev_keys ? n_keys : c->total_bases};
+    build_plan(hp0, one, tile0, bins0);
+  }
+  if (hp0.lp.n_tiles == 0) {  // nothing to count
+    c->n_instances = 0; c->n_distinct = 0; c->n_big = 0;
+    CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
+    CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
+    c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
+    return APGK_OK;
+  }
+  { int rc = upload_plan(c, hp0); if (rc) return rc; }
+  CU(c->cnt16.ensure((size_t)hp0.lp.n_tiles * bins0 * 2));
+  stage_begin(c, ST_HIST0);
+  if (dev_keys) {
+    k_hist_keys<Key<W>, Geo<W>::NT1><<<hp0.lp.n_tiles, Geo<W>::NT1, bins0 * 4, c->stream>>>(dev_keys, hp0.lp, ds0,
+                                                                                             c->cnt16.as<uint16_t>());
+  } else {
+    k_hist_reads<W, Geo<W>::NT0><<<hp0.lp.n_tiles, Geo<W>::NT0, bins0 * 4, c->stream>>>(read_store(c), ds0, bins0,
+                                                                                         c->cnt16.as<uint16_t>());
+  }
+  LAUNCHED();
+  stage_end(c, ST_HIST0);
+  stage_begin(c, ST_SCAN0);
+  { int rc = column_scan(c, hp0, 0, nullptr); if (rc) return rc; }
+  stage_end(c, ST_SCAN0);
+  std::vector<uint64_t> tot0(bins0), bstart0(bins0 + 1, 0);
+  CU(cudaMemcpyAsync(tot0.data(), c->segtot.p, (size_t)bins0 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int d = 0; d < bins0; d++) {
+    if (tot0[d] >= (1ull << 32)) FAIL(APGK_E_RANGE, "level-0 bucket %d holds %llu k-mers (>= 2^32)", d, (unsigned long long)tot0[d]);
+    bstart0[d + 1] = bstart0[d] + tot0[d];
+  }
+  const uint64_t N = bstart0[bins0];
+  c->n_instances = N;
+  if (N == 0) {
+    c->n_distinct = 0; c->n_big = 0;
+    CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
+    CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
+    c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
+    return APGK_OK;
+  }
+  CU(c->bstart64.ensure(((size_t)bins0 + 1) * 8));
+  CU(cudaMemcpyAsync(c->bstart64.p, bstart0.data(), ((size_t)bins0 + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c->A.ensure(std::max<size_t>(N, 1) * sizeof(Key<W>)));
+  stage_begin(c, ST_SCATTER0);
+  if (dev_keys) {
+    auto kern = k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1>;
+    const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
+    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+    kern<<<hp0.lp.n_tiles, Geo<W>::NT1, sm, c->stream>>>(dev_keys, hp0.lp, ds0, c->cnt16.as<uint16_t>(),
+                                                         c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(), 0, 0,
+                                                         c->A.as<Key<W>>());
+  } else {
+    auto kern = k_scatter_reads<W, Geo<W>::NT0>;
+    const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
+    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+    kern<<<hp0.lp.n_tiles, Geo<W>::NT0, sm, c->stream>>>(read_store(c), ds0, bins0, c->cnt16.as<uint16_t>(),
+                                                         c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(),
+                                                         c->A.as<Key<W>>());
+  }
+  LAUNCHED();
+  stage_end(c, ST_SCATTER0);
+
+  // ================= level 1
+  DigitSpec ds1{DIGIT_BITS, g.TB - g.D0 - g.D1, g.D1, g.pad, 0, 0u, (uint32_t)bins1};
+  HostPlan hp1;
+  build_plan(hp1, tot0, Geo<W>::TILE1, bins1);
+  { int rc = upload_plan(c, hp1); if (rc) return rc; }
+  CU(c->bofs.ensure(((size_t)c->nb1 + 1) * 8));
+  CU(c->stats.ensure(64));
+  CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
+  if (hp1.lp.n_tiles) {
+    CU(c->cnt16.ensure((size_t)hp1.lp.n_tiles * bins1 * 2));
+    stage_begin(c, ST_HIST1);
+    k_hist_keys<Key<W>, Geo<W>::NT1><<<hp1.lp.n_tiles, Geo<W>::NT1, bins1 * 4, c->stream>>>(
+        c->A.as<Key<W>>(), hp1.lp, ds1, c->cnt16.as<uint16_t>());
+    LAUNCHED();
+    stage_end(c, ST_HIST1);
+  }
+  stage_begin(c, ST_SCAN1);
+  if (hp1.lp.n_chunks == 0) {
+    CU(c->segtot.ensure((size_t)c->nb1 * 8));
+    CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
+  } else {
+    // segments with no tiles still need their bucket rows written: k_segscan runs one CTA per segment
+    int rc = column_scan(c, hp1, 1, c->bofs.as<unsigned long long>());
+    if (rc) return rc;
+  }
+  // bucket classification (oversize list)
+  CU(c->big_list.ensure(((size_t)N / local_max + 16) * 4));
+  const uint32_t big_cap = (uint32_t)(N / local_max + 16);
+  k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
+                                                         (uint32_t)local_max, c->big_list.as<uint32_t>(), big_cap,
+                                                         c->stats.as<unsigned long long>());
+  LAUNCHED();
+  stage_end(c, ST_SCAN1);
+  unsigned long long stats[2] = {0, 0};
+  CU(cudaMemcpyAsync(stats, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->n_big = stats[0];
+  if (getenv("APGK_DEBUG")) {
+    std::vector<unsigned long long> bs(c->nb1), bo(c->nb1);
+    cudaMemcpyAsync(bs.data(), c->segtot.p, (size_t)c->nb1 * 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(bo.data(), c->bofs.p, (size_t)c->nb1 * 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    unsigned long long mx = 0, sum = 0; uint32_t am = 0, bad_ofs = 0;
+    unsigned long long run = 0;
+    for (uint32_t b = 0; b < c->nb1; b++) {
+      if (bs[b] > mx) { mx = bs[b]; am = b; }
+      if (bo[b] != run) bad_ofs++;
+      run += bs[b]; sum += bs[b];
+    }
+    uint64_t mx0 = 0; int am0 = 0;
+    for (int d = 0; d < bins0; d++) if (tot0[d] > mx0) { mx0 = tot0[d]; am0 = d; }
+    fprintf(stderr, "[apgk] K=%d W=%d P=%d+%d REM=%d N=%llu tiles0=%u tiles1=%u chunks1=%u ct1=%d | L0 max %llu @%d | L1 max %llu @%u sum %llu bad_ofs %u | n_big %llu big_total %llu\n",
+            g.K, W, g.D0, g.D1, g.REM, (unsigned long long)N, hp0.lp.n_tiles, hp1.lp.n_tiles, hp1.lp.n_chunks, hp1.lp.chunk_tiles,
+            (unsigned long long)mx0, am0, mx, am, sum, bad_ofs, stats[0], stats[1]);
+  }
+  CU(c->B.ensure(std::max<size_t>(N, 1) * sizeof(ElemB) + 16));
+  if (hp1.lp.n_tiles) {
+    stage_begin(c, ST_SCATTER1);
+    auto kern = ScatterSel<ElemB, W>::kernel();
+    const size_t sm = scatter_smem_bytes<Key<W>>(Geo<W>::TILE1, bins1);
+    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+    kern<<<hp1.lp.n_tiles, Geo<W>::NT1, sm, c->stream>>>(c->A.as<Key<W>>(), hp1.lp, ds1, c->cnt16.as<uint16_t>(),
+                                                         c->base32.as<uint32_t>(), nullptr, g.pad, g.REM,
+                                                         c->B.as<ElemB>());
+    LAUNCHED();
+    stage_end(c, ST_SCATTER1);
+  }
+
+  // ================= local sort + count
+  const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
+  CU(c->nd.ensure(((size_t)c->nb1 + 1) * 4));
+  CU(c->spec_ovf.ensure(((size_t)N / SPEC_DENSE + 16) * 8));
+  CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
+  EmitCtx<W> ec;
+  ec.want_table = want_table; ec.rem_bits = g.REM; ec.pad = g.pad;
+  ec.tmp_keys = c->A.as<Key<W>>();
+  ec.spec_dense = c->spec_dense.as<unsigned long long>();
+  ec.spec_ovf = c->spec_ovf.as<unsigned long long>();
+  ec.spec_ovf_cap = (uint32_t)(N / SPEC_DENSE + 8);
+  BucketTable bt;
+  bt.bofs = c->bofs.as<unsigned long long>();
+  bt.bsize = c->segtot.as<unsigned long long>();
+  bt.nb = c->nb1; bt.local_max = (uint32_t)local_max;
+  {
+    auto kern = k_local<ElemB, W>;
+    const size_t sm = LocalSmem<ElemB>::bytes(local_max);
+    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
+    const uint32_t grid = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ, 1)));
+    stage_begin(c, ST_LOCAL);
+    kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>());
+    LAUNCHED();
+    stage_end(c, ST_LOCAL);
+  }
+  if (c->n_big) {
+    if (c->n_big > big_cap) FAIL(APGK_E_RANGE, "internal: oversize bucket list overflow");
+    auto kern = k_big<ElemB, W>;
+    const size_t sm = LocalSmem<ElemB>::bytes(local_max);
+    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(c->n_big, (uint64_t)c->n_sm * std::max(occ, 1));
+    CU(c->scratch.ensure((size_t)stats[1] * sizeof(ElemB) + 16));
+    CU(c->stacks.ensure((size_t)grid * BIG_STACK * 16));
+    CU(c->misc.ensure(64));
+    CU(cudaMemsetAsync(c->misc.p, 0, 64, c->stream));
+    BigParams bp;
+    bp.big_list = c->big_list.as<uint32_t>();
+    bp.n_big = (const uint32_t*)c->stats.p;  // low word of stats[0]
+    bp.ticket = c->misc.as<unsigned int>();
+    bp.scratch_cursor = (unsigned long long*)(c->misc.as<unsigned char>() + 8);
+    bp.scratch = c->scratch.p;
+    bp.stacks = c->stacks.as<unsigned long long>();
+    stage_begin(c, ST_BIG);
+    kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(), bp);
+    LAUNCHED();
+    stage_end(c, ST_BIG);
+  }
+
+  // ================= table
+  stage_begin(c, ST_TABLE);
+  {
+    const uint64_t n = c->nb1;
+    const uint32_t nblocks = (uint32_t)((n + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    CU(c->blocksum.ensure(((size_t)nblocks + 1) * 8));
+    CU(c->out_off.ensure(((size_t)n + 1) * 8));
+    k_scan_blocksum<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>());
+    LAUNCHED();
+    k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks);
+    LAUNCHED();
+    k_scan_apply<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>(),
+                                                     c->out_off.as<unsigned long long>());
+    LAUNCHED();
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, c->blocksum.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_distinct = total;
+    if (want_table) {
+      CU(c->out_keys.ensure(std::max<size_t>(total, 1) * sizeof(Key<W>)));
+      CU(c->out_cnt.ensure(std::max<size_t>(total, 1) * 4));
+      k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(c->A.as<Key<W>>(), c->B.as<unsigned char>(), (uint32_t)sizeof(ElemB),
+                                                       c->bofs.as<unsigned long long>(),
+                                                       c->out_off.as<unsigned long long>(), c->nb1,
+                                                       c->out_keys.as<Key<W>>(), c->out_cnt.as<uint32_t>());
+      LAUNCHED();
+      c->have_table = true;
+    }
+  }
+  stage_end(c, ST_TABLE);
+  return APGK_OK;
+}
+
+int load_spectrum(apgk_ctx* c) {
+  if (c->spec_loaded) return APGK_OK;
+  if (!c->finished) FAIL(APGK_E_STATE, "apgk_finish has not run");
+  std::vector<uint64_t> dense(SPEC_DENSE, 0);
+  c->sparse_f.clear(); c->sparse_n.clear(); c->spec_host.clear();
+  std::vector<uint64_t> ovf;
+  if (c->n_instances) {
+    CU(cudaMemcpyAsync(dense.data(), c->spec_dense.p, (size_t)SPEC_DENSE * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->spec_ovf.p) {
+      unsigned long long n_ovf = 0;
+      CU(cudaMemcpyAsync(&n_ovf, c->spec_ovf.p, 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      if (n_ovf) {
+        ovf.resize(n_ovf);
+        CU(cudaMemcpyAsync(ovf.data(), (unsigned long long*)c->spec_ovf.p + 1, n_ovf * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        std::sort(ovf.begin(), ovf.end());
+      }
+    }
+  }
+  for (uint64_t f = 1; f < SPEC_DENSE; f++)
+    if (dense[f]) { c->sparse_f.push_back(f); c->sparse_n.push_back(dense[f]); }
+  for (size_t i = 0; i < ovf.size();) {
+    size_t j = i;
+    while (j < ovf.size() && ovf[j] == ovf[i]) j++;
+    c->sparse_f.push_back(ovf[i]); c->sparse_n.push_back(j - i);
+    i = j;
+  }
+  c->spec_loaded = true;
+  return APGK_OK;
+}
+
+template <int W>
+FreqTable<W> freq_table(const apgk_ctx* c) {
+  FreqTable<W> t;
+  t.keys = c->out_keys.as<Key<W>>();
+  t.counts = c->out_cnt.as<uint32_t>();
+  t.index = c->out_off.as<unsigned long long>();
+  t.nb = c->nb1;
+  t.prefix_pos = c->geom.REM; t.prefix_len = c->geom.D0 + c->geom.D1; t.pad = c->geom.pad; t.D1 = c->geom.D1;
+  return t;
+}
+
+template <int W>
+int lookup_impl(apgk_ctx* c, const uint64_t* kmers, uint64_t n, int canon, uint32_t* out) {
+  if (!n) return APGK_OK;
+  DevBuf q, r;
+  CU(q.ensure(n * sizeof(Key<W>)));
+  CU(r.ensure(n * 4));
+  CU(cudaMemcpyAsync(q.p, kmers, n * sizeof(Key<W>), cudaMemcpyHostToDevice, c->stream));
+  k_lookup<W><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(freq_table<W>(c), q.as<Key<W>>(), n, c->cfg.K, canon,
+                                                                 r.as<uint32_t>());
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, r.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  q.release(); r.release();
+  CU(e);
+  return APGK_OK;
+}
+
+template <int W>
+int read_freqs_impl(apgk_ctx* c, uint64_t first, uint64_t n, uint32_t* out) {
+  if (!n) return APGK_OK;
+  DevBuf r;
+  CU(r.ensure(n * 4));
+  constexpr int NT = 128;
+  const uint64_t span = (first + n) - (first & ~15ull);
+  const uint64_t threads = (span + POS_PER_THREAD - 1) / POS_PER_THREAD;
+  k_read_freqs<W, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(read_store(c), freq_table<W>(c), first, n,
+                                                                               r.as<uint32_t>());
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, r.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  r.release();
+  CU(e);
+  return APGK_OK;
+}
+
+// ---------------------------------------------------------------- owner partition (multi-GPU shuffle, sender side)
+template <int W>
+int owner_plan_impl(apgk_ctx* c, uint32_t n_ranks, uint64_t* counts_out) {
+  DigitSpec ds{DIGIT_OWNER, 0, 0, 0, n_ranks, 0u, n_ranks};
+  const uint32_t tile0 = (uint32_t)Geo<W>::NT0 * POS_PER_THREAD;
+  HostPlan hp;
+  std::vector<uint64_t> one{c->total_bases};
+  build_plan(hp, one, tile0, (int)n_ranks);
+  c->owner_counts.assign(n_ranks, 0);
+  c->owner_ranks = n_ranks; c->owner_tiles = hp.lp.n_tiles;
+  if (hp.lp.n_tiles) {
+    { int rc = upload_plan(c, hp); if (rc) return rc; }
+    CU(c->cnt16.ensure((size_t)hp.lp.n_tiles * n_ranks * 2));
+    stage_begin(c, ST_OWNER);
+    k_hist_reads<W, Geo<W>::NT0><<<hp.lp.n_tiles, Geo<W>::NT0, n_ranks * 4, c->stream>>>(read_store(c), ds, (int)n_ranks,
+                                                                                          c->cnt16.as<uint16_t>());
+    LAUNCHED();
+    { int rc = column_scan(c, hp, 0, nullptr); if (rc) return rc; }
+    CU(cudaMemcpyAsync(c->owner_counts.data(), c->segtot.p, (size_t)n_ranks * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  for (uint32_t r = 0; r < n_ranks; r++) {
+    if (c->owner_counts[r] >= (1ull << 32)) FAIL(APGK_E_RANGE, "more than 2^32 k-mers for one owner in one call");
+    counts_out[r] = c->owner_counts[r];
+  }
+  return APGK_OK;
+}
+
+template <int W>
+int owner_scatter_impl(apgk_ctx* c, uint64_t* d_out) {
+  const uint32_t n_ranks = c->owner_ranks;
+  if (!c->owner_tiles) return APGK_OK;
+  DigitSpec ds{DIGIT_OWNER, 0, 0, 0, n_ranks, 0u, n_ranks};
+  std::vector<uint64_t> bstart(n_ranks + 1, 0);
+  for (uint32_t r = 0; r < n_ranks; r++) bstart[r + 1] = bstart[r] + c->owner_counts[r];
+  CU(c->bstart64.ensure(((size_t)n_ranks + 1) * 8));
+  CU(cudaMemcpyAsync(c->bstart64.p, bstart.data(), ((size_t)n_ranks + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  auto kern = k_scatter_reads<W, Geo<W>::NT0>;
+  const size_t sm = scatter_smem_bytes<Key<W>>((uint32_t)Geo<W>::NT0 * POS_PER_THREAD, (int)n_ranks);
+  { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+  kern<<<c->owner_tiles, Geo<W>::NT0, sm, c->stream>>>(read_store(c), ds, (int)n_ranks, c->cnt16.as<uint16_t>(),
+                                                       c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(),
+                                                       (Key<W>*)d_out);
+  LAUNCHED();
+  stage_end(c, ST_OWNER);
+  CU(cudaStreamSynchronize(c->stream));
+  return APGK_OK;
+}
+
+}  // namespace
+
+namespace {
+template <int W>
+static void host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, uint64_t* kmers_out,
+                         uint8_t* valid_out) {
+  const uint64_t b0 = off[0], total = off[n_reads] - b0;
+  // build the store exactly as the device sees it: bases from position 0, zero padded
+  std::vector<uint32_t> bases((total + 15) / 16 + 2 * W + 8, 0), starts((total + 31) / 32 + 16, 0);
+  for (uint64_t q = 0; q < total; q++) {
+    const uint64_t s = b0 + q;
+    const uint32_t b = (packed[s >> 2] >> ((s & 3) * 2)) & 3u;
+    bases[q >> 4] |= b << ((q & 15) * 2);
+  }
+  for (uint64_t r = 0; r < n_reads; r++) { const uint64_t q = off[r] - b0; starts[q >> 5] |= 1u << (q & 31); }
+  for (uint64_t p = 0; p < total; p += 16) {
+    const uint32_t valid = window_valid_mask16(starts.data(), p, K, total);
+    Window16<W> win;
+    load_window16<W>(bases.data(), p, K, win);
+    extract16<W>(win, K, [&](int j, const Key<W>& c, bool) {
+      if (p + j < total) {
+        valid_out[p + j] = (valid >> j) & 1u;
+        for (int i = 0; i < W; i++) kmers_out[(p + j) * W + i] = c.w[i];
+      }
+    });
+  }
+}
+
+}  // namespace
+
+// ================================================================= C ABI
+extern "C" {
+
+int apgk_words_per_kmer(int K) { return words_for(K); }
+
+int apgk_create(const apgk_config* cfg, apgk_ctx** out) {
+  if (!cfg || !out) return APGK_E_ARG;
+  *out = nullptr;
+  if (cfg->K < 1 || cfg->K > APGK_MAX_K) return APGK_E_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return APGK_E_CUDA;  // no CPU fallback
+  if (cfg->device < 0 || cfg->device >= ndev) return APGK_E_ARG;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return APGK_E_CUDA;
+  apgk_ctx* c = new apgk_ctx();
+  c->cfg = *cfg;
+  c->cfg.flags |= APGK_WANT_SPECTRUM;
+  c->W = words_for(cfg->K);
+  c->device = cfg->device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete c; return APGK_E_CUDA; }
+  c->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return APGK_E_CUDA; }
+  for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventCreate(&c->ev[s][0]); cudaEventCreate(&c->ev[s][1]); }
+  if (cfg->reserve_bases && ensure_store(c, cfg->reserve_bases) != APGK_OK) {
+    apgk_destroy(c);
+    return APGK_E_NOMEM;
+  }
+  *out = c;
+  return APGK_OK;
+}
+
+void apgk_destroy(apgk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->cnt16, &c->base32, &c->chunksum,
+                   &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
+                   &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc,
+                   &c->out_keys, &c->out_cnt};
+  for (DevBuf* b : all) b->release();
+  for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* apgk_last_error(const apgk_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int apgk_reset(apgk_ctx* c) {
+  if (!c) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  if (c->total_bases) {
+    CU(cudaMemsetAsync(c->bases.p, 0, std::min(c->bases.cap, (size_t)((c->total_bases + 31) / 32) * 8 + 256), c->stream));
+    CU(cudaMemsetAsync(c->starts.p, 0, std::min(c->starts.cap, (size_t)((c->total_bases + 31) / 32) * 4 + 256), c->stream));
+  }
+  c->total_bases = 0; c->n_reads = 0;
+  invalidate_results(c);
+  return APGK_OK;
+}
+
+int apgk_add_reads(apgk_ctx* c, const uint8_t* packed, const uint64_t* off, uint64_t n_reads) {
+  if (!c || (!packed && n_reads) || (!off && n_reads)) return APGK_E_ARG;
+  if (!n_reads) return APGK_OK;
+  CU(cudaSetDevice(c->device));
+  for (uint64_t r = 0; r < n_reads; r++)
+    if (off[r + 1] < off[r]) FAIL(APGK_E_ARG, "read offsets must be non-decreasing (read %llu)", (unsigned long long)r);
+  const uint64_t nb = off[n_reads] - off[0];
+  const uint64_t dst0 = c->total_bases;
+  int rc = append_bases(c, packed, off[0], nb);
+  if (rc) return rc;
+  if (nb) {
+    CU(c->off_dev.ensure(n_reads * 8));
+    CU(cudaMemcpyAsync(c->off_dev.p, off, n_reads * 8, cudaMemcpyHostToDevice, c->stream));
+    k_mark_starts<<<(unsigned)((n_reads + 255) / 256), 256, 0, c->stream>>>(c->off_dev.as<uint64_t>(), n_reads, off[0],
+                                                                           dst0, c->starts.as<uint32_t>());
+    LAUNCHED();
+  }
+  CU(cudaStreamSynchronize(c->stream));  // inputs are only borrowed for the duration of the call
+  c->total_bases += nb; c->n_reads += n_reads;
+  invalidate_results(c);
+  return APGK_OK;
+}
+
+int apgk_add_reads_uniform(apgk_ctx* c, const uint8_t* packed, uint64_t first_base, uint64_t n_reads, uint32_t read_len) {
+  if (!c || (!packed && n_reads)) return APGK_E_ARG;
+  if (!n_reads || !read_len) return APGK_OK;
+  CU(cudaSetDevice(c->device));
+  const uint64_t nb = n_reads * (uint64_t)read_len;
+  const uint64_t dst0 = c->total_bases;
+  int rc = append_bases(c, packed, first_base, nb);
+  if (rc) return rc;
+  k_mark_starts_uniform<<<(unsigned)((n_reads + 255) / 256), 256, 0, c->stream>>>(n_reads, read_len, dst0,
+                                                                                 c->starts.as<uint32_t>());
+  LAUNCHED();
+  CU(cudaStreamSynchronize(c->stream));
+  c->total_bases += nb; c->n_reads += n_reads;
+  invalidate_results(c);
+  return APGK_OK;
+}
+
+int apgk_synth_reads(apgk_ctx* c, const apgk_synth_params* p, uint64_t r0, uint64_t n_reads) {
+  if (!c || !p) return APGK_E_ARG;
+  if (!n_reads) return APGK_OK;
+  if (p->read_len == 0 || p->genome_len < p->read_len) FAIL(APGK_E_ARG, "genome shorter than a read");
+  if (c->total_bases % 16) FAIL(APGK_E_STATE, "apgk_synth_reads needs the store to hold a multiple of 16 bases");
+  CU(cudaSetDevice(c->device));
+  const uint64_t nb = n_reads * (uint64_t)p->read_len;
+  int rc = ensure_store(c, c->total_bases + nb);
+  if (rc) return rc;
+  SynthParams sp{p->genome_len, p->seed_g, p->seed_p, p->seed_q, p->seed_r, p->seed_e, p->read_len, p->err_per_200};
+  const uint64_t nwords = (nb + 15) / 16;
+  k_synth<<<(unsigned)((nwords + 255) / 256), 256, 0, c->stream>>>(sp, r0, n_reads, c->total_bases, c->bases.as<uint32_t>());
+  LAUNCHED();
+  k_mark_starts_uniform<<<(unsigned)((n_reads + 255) / 256), 256, 0, c->stream>>>(n_reads, p->read_len, c->total_bases,
+                                                                                 c->starts.as<uint32_t>());
+  LAUNCHED();
+  CU(cudaStreamSynchronize(c->stream));
+  c->total_bases += nb; c->n_reads += n_reads;
+  invalidate_results(c);
+  return APGK_OK;
+}
+
+int apgk_export_reads(apgk_ctx* c, uint8_t* out) {
+  if (!c || !out) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  if (c->total_bases) {
+    CU(cudaMemcpyAsync(out, c->bases.p, ((c->total_bases + 31) / 32) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return APGK_OK;
+}
+
+int apgk_read_store_info(const apgk_ctx* c, uint64_t* total_bases, uint64_t* n_reads) {
+  if (!c) return APGK_E_ARG;
+  if (total_bases) *total_bases = c->total_bases;
+  if (n_reads) *n_reads = c->n_reads;
+  return APGK_OK;
+}
+
+int apgk_finish(apgk_ctx* c) {
+  if (!c) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return finish_impl<1>(c, nullptr, 0);
+    case 2: return finish_impl<2>(c, nullptr, 0);
+    case 3: return finish_impl<3>(c, nullptr, 0);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_finish_keys_device(apgk_ctx* c, const uint64_t* d_keys, uint64_t n) {
+  if (!c || (!d_keys && n)) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return finish_impl<1>(c, (const Key<1>*)d_keys, n);
+    case 2: return finish_impl<2>(c, (const Key<2>*)d_keys, n);
+    case 3: return finish_impl<3>(c, (const Key<3>*)d_keys, n);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_totals(const apgk_ctx* c, uint64_t* n_instances, uint64_t* n_distinct) {
+  if (!c) return APGK_E_ARG;
+  if (!c->finished) return APGK_E_STATE;
+  if (n_instances) *n_instances = c->n_instances;
+  if (n_distinct) *n_distinct = c->n_distinct;
+  return APGK_OK;
+}
+
+int apgk_spectrum_sparse(apgk_ctx* c, const uint64_t** freq, const uint64_t** n_kmers, uint64_t* n) {
+  if (!c) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  int rc = load_spectrum(c);
+  if (rc) return rc;
+  if (freq) *freq = c->sparse_f.data();
+  if (n_kmers) *n_kmers = c->sparse_n.data();
+  if (n) *n = c->sparse_f.size();
+  return APGK_OK;
+}
+
+int apgk_spectrum(apgk_ctx* c, const uint64_t** spec, uint64_t* len) {
+  if (!c || !spec || !len) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  int rc = load_spectrum(c);
+  if (rc) return rc;
+  if (c->spec_host.empty()) {
+    const uint64_t mx = c->sparse_f.empty() ? 0 : c->sparse_f.back();
+    if (mx + 1 > (1ull << 28)) FAIL(APGK_E_RANGE, "largest count %llu: use apgk_spectrum_sparse", (unsigned long long)mx);
+    c->spec_host.assign(mx + 1, 0);
+    for (size_t i = 0; i < c->sparse_f.size(); i++) c->spec_host[c->sparse_f[i]] = c->sparse_n[i];
+  }
+  *spec = c->spec_host.data();
+  *len = c->spec_host.size();
+  return APGK_OK;
+}
+
+int apgk_counts_device(apgk_ctx* c, const uint64_t** d_kmers, const uint32_t** d_counts, uint64_t* n_distinct) {
+  if (!c) return APGK_E_ARG;
+  if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
+  if (d_kmers) *d_kmers = c->out_keys.as<uint64_t>();
+  if (d_counts) *d_counts = c->out_cnt.as<uint32_t>();
+  if (n_distinct) *n_distinct = c->n_distinct;
+  return APGK_OK;
+}
+
+int apgk_counts_copy(apgk_ctx* c, uint64_t first, uint64_t n, uint64_t* kmers_out, uint32_t* counts_out) {
+  if (!c) return APGK_E_ARG;
+  if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
+  if (first + n > c->n_distinct) FAIL(APGK_E_ARG, "range beyond the table");
+  if (!n) return APGK_OK;
+  CU(cudaSetDevice(c->device));
+  const size_t kb = (size_t)c->W * 8;
+  if (kmers_out) CU(cudaMemcpyAsync(kmers_out, c->out_keys.as<unsigned char>() + first * kb, n * kb, cudaMemcpyDeviceToHost, c->stream));
+  if (counts_out) CU(cudaMemcpyAsync(counts_out, c->out_cnt.as<uint32_t>() + first, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return APGK_OK;
+}
+
+int apgk_lookup(apgk_ctx* c, const uint64_t* kmers, uint64_t n, int canonicalise, uint32_t* counts_out) {
+  if (!c || (!kmers && n) || (!counts_out && n)) return APGK_E_ARG;
+  if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return lookup_impl<1>(c, kmers, n, canonicalise, counts_out);
+    case 2: return lookup_impl<2>(c, kmers, n, canonicalise, counts_out);
+    case 3: return lookup_impl<3>(c, kmers, n, canonicalise, counts_out);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_read_freqs(apgk_ctx* c, uint64_t first_base, uint64_t n_bases, uint32_t* out) {
+  if (!c || (!out && n_bases)) return APGK_E_ARG;
+  if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
+  if (first_base + n_bases > c->total_bases) FAIL(APGK_E_ARG, "range beyond the read store");
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return read_freqs_impl<1>(c, first_base, n_bases, out);
+    case 2: return read_freqs_impl<2>(c, first_base, n_bases, out);
+    case 3: return read_freqs_impl<3>(c, first_base, n_bases, out);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_owner_plan(apgk_ctx* c, uint32_t n_ranks, uint64_t* counts_out) {
+  if (!c || !counts_out || n_ranks < 1 || n_ranks > 1024) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return owner_plan_impl<1>(c, n_ranks, counts_out);
+    case 2: return owner_plan_impl<2>(c, n_ranks, counts_out);
+    case 3: return owner_plan_impl<3>(c, n_ranks, counts_out);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_owner_scatter(apgk_ctx* c, uint64_t* d_keys_out) {
+  if (!c) return APGK_E_ARG;
+  if (!c->owner_ranks) FAIL(APGK_E_STATE, "apgk_owner_plan has not run");
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return owner_scatter_impl<1>(c, d_keys_out);
+    case 2: return owner_scatter_impl<2>(c, d_keys_out);
+    case 3: return owner_scatter_impl<3>(c, d_keys_out);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_owner_of(int K, const uint64_t* kmers, uint64_t n, uint32_t n_ranks, uint32_t* owner_out) {
+  if (K < 1 || K > APGK_MAX_K || !kmers || !owner_out || !n_ranks) return APGK_E_ARG;
+  const int W = words_for(K);
+  for (uint64_t i = 0; i < n; i++) {
+    if (W == 1) { Key<1> k; k.w[0] = kmers[i]; owner_out[i] = key_owner(k, n_ranks); }
+    else if (W == 2) { Key<2> k; k.w[0] = kmers[2 * i]; k.w[1] = kmers[2 * i + 1]; owner_out[i] = key_owner(k, n_ranks); }
+    else { Key<3> k; k.w[0] = kmers[3 * i]; k.w[1] = kmers[3 * i + 1]; k.w[2] = kmers[3 * i + 2]; owner_out[i] = key_owner(k, n_ranks); }
+  }
+  return APGK_OK;
+}
+
+int apgk_spectrum_device(apgk_ctx* c, uint64_t** d_spec, uint64_t* len) {
+  if (!c || !d_spec) return APGK_E_ARG;
+  if (!c->finished) FAIL(APGK_E_STATE, "apgk_finish has not run");
+  *d_spec = c->spec_dense.as<uint64_t>();
+  if (len) *len = SPEC_DENSE;
+  return APGK_OK;
+}
+
+int apgk_spectrum_reload(apgk_ctx* c) {
+  if (!c) return APGK_E_ARG;
+  c->spec_loaded = false;
+  c->spec_host.clear();
+  return APGK_OK;
+}
+
+int apgk_stage_ms(const apgk_ctx* c, float* ms_out) {
+  if (!c || !ms_out) return APGK_E_ARG;
+  for (int s = 0; s < APGK_N_STAGES; s++) ms_out[s] = c->stage_ms[s];
+  return APGK_OK;
+}
+const char* apgk_stage_name(int i) { return (i >= 0 && i < APGK_N_STAGES) ? kStageNames[i] : ""; }
+uint64_t apgk_kernel_launches(const apgk_ctx* c) { return c ? c->launches : 0; }
+void apgk_reset_counters(apgk_ctx* c) { if (c) c->launches = 0; }
+
+int apgk_geometry(const apgk_ctx* c, int32_t* out5) {
+  if (!c || !out5) return APGK_E_ARG;
+  out5[0] = c->geom.D0; out5[1] = c->geom.D1; out5[2] = c->geom.REM; out5[3] = (int32_t)c->elem_bytes;
+  out5[4] = (int32_t)std::min<uint64_t>(c->n_big, 0x7fffffff);
+  return APGK_OK;
+}
+
+int apgk_host_alloc(void** p, size_t bytes) {
+  if (!p) return APGK_E_ARG;
+  return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? APGK_OK : APGK_E_NOMEM;
+}
+int apgk_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? APGK_OK : APGK_E_CUDA; }
+
+// ---------------------------------------------------------------- host test hooks
+int apgk_debug_host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, uint64_t* kmers_out,
+                            uint8_t* valid_out) {
+  if (!packed || !off || K < 1 || K > APGK_MAX_K) return APGK_E_ARG;
+  if (!n_reads) return APGK_OK;
+  switch (words_for(K)) {
+    case 1: host_extract<1>(packed, off, n_reads, K, kmers_out, valid_out); break;
+    case 2: host_extract<2>(packed, off, n_reads, K, kmers_out, valid_out); break;
+    case 3: host_extract<3>(packed, off, n_reads, K, kmers_out, valid_out); break;
+  }
+  return APGK_OK;
+}
+
+int apgk_debug_host_canonical(int K, const uint64_t* kmers, uint64_t n, uint64_t* out) {
+  if (K < 1 || K > APGK_MAX_K) return APGK_E_ARG;
+  const int W = words_for(K);
+  for (uint64_t i = 0; i < n; i++) {
+    if (W == 1) { Key<1> k; k.w[0] = kmers[i]; k = key_canonical(k, K); out[i] = k.w[0]; }
+    else if (W == 2) { Key<2> k; memcpy(k.w, kmers + 2 * i, 16); k = key_canonical(k, K); memcpy(out + 2 * i, k.w, 16); }
+    else { Key<3> k; memcpy(k.w, kmers + 3 * i, 24); k = key_canonical(k, K); memcpy(out + 3 * i, k.w, 24); }
+  }
+  return APGK_OK;
+}
+
+int apgk_debug_host_synth(const apgk_synth_params* p, uint64_t r0, uint64_t n_reads, uint8_t* packed_out) {
+  if (!p || !packed_out) return APGK_E_ARG;
+  SynthParams sp{p->genome_len, p->seed_g, p->seed_p, p->seed_q, p->seed_r, p->seed_e, p->read_len, p->err_per_200};
+  const uint64_t nb = n_reads * (uint64_t)p->read_len;
+  uint32_t* w = (uint32_t*)packed_out;
+  for (uint64_t wi = 0; wi * 16 < nb; wi++) w[wi] = synth_word(sp, r0, wi * 16, nb);
+  return APGK_OK;
+}
+
+}  // extern "C"

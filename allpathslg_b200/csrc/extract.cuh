@@ -1,0 +1,126 @@
+// extract.cuh -- canonical k-mer extraction from the 2-bit packed base stream.
+//
+// Replaces the inner loop of the reference's k-mer builders (the per-base
+// "fw = fw<<2|b ; rc = rc>>2|(3-b)<<2(K-1) ; canonical = min(fw,rc)" roll that
+// SURVEY.md section 8(a) attributes to kmers/SortKmers, kmers/KmerParcels and
+// kmers/naif_kmer; no file:line exists -- the reference tree was empty).
+//
+// B200 formulation: the base stream is little-endian 2-bit (base q at bits
+// [2q,2q+2)).  For a window starting at base p the K bases read as a
+// little-endian integer ARE the reverse strand with the last base most
+// significant, so   revcomp(window) = ~(stream >> 2p) & mask   -- one funnel
+// shift per 32 bits, no roll, no warm-up.  The forward k-mer is initialised
+// once per thread with a bit reversal (BREV) and then rolled two bits per
+// position.  Each thread owns 16 consecutive window starts (one 32-bit word of
+// bases), so every shift amount inside the unrolled loop is an immediate.
+#pragma once
+#include "kmer_types.cuh"
+
+namespace apgk {
+
+constexpr int POS_PER_THREAD = 16;
+
+// Registers a thread needs for its 16 windows: 2W+1 stream words and the word
+// holding bases [p+K, p+K+16) that feed the forward roll.
+template <int W>
+struct Window16 {
+  uint32_t w[2 * W + 1];
+  uint32_t v0;
+};
+
+// p must be a multiple of 16.  bases32 must be readable (zero padded) for
+// 2W+3 words past the last base.
+template <int W>
+APGK_HD void load_window16(const uint32_t* __restrict__ bases32, uint64_t p, int K, Window16<W>& win) {
+  const uint64_t wi = p >> 4;
+  const int nw = (K + 15 + 15) >> 4;  // words that can hold needed bits: ceil((K+15)/16) <= 2W+1
+#pragma unroll
+  for (int m = 0; m < 2 * W + 1; m++) win.w[m] = (m < nw) ? bases32[wi + m] : 0u;
+  const uint64_t vi = wi + (uint64_t)(K >> 4);
+  const uint32_t ks = 2u * (uint32_t)(K & 15);
+  win.v0 = funnel_r(bases32[vi], bases32[vi + 1], ks);
+}
+
+// Calls f(j, canonical, canonical_is_reverse) for j = 0..15 (window start p+j).
+// Validity of each window is the caller's business (see window_valid_mask16).
+template <int W, typename F>
+APGK_HD void extract16(const Window16<W>& win, int K, F&& f) {
+  const int topbits = 2 * K - 64 * (W - 1);
+  const uint64_t topmask = lowmask64(topbits);
+  // ---- forward k-mer of window 0: reverse the 2-bit groups of the LE window
+  Key<W> fw;
+  {
+    uint64_t rm[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+      uint64_t x = (uint64_t)win.w[2 * i] | ((uint64_t)win.w[2 * i + 1] << 32);  // LE chunk i (i=0 least significant)
+      rm[i] = swap_pairs(brev64(x));  // becomes word i of the reversed value, most significant first
+    }
+    const int s = 64 * W - 2 * K;  // 0..62
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+      uint64_t v = rm[i] >> s;
+      if (i > 0 && s > 0) v |= rm[i - 1] << (64 - s);
+      fw.w[i] = v;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < POS_PER_THREAD; j++) {
+    // ---- reverse complement of window j straight from the stream
+    Key<W> rc;
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      uint32_t lo = funnel_r(win.w[2 * q], win.w[2 * q + 1], 2 * j);
+      uint32_t hi = funnel_r(win.w[2 * q + 1], win.w[2 * q + 2], 2 * j);
+      rc.w[W - 1 - q] = ~((uint64_t)lo | ((uint64_t)hi << 32));
+    }
+    rc.w[0] &= topmask;
+    const bool use_rc = key_less(rc, fw);
+    Key<W> c;
+#pragma unroll
+    for (int i = 0; i < W; i++) c.w[i] = use_rc ? rc.w[i] : fw.w[i];
+    f(j, c, use_rc);
+    // ---- roll the forward k-mer to window j+1
+    if (j + 1 < POS_PER_THREAD) {
+      const uint64_t b = (win.v0 >> (2 * j)) & 3u;
+#pragma unroll
+      for (int i = 0; i < W - 1; i++) fw.w[i] = (fw.w[i] << 2) | (fw.w[i + 1] >> 62);
+      fw.w[W - 1] = (fw.w[W - 1] << 2) | b;
+      fw.w[0] &= topmask;
+    }
+  }
+}
+
+// Bit j of the result is set iff window [p+j, p+j+K) lies inside one read:
+// p+j+K <= total_bases and no read starts strictly inside the window.
+// starts32: 1 bit per base (bit q of the bitmap = "a read starts at base q"),
+// zero padded past the end.
+APGK_HD uint32_t window_valid_mask16(const uint32_t* __restrict__ starts32, uint64_t p, int K, uint64_t total_bases) {
+  if (p + (uint64_t)K > total_bases) return 0u;
+  uint32_t ok = 0xFFFFu;
+  const uint64_t room = total_bases - (uint64_t)K - p;  // largest valid j
+  if (room < 15) ok = (2u << (uint32_t)room) - 1u;
+  if (K < 2) return ok;
+  const uint64_t lo = p + 1, hi = p + (uint64_t)K + 14;  // candidate interior positions (inclusive)
+  uint32_t inv = 0;
+  for (uint64_t wi = lo >> 5; wi <= (hi >> 5); wi++) {
+    uint32_t bits = starts32[wi];
+    if (wi == (lo >> 5)) bits &= 0xFFFFFFFFu << (uint32_t)(lo & 31);
+    if (wi == (hi >> 5)) bits &= 0xFFFFFFFFu >> (31u - (uint32_t)(hi & 31));
+    while (bits) {
+#ifdef __CUDA_ARCH__
+      const int b = __ffs((int)bits) - 1;
+#else
+      const int b = __builtin_ctz(bits);
+#endif
+      bits &= bits - 1;
+      const int s = (int)((wi << 5) + (uint64_t)b - p);  // 1 .. K+14 : start strictly inside windows j with s-K < j < s
+      const int j0 = s - K + 1 > 0 ? s - K + 1 : 0;
+      const int j1 = s - 1 < 15 ? s - 1 : 15;
+      if (j0 <= j1) inv |= ((2u << j1) - 1u) & ~((1u << j0) - 1u);
+    }
+  }
+  return ok & ~inv;
+}
+
+}  // namespace apgk

@@ -1,0 +1,282 @@
+// table.cuh -- the k-mer frequency table: compaction of per-bucket records into
+// one sorted (k-mer, count) table with a prefix index, and the lookups error
+// correction makes against it ("k-mer frequency tables consumed by FindErrors",
+// BASELINE.json north_star; SURVEY.md section 3.2 -- no file:line available).
+#pragma once
+#include "local.cuh"
+
+namespace apgk {
+
+// ---------------------------------------------------------------- exclusive scan of u32 -> u64 (three kernels)
+constexpr int SCAN_NT = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_BLOCK = SCAN_NT * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_NT) k_scan_blocksum(const uint32_t* __restrict__ in, uint64_t n,
+                                                           unsigned long long* __restrict__ blocksum) {
+  __shared__ uint32_t scratch[34];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) if (base + j < n) s += in[base + j];
+  block_excl_scan<SCAN_NT>(s, scratch);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = scratch[32];
+}
+// single block: exclusive scan of blocksum[nblocks] in place; total -> blocksum[nblocks]
+__global__ void __launch_bounds__(SCAN_NT) k_scan_top(unsigned long long* blocksum, uint32_t nblocks) {
+  __shared__ unsigned long long part[SCAN_NT];
+  const uint32_t per = (nblocks + SCAN_NT - 1) / SCAN_NT;
+  const uint32_t b0 = threadIdx.x * per;
+  unsigned long long s = 0;
+  for (uint32_t j = 0; j < per; j++) if (b0 + j < nblocks) s += blocksum[b0 + j];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < SCAN_NT; i++) { unsigned long long v = part[i]; part[i] = run; run += v; }
+    blocksum[nblocks] = run;
+  }
+  __syncthreads();
+  unsigned long long run = part[threadIdx.x];
+  for (uint32_t j = 0; j < per; j++) {
+    if (b0 + j < nblocks) { unsigned long long v = blocksum[b0 + j]; blocksum[b0 + j] = run; run += v; }
+  }
+}
+__global__ void __launch_bounds__(SCAN_NT) k_scan_apply(const uint32_t* __restrict__ in, uint64_t n,
+                                                        const unsigned long long* __restrict__ blocksum,
+                                                        unsigned long long* __restrict__ out /* [n+1] */) {
+  __shared__ uint32_t scratch[34];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = base + j < n ? in[base + j] : 0u; s += v[j]; }
+  unsigned long long run = blocksum[blockIdx.x] + block_excl_scan<SCAN_NT>(s, scratch);
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    if (base + j < n) out[base + j] = run;
+    run += v[j];
+  }
+  if (base <= n && n < base + SCAN_ITEMS) out[n] = run;  // the thread owning index n writes the total
+}
+
+// ---------------------------------------------------------------- classify level-1 buckets
+// big_list <- ids of buckets larger than local_max; stats[0] = how many, stats[1] = their total size.
+__global__ void k_classify(const unsigned long long* __restrict__ bsize, uint32_t nb, uint32_t local_max,
+                           uint32_t* __restrict__ big_list, uint32_t big_cap, unsigned long long* __restrict__ stats) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const unsigned long long n = bsize[b];
+  if (n > local_max) {
+    unsigned long long i = atomicAdd(&stats[0], 1ull);
+    atomicAdd(&stats[1], n);
+    if (i < big_cap) big_list[i] = b;
+  }
+}
+
+// ---------------------------------------------------------------- compaction: temp records -> final table
+// One warp per bucket.  Temp keys live at element offset bofs[b] of the level-0
+// buffer; temp counts at BYTE offset bofs[b] * elem_bytes of the level-1 buffer.
+template <int W>
+__global__ void k_compact(const Key<W>* __restrict__ tmp_keys, const unsigned char* __restrict__ tmp_cnt_base,
+                          uint32_t elem_bytes, const unsigned long long* __restrict__ bofs,
+                          const unsigned long long* __restrict__ out_off, uint32_t nb, Key<W>* __restrict__ out_keys,
+                          uint32_t* __restrict__ out_cnt) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t b = warp; b < nb; b += nwarps) {
+    const unsigned long long o0 = out_off[b], nd = out_off[b + 1] - o0;
+    if (!nd) continue;
+    const unsigned long long src = bofs[b];
+    const uint32_t* c = (const uint32_t*)(tmp_cnt_base + src * elem_bytes);
+    for (unsigned long long j = lane; j < nd; j += 32) {
+      out_keys[o0 + j] = tmp_keys[src + j];
+      out_cnt[o0 + j] = c[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- lookups
+template <int W>
+APGK_HD Key<W> key_revcomp(const Key<W>& x, int K) {
+  const int topbits = 2 * K - 64 * (W - 1);
+  Key<W> y;
+#pragma unroll
+  for (int i = 0; i < W; i++) y.w[i] = ~x.w[i];
+  y.w[0] &= lowmask64(topbits);
+  // reverse the 2-bit groups of the 64W-bit value, then shift right by 64W - 2K
+  uint64_t rm[W];
+#pragma unroll
+  for (int i = 0; i < W; i++) rm[i] = swap_pairs(brev64(y.w[W - 1 - i]));
+  const int s = 64 * W - 2 * K;
+  Key<W> r;
+#pragma unroll
+  for (int i = 0; i < W; i++) {
+    uint64_t v = rm[i] >> s;
+    if (i > 0 && s > 0) v |= rm[i - 1] << (64 - s);
+    r.w[i] = v;
+  }
+  return r;
+}
+template <int W>
+APGK_HD Key<W> key_canonical(const Key<W>& x, int K) {
+  Key<W> rc = key_revcomp(x, K);
+  return key_less(rc, x) ? rc : x;
+}
+
+template <int W>
+struct FreqTable {
+  const Key<W>* keys;               // n_distinct, ascending
+  const uint32_t* counts;           // n_distinct
+  const unsigned long long* index;  // [nb+1] first record of each prefix bucket
+  uint32_t nb;
+  int prefix_pos, prefix_len, pad;  // bucket = digits of the key's leading P bits
+  int D1;
+};
+
+template <int W>
+__device__ __forceinline__ uint32_t table_find(const FreqTable<W>& t, const Key<W>& c) {
+  // prefix bucket = (digit0 << D1) | digit1 = bits [prefix_pos, prefix_pos + prefix_len) of the virtual key
+  const uint32_t b = digit_of(c, t.prefix_pos, t.prefix_len, t.pad);
+  unsigned long long lo = t.index[b], hi = t.index[b + 1];
+  while (lo < hi) {
+    unsigned long long mid = (lo + hi) >> 1;
+    if (key_less(t.keys[mid], c)) lo = mid + 1; else hi = mid;
+  }
+  if (lo < t.index[b + 1] && key_eq(t.keys[lo], c)) return t.counts[lo];
+  return 0u;
+}
+
+template <int W>
+__global__ void k_lookup(FreqTable<W> t, const Key<W>* __restrict__ q, uint64_t nq, int K, int canonicalise,
+                         uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  Key<W> c = q[i];
+  if (canonicalise) c = key_canonical(c, K);
+  out[i] = table_find(t, c);
+}
+
+// count of the canonical k-mer starting at every base of the read store
+// (0xFFFFFFFF where the window leaves its read).
+template <int W, int NT>
+__global__ void __launch_bounds__(NT) k_read_freqs(ReadStore rs, FreqTable<W> t, uint64_t first_base, uint64_t n_bases,
+                                                   uint32_t* __restrict__ out) {
+  const uint64_t p = (first_base & ~15ull) + ((uint64_t)blockIdx.x * NT + threadIdx.x) * POS_PER_THREAD;
+  if (p >= first_base + n_bases) return;
+  const uint32_t valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
+  uint32_t res[POS_PER_THREAD];
+#pragma unroll
+  for (int j = 0; j < POS_PER_THREAD; j++) res[j] = 0xFFFFFFFFu;
+  if (valid) {
+    Window16<W> win;
+    load_window16<W>(rs.bases32, p, rs.K, win);
+    extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
+      if ((valid >> j) & 1u) res[j] = table_find(t, c);
+    });
+  }
+#pragma unroll
+  for (int j = 0; j < POS_PER_THREAD; j++) {
+    const uint64_t q = p + j;
+    if (q >= first_base && q < first_base + n_bases) out[q - first_base] = res[j];
+  }
+}
+
+// ---------------------------------------------------------------- read store maintenance
+// Append nbits of a bit stream (src, starting at bit src_bit0) to dst at bit dst_bit0.
+// One thread per destination 64-bit word; partial first/last words are OR-ed in
+// (destination beyond the current end must be zero).
+__global__ void k_append_bits(const uint64_t* __restrict__ src, uint64_t src_bit0, uint64_t* __restrict__ dst,
+                              uint64_t dst_bit0, uint64_t nbits) {
+  const uint64_t w0 = dst_bit0 >> 6, w1 = (dst_bit0 + nbits + 63) >> 6;
+  const uint64_t w = w0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= w1) return;
+  // destination bits [lo, hi) of this word, absolute
+  uint64_t lo = w << 6, hi = lo + 64;
+  if (lo < dst_bit0) lo = dst_bit0;
+  if (hi > dst_bit0 + nbits) hi = dst_bit0 + nbits;
+  const uint64_t sb = src_bit0 + (lo - dst_bit0);  // source bit matching destination bit lo
+  const uint64_t si = sb >> 6;
+  const uint32_t ss = (uint32_t)(sb & 63);
+  uint64_t v = src[si] >> ss;
+  if (ss) v |= src[si + 1] << (64 - ss);  // src is padded by one word
+  const uint32_t len = (uint32_t)(hi - lo);
+  v &= lowmask64((int)len);
+  v <<= (lo & 63);
+  if (len == 64) dst[w] = v; else atomicOr((unsigned long long*)&dst[w], (unsigned long long)v);
+}
+
+// starts bitmap from read offsets: bit (dst_base0 + off[r] - off0) for every read r
+__global__ void k_mark_starts(const uint64_t* __restrict__ off, uint64_t n_reads, uint64_t off0, uint64_t dst_base0,
+                              uint32_t* __restrict__ starts32) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint64_t q = dst_base0 + (off[r] - off0);
+  atomicOr(&starts32[q >> 5], 1u << (q & 31));
+}
+__global__ void k_mark_starts_uniform(uint64_t n_reads, uint32_t read_len, uint64_t dst_base0,
+                                      uint32_t* __restrict__ starts32) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint64_t q = dst_base0 + r * read_len;
+  atomicOr(&starts32[q >> 5], 1u << (q & 31));
+}
+
+// ---------------------------------------------------------------- synthetic reads (SURVEY.md section 8d generator)
+struct SynthParams {
+  uint64_t genome_len;
+  uint64_t seed_g, seed_p, seed_q, seed_r, seed_e;
+  uint32_t read_len;
+  uint32_t err_per_200;
+};
+APGK_HD uint32_t synth_genome_base(const SynthParams& p, uint64_t i) {
+  const uint64_t b = i / 5000u;
+  if (b > 0 && sm64(p.seed_p ^ b) % 50u == 0) {
+    const uint64_t src = sm64(p.seed_q ^ b) % b;
+    i = src * 5000u + i % 5000u;
+  }
+  return (uint32_t)(sm64(p.seed_g ^ i) & 3u);
+}
+struct SynthRead {
+  uint64_t start;
+  bool rev;
+};
+APGK_HD SynthRead synth_read_info(const SynthParams& p, uint64_t r) {
+  SynthRead sr;
+  sr.start = sm64(p.seed_r ^ (2 * r)) % (p.genome_len - p.read_len + 1);
+  sr.rev = (sm64(p.seed_r ^ (2 * r + 1)) >> 63) != 0;
+  return sr;
+}
+APGK_HD uint32_t synth_read_base(const SynthParams& p, const SynthRead& sr, uint64_t r, uint32_t j) {
+  const uint32_t L = p.read_len;
+  uint32_t b = sr.rev ? 3u - synth_genome_base(p, sr.start + (L - 1 - j)) : synth_genome_base(p, sr.start + j);
+  if (p.err_per_200) {
+    const uint64_t e = sm64(p.seed_e ^ (r * (uint64_t)L + j));
+    if ((e >> 32) % 200u < p.err_per_200) b = (b + 1u + (uint32_t)((e >> 8) % 3u)) & 3u;
+  }
+  return b;
+}
+// 16 bases (one store word) starting at base q of the concatenated reads r0, r0+1, ...
+APGK_HD uint32_t synth_word(const SynthParams& sp, uint64_t r0, uint64_t q, uint64_t nb) {
+  uint32_t v = 0;
+  uint64_t r = q / sp.read_len;
+  uint32_t j = (uint32_t)(q % sp.read_len);
+  SynthRead sr = synth_read_info(sp, r0 + r);
+  for (int t = 0; t < 16 && q < nb; t++, q++) {
+    v |= synth_read_base(sp, sr, r0 + r, j) << (2 * t);
+    if (++j == sp.read_len) {
+      j = 0;
+      r++;
+      sr = synth_read_info(sp, r0 + r);
+    }
+  }
+  return v;
+}
+// one thread per 32-bit word (16 bases) of the store, starting at base dst_base0 (multiple of 16)
+__global__ void k_synth(SynthParams sp, uint64_t r0, uint64_t n_reads, uint64_t dst_base0, uint32_t* __restrict__ bases32) {
+  const uint64_t nb = n_reads * sp.read_len;
+  const uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi * 16 >= nb) return;
+  bases32[(dst_base0 >> 4) + wi] = synth_word(sp, r0, wi * 16, nb);
+}
+
+}  // namespace apgk

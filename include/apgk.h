@@ -1,0 +1,165 @@
+/*
+ * apgk.h -- C ABI of libapgk.so, the B200-native k-mer spectrum engine that
+ * replaces ALLPATHS-LG's k-mer hot path (extract -> canonicalise -> sort ->
+ * count -> spectrum, plus the frequency-table lookups error correction makes).
+ *
+ * REFERENCE INTERFACES REPLACED.  The reference tree was not available when
+ * this was written (/root/reference held one empty README),
+ * so the entry points below cite the reference by the names BASELINE.json's
+ * north_star gives them, with the unverified locations SURVEY.md section 2.2 / A.1
+ * recalls.  No file:line exists to cite; each is marked [BJ] (named by
+ * BASELINE.json) or [U] (unverified recollection).
+ *
+ *   apgk_add_reads*      <- the vecbasevector& argument of the builders
+ *                           (src/Basevector.h, src/feudal/BaseVec.h [U])
+ *   apgk_finish          <- SortKmers<K,...>(...) and KmerParcelsBuilder::Build()
+ *                           (src/kmers/SortKmers.{h,cc},
+ *                            src/kmers/kmer_parcels/KmerParcelsBuilder.{h,cc} [BJ names, U paths]);
+ *                           naif_kmerize(kernel, n_threads) (src/kmers/naif_kmer/ [U])
+ *   apgk_spectrum*       <- class KmerSpectrum (src/kmers/KmerSpectra.h [BJ name, U path])
+ *   apgk_counts_*        <- the sorted (k-mer, frequency) records: vec<kmer_record>,
+ *                           KmerParcelReader batches, KmerKmerFreq vectors [U]
+ *   apgk_lookup*, apgk_read_freqs*
+ *                        <- the k-mer frequency tables FindErrors queries per read
+ *                           position (src/paths/FindErrors*.cc [BJ name, U path])
+ *
+ * CONVENTIONS (SURVEY.md section 8 "Definition"): bases A=0 C=1 G=2 T=3, packed
+ * 2 bits per base, base q of a buffer at bits [2q, 2q+2) (little-endian inside
+ * a byte).  A k-mer is the 2K-bit integer with its first base most significant,
+ * stored in W = ceil(2K/64) uint64 words, most significant word first, value
+ * right-aligned.  canonical(x) = min(x, revcomp(x)).  count = number of window
+ * instances with that canonical form.  spectrum[f] = number of distinct
+ * canonical k-mers with count f.
+ *
+ * Every function returns APGK_OK (0) or a negative error code and never
+ * aborts or throws; apgk_last_error() describes the last failure.  There is no
+ * CPU fallback: without a CUDA device apgk_create fails with APGK_E_CUDA.
+ * A context is single-caller.  Inputs are borrowed for the duration of a call;
+ * outputs are library-owned until apgk_reset / apgk_destroy.
+ */
+#ifndef APGK_H
+#define APGK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APGK_OK 0
+#define APGK_E_ARG (-1)      /* bad argument */
+#define APGK_E_CUDA (-2)     /* CUDA runtime error / no device */
+#define APGK_E_NOMEM (-3)    /* device or host allocation failed */
+#define APGK_E_STATE (-4)    /* call out of order (e.g. results before apgk_finish) */
+#define APGK_E_RANGE (-5)    /* a size exceeds what this build handles (see message) */
+
+#define APGK_WANT_SPECTRUM 1u /* always produced */
+#define APGK_WANT_COUNTS 2u   /* also build the sorted (k-mer, count) table + lookup index */
+
+#define APGK_MAX_K 96
+
+typedef struct apgk_ctx apgk_ctx;
+
+typedef struct {
+  int32_t K;            /* 1..APGK_MAX_K */
+  int32_t device;       /* CUDA device ordinal */
+  uint32_t flags;       /* APGK_WANT_* */
+  int32_t prefix_bits;  /* 0 = auto; else total bits of the two partition levels (2..24) */
+  uint64_t reserve_bases; /* 0 or a hint: pre-size the device read store for this many bases */
+} apgk_config;
+
+/* Parameters of the synthetic read generator; identical in the oracle. */
+typedef struct {
+  uint64_t genome_len;
+  uint64_t seed_g, seed_p, seed_q, seed_r, seed_e;
+  uint32_t read_len;
+  uint32_t err_per_200; /* 1 = 0.5 % substitutions, 0 = none */
+} apgk_synth_params;
+
+int apgk_create(const apgk_config* cfg, apgk_ctx** out);
+void apgk_destroy(apgk_ctx* ctx);
+const char* apgk_last_error(const apgk_ctx* ctx);
+int apgk_words_per_kmer(int K);
+
+/* Drop reads and results, keep device buffers (for reuse in a streaming loop). */
+int apgk_reset(apgk_ctx* ctx);
+
+/* ---- reads in.  May be called repeatedly; reads accumulate in the device store.
+ * packed/off are HOST buffers: read r = bases off[r] .. off[r+1]-1 of `packed`. */
+int apgk_add_reads(apgk_ctx* ctx, const uint8_t* packed, const uint64_t* off, uint64_t n_reads);
+/* n_reads reads of read_len bases each, back to back, starting at base first_base of `packed`. */
+int apgk_add_reads_uniform(apgk_ctx* ctx, const uint8_t* packed, uint64_t first_base, uint64_t n_reads,
+                           uint32_t read_len);
+/* Generate synthetic reads [r0, r0+n) straight into the device store (store must be empty or
+ * hold a multiple of 16 bases). */
+int apgk_synth_reads(apgk_ctx* ctx, const apgk_synth_params* p, uint64_t r0, uint64_t n_reads);
+/* Copy the device store's packed bases to a host buffer of ceil(total_bases/32)*8 bytes. */
+int apgk_export_reads(apgk_ctx* ctx, uint8_t* packed_out);
+int apgk_read_store_info(const apgk_ctx* ctx, uint64_t* total_bases, uint64_t* n_reads);
+
+/* ---- the hot path: extract + canonicalise + partition + sort + count + spectrum. */
+int apgk_finish(apgk_ctx* ctx);
+
+/* ---- results */
+int apgk_totals(const apgk_ctx* ctx, uint64_t* n_instances, uint64_t* n_distinct);
+/* Dense spectrum: (*spec)[f] for f in [0, *len); (*spec)[0] == 0.  APGK_E_RANGE if the largest
+ * count would need more than 2^28 entries -- use apgk_spectrum_sparse then. */
+int apgk_spectrum(apgk_ctx* ctx, const uint64_t** spec, uint64_t* len);
+/* Sparse spectrum: *n pairs (freq[i], n_kmers[i]) with n_kmers > 0, ascending freq. */
+int apgk_spectrum_sparse(apgk_ctx* ctx, const uint64_t** freq, const uint64_t** n_kmers, uint64_t* n);
+/* Sorted table on the DEVICE: kmers = n_distinct * W words, counts = n_distinct uint32
+ * (saturating at 0xFFFFFFFF).  Needs APGK_WANT_COUNTS. */
+int apgk_counts_device(apgk_ctx* ctx, const uint64_t** d_kmers, const uint32_t** d_counts, uint64_t* n_distinct);
+/* Copy records [first, first+n) of the table to host buffers (either may be NULL). */
+int apgk_counts_copy(apgk_ctx* ctx, uint64_t first, uint64_t n, uint64_t* kmers_out, uint32_t* counts_out);
+
+/* ---- frequency-table queries (need APGK_WANT_COUNTS and a finished context) */
+/* counts_out[i] = count of query k-mer i (W words each, host), 0 if absent.  Queries are
+ * canonicalised first when canonicalise != 0. */
+int apgk_lookup(apgk_ctx* ctx, const uint64_t* kmers, uint64_t n, int canonicalise, uint32_t* counts_out);
+/* out[i] = count of the canonical k-mer starting at base first_base+i of the device read store,
+ * 0xFFFFFFFF where the window crosses a read end.  out is a HOST buffer of n_bases entries. */
+int apgk_read_freqs(apgk_ctx* ctx, uint64_t first_base, uint64_t n_bases, uint32_t* out);
+
+/* ---- multi-GPU building blocks (one context per rank; the exchange itself is the caller's,
+ * e.g. NCCL all-to-all).  Canonical k-mers are owned by rank hash(kmer) % n_ranks. */
+/* Pass 1: per-owner instance counts of this rank's reads (counts_out[n_ranks], host). */
+int apgk_owner_plan(apgk_ctx* ctx, uint32_t n_ranks, uint64_t* counts_out);
+/* Pass 2: write this rank's canonical k-mers grouped by owner (owner 0 first) into the DEVICE
+ * buffer d_keys_out (sum(counts) * W words). */
+int apgk_owner_scatter(apgk_ctx* ctx, uint64_t* d_keys_out);
+/* Owner hash of k-mers (host arrays), for tests. */
+int apgk_owner_of(int K, const uint64_t* kmers, uint64_t n, uint32_t n_ranks, uint32_t* owner_out);
+/* Sort + count a DEVICE array of n canonical k-mers (W words each) instead of the read store. */
+int apgk_finish_keys_device(apgk_ctx* ctx, const uint64_t* d_keys, uint64_t n);
+/* Device pointer to the dense spectrum accumulator (uint64[65536]) after finish, for all-reduce;
+ * apgk_spectrum_reload() re-reads it after the caller summed it in place. */
+int apgk_spectrum_device(apgk_ctx* ctx, uint64_t** d_spec, uint64_t* len);
+int apgk_spectrum_reload(apgk_ctx* ctx);
+
+/* ---- instrumentation */
+#define APGK_N_STAGES 12
+/* Device milliseconds of the last finish, by stage; names via apgk_stage_name(i). */
+int apgk_stage_ms(const apgk_ctx* ctx, float* ms_out /* [APGK_N_STAGES] */);
+const char* apgk_stage_name(int i);
+/* Number of kernels this library launched since creation (or the last apgk_reset_counters). */
+uint64_t apgk_kernel_launches(const apgk_ctx* ctx);
+void apgk_reset_counters(apgk_ctx* ctx);
+/* Geometry chosen by the last finish: D0, D1, REM bits, element bytes of the level-1 buffer,
+ * number of oversize buckets. */
+int apgk_geometry(const apgk_ctx* ctx, int32_t* out5);
+/* Pinned host memory helpers for callers that stream batches. */
+int apgk_host_alloc(void** p, size_t bytes);
+int apgk_host_free(void* p);
+
+/* ---- test hooks: run the device code's inline helpers on the HOST (no GPU needed).  They exist
+ * so the CPU test-suite can check extraction against the oracle; the library never calls them. */
+int apgk_debug_host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K,
+                            uint64_t* kmers_out /* total_bases * W */, uint8_t* valid_out /* total_bases */);
+int apgk_debug_host_canonical(int K, const uint64_t* kmers, uint64_t n, uint64_t* out);
+int apgk_debug_host_synth(const apgk_synth_params* p, uint64_t r0, uint64_t n_reads, uint8_t* packed_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APGK_H */

@@ -1,0 +1,84 @@
+"""world_size-2 (and 3) CPU tests of the multi-GPU host logic over the gloo backend: the ownership
+rule + all-to-all routing of allpathslg_b200.dist, with the oracle standing in for the per-rank
+sort/count kernels.  Identical k-mers must meet on one rank, so summed per-rank spectra equal the
+single-process spectrum bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, K, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from allpathslg_b200 import _lib
+    from allpathslg_b200.dist import host_shuffle
+    from oracle import oracle_a as A
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = _lib.lib()
+    n_per = 3000
+    sp = A.synth_params(40_000, 100)
+    packed, off = A.synth_reads(sp, rank * n_per, n_per)  # this rank's slice of the reads
+    # every canonical k-mer INSTANCE of this rank's reads, via the library's host-executable extractor
+    W = (2 * K + 63) // 64
+    total = int(off[-1])
+    km = np.zeros(total * W, dtype=np.uint64)
+    va = np.zeros(total, dtype=np.uint8)
+    assert L.apgk_debug_host_extract(packed.ctypes.data, off.ctypes.data, n_per, K, km.ctypes.data, va.ctypes.data) == 0
+    inst = km.reshape(-1, W)[va.astype(bool)]
+    mine = host_shuffle(inst, K, rank, world)
+    # sort + count the shard this rank owns
+    if len(mine):
+        order = np.lexsort(tuple(mine[:, j] for j in range(W - 1, -1, -1)))
+        srt = mine[order]
+        new = np.ones(len(srt), dtype=bool)
+        new[1:] = (srt[1:] != srt[:-1]).any(axis=1)
+        idx = np.nonzero(new)[0]
+        counts = np.diff(np.append(idx, len(srt)))
+        kmers = srt[idx]
+    else:
+        counts = np.zeros(0, dtype=np.int64)
+        kmers = np.zeros((0, W), dtype=np.uint64)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), kmers=kmers, counts=counts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,K", [(2, 25), (3, 40), (2, 96)])
+def test_hash_sharded_count_gloo(oracle, tmp_path, world, K):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, K, str(tmp_path)), nprocs=world, join=True)
+    sp = oracle.synth_params(40_000, 100)
+    packed, off = oracle.synth_reads(sp, 0, 3000 * world)
+    ek, ec, en = oracle.count(packed, off, K)
+    from allpathslg_b200 import owner_of
+
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    # shards are disjoint, each holds exactly the k-mers it owns, counts are final
+    own = owner_of(K, ek, world)
+    for r, pt in enumerate(parts):
+        sel = own == r
+        assert (pt["kmers"] == ek[sel]).all()
+        assert (pt["counts"].astype(np.uint64) == ec[sel]).all()
+    spec = np.zeros(int(ec.max()) + 1, dtype=np.uint64)
+    for pt in parts:
+        spec += np.bincount(pt["counts"], minlength=len(spec)).astype(np.uint64)
+    assert (spec == oracle.spectrum(ec)).all()
+    assert sum(int(pt["counts"].sum()) for pt in parts) == en

@@ -1,0 +1,92 @@
+"""CPU tests of the oracle itself: golden vectors, A-vs-B agreement, invariants.
+(Parity unpinned: no reference vectors exist -- see tests/golden/make_golden.py.)"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle_b as B
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))
+
+
+def _to_int(row):
+    W = len(row)
+    return sum(int(row[j]) << (64 * (W - 1 - j)) for j in range(W))
+
+
+@pytest.mark.parametrize("v", GOLD["hand"], ids=lambda v: "%s-K%d" % ("+".join(v["reads"]) or "empty", v["K"]))
+def test_hand_vectors(oracle, v):
+    p, o = oracle.pack_strings(v["reads"])
+    k, c, n = oracle.count(p, o, v["K"])
+    assert [_to_int(r) for r in k] == v["kmers"]
+    assert [int(x) for x in c] == v["counts"]
+    assert [int(x) for x in oracle.spectrum(c)] == v["spectrum"]
+    assert n == sum(max(0, len(r) - v["K"] + 1) for r in v["reads"])
+
+
+@pytest.mark.parametrize("s", GOLD["synth"], ids=lambda s: "G%d-K%d" % (s["genome_len"], s["K"]))
+def test_synth_golden(oracle, s):
+    sp = oracle.synth_params(s["genome_len"], s["read_len"])
+    p, o = oracle.synth_reads(sp, 0, s["n_reads"])
+    k, c, n = oracle.count(p, o, s["K"])
+    assert n == s["n_instances"] and len(k) == s["n_distinct"]
+    assert [int(x) for x in oracle.spectrum(c)] == s["spectrum"]
+    M = (1 << 61) - 1
+    chk = 0
+    for row, cnt in zip(k, c):
+        chk = (chk + (_to_int(row) % M) * int(cnt)) % M
+    assert chk == s["table_checksum"]
+    assert [str(_to_int(r)) for r in k[:4]] == s["first_kmers"]
+
+
+@pytest.mark.parametrize("K", [1, 2, 7, 16, 25, 31, 32, 33, 47, 64, 65, 96])
+def test_oracle_a_matches_b(oracle, K):
+    rnd = random.Random(K)
+    reads = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([0, 1, K - 1, K, K + 1, K + 9, 140]))) for _ in range(50)]
+    reads += ["A" * (K + 25), "ACGT" * 30, "CG" * (K + 3)]
+    rc = reads[4].translate(str.maketrans("ACGT", "TGCA"))[::-1]
+    reads.append(rc)
+    p, o = oracle.pack_strings(reads)
+    k, c, n = oracle.count(p, o, K)
+    pairs = B.count_reads(reads, K)
+    assert [_to_int(r) for r in k] == [x for x, _ in pairs]
+    assert [int(x) for x in c] == [y for _, y in pairs]
+    spec = oracle.spectrum(c)
+    assert [int(x) for x in spec] == B.spectrum(pairs)
+    # invariants of SURVEY.md section 8: sum f*spectrum[f] = instances ; sum spectrum = distinct
+    assert int((spec * np.arange(len(spec), dtype=np.uint64)).sum()) == n
+    assert int(spec.sum()) == len(pairs)
+
+
+def test_strand_symmetry(oracle):
+    """A read set and its reverse complement have identical canonical counts."""
+    rnd = random.Random(5)
+    reads = ["".join(rnd.choice("ACGT") for _ in range(120)) for _ in range(40)]
+    rcs = [r.translate(str.maketrans("ACGT", "TGCA"))[::-1] for r in reads]
+    for K in (8, 25, 33):
+        a = oracle.count(*oracle.pack_strings(reads), K)
+        b = oracle.count(*oracle.pack_strings(rcs), K)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_thread_count_independent(oracle):
+    sp = oracle.synth_params(30000, 100)
+    p, o = oracle.synth_reads(sp, 0, 5000)
+    a = oracle.count(p, o, 25, n_threads=1)
+    b = oracle.count(p, o, 25, n_threads=4)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_lookup_and_read_freqs(oracle):
+    sp = oracle.synth_params(5000, 80)
+    p, o = oracle.synth_reads(sp, 0, 300)
+    K = 21
+    k, c, _ = oracle.count(p, o, K)
+    assert (oracle.lookup(k, c, K, k, canonicalise=False) == c).all()
+    rf = oracle.read_freqs(p, o, K, k, c)
+    valid = rf != np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert valid.sum() == 300 * (80 - K + 1)
+    assert (rf[valid] >= 1).all()
