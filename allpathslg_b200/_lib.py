@@ -60,6 +60,9 @@ SYMBOLS = {
     "apgk_kernel_launches": (C.c_uint64, [_vp]),
     "apgk_reset_counters": (None, [_vp]),
     "apgk_geometry": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "apgk_device_alloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
+    "apgk_device_free": (C.c_int, [_vp, _vp]),
+    "apgk_device_copy_to_host": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "apgk_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "apgk_host_free": (C.c_int, [_vp]),
     "apgk_debug_host_extract": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp]),

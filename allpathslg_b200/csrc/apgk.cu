@@ -107,7 +107,8 @@ namespace {
     return (code);                             \
   } while (0)
 
-#define LAUNCHED() do { c->launches++; CU(cudaGetLastError()); } while (0)
+static const bool kSyncDebug = getenv("APGK_SYNC_DEBUG") != nullptr;  // sync after every launch to localise faults
+#define LAUNCHED() do { c->launches++; CU(cudaGetLastError()); if (kSyncDebug) CU(cudaStreamSynchronize(c->stream)); } while (0)
 
 void stage_begin(apgk_ctx* c, int s) { cudaEventRecord(c->ev[s][0], c->stream); c->ev_used[s] = true; }
 void stage_end(apgk_ctx* c, int s) { cudaEventRecord(c->ev[s][1], c->stream); }
@@ -395,7 +396,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     { int rc = set_smem(c, kern, sm); if (rc) return rc; }
     kern<<<hp0.lp.n_tiles, Geo<W>::NT0, sm, c->stream>>>(read_store(c), ds0, bins0, c->cnt16.as<uint16_t>(),
                                                          c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(),
-                                                         c->A.as<Key<W>>());
+                                                         c->A.as<Key<W>>(), (unsigned long long)N);
   }
   LAUNCHED();
   stage_end(c, ST_SCATTER0);
@@ -676,7 +677,7 @@ int owner_scatter_impl(apgk_ctx* c, uint64_t* d_out) {
   { int rc = set_smem(c, kern, sm); if (rc) return rc; }
   kern<<<c->owner_tiles, Geo<W>::NT0, sm, c->stream>>>(read_store(c), ds, (int)n_ranks, c->cnt16.as<uint16_t>(),
                                                        c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(),
-                                                       (Key<W>*)d_out);
+                                                       (Key<W>*)d_out, (unsigned long long)bstart[n_ranks]);
   LAUNCHED();
   stage_end(c, ST_OWNER);
   CU(cudaStreamSynchronize(c->stream));
@@ -1017,6 +1018,28 @@ int apgk_geometry(const apgk_ctx* c, int32_t* out5) {
   if (!c || !out5) return APGK_E_ARG;
   out5[0] = c->geom.D0; out5[1] = c->geom.D1; out5[2] = c->geom.REM; out5[3] = (int32_t)c->elem_bytes;
   out5[4] = (int32_t)std::min<uint64_t>(c->n_big, 0x7fffffff);
+  return APGK_OK;
+}
+
+int apgk_device_alloc(apgk_ctx* c, void** p, size_t bytes) {
+  if (!c || !p) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(p, bytes ? bytes : 1));
+  return APGK_OK;
+}
+int apgk_device_free(apgk_ctx* c, void* p) {
+  if (!c) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaFree(p));
+  return APGK_OK;
+}
+int apgk_device_copy_to_host(apgk_ctx* c, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!c || (!dst_host && bytes)) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  if (bytes) {
+    CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   return APGK_OK;
 }
 

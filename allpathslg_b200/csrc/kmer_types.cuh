@@ -71,7 +71,14 @@ APGK_HD uint64_t key_hash(const Key<W>& k) {
 // owner rank of a canonical k-mer among n_ranks (multiply-shift range reduction of the hash)
 template <int W>
 APGK_HD uint32_t key_owner(const Key<W>& k, uint32_t n_ranks) {
-  return (uint32_t)(((key_hash(k) >> 32) * (uint64_t)n_ranks) >> 32);
+  const uint32_t h = (uint32_t)(key_hash(k) >> 32);
+#ifdef __CUDA_ARCH__
+  // Explicit mul.hi: with the 64-bit product form, ptxas 12.9 (sm_100a) folded the shift into a
+  // wrong shared-memory address in a loop remainder of k_scatter_reads (illegal address at run time).
+  return __umulhi(h, n_ranks);
+#else
+  return (uint32_t)(((uint64_t)h * (uint64_t)n_ranks) >> 32);
+#endif
 }
 
 APGK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {

@@ -19,6 +19,16 @@
 // the input, so results are reproducible run to run.
 #pragma once
 #include "extract.cuh"
+#include <cstdio>
+
+// Debug build (-DAPGK_CHECKS): bounds checks that report and skip instead of faulting.
+#ifdef APGK_CHECKS
+#define APGK_CHECK(cond, ...) do { if (!(cond)) { printf(__VA_ARGS__); } } while (0)
+#define APGK_OK_OR_SKIP(cond) (cond)
+#else
+#define APGK_CHECK(cond, ...) do { } while (0)
+#define APGK_OK_OR_SKIP(cond) true
+#endif
 
 namespace apgk {
 
@@ -190,7 +200,8 @@ template <int W, int NT>
 __global__ void __launch_bounds__(NT) k_scatter_reads(ReadStore rs, DigitSpec ds, int bins,
                                                       const uint16_t* __restrict__ cnt16,
                                                       const uint32_t* __restrict__ base32,
-                                                      const uint64_t* __restrict__ bstart64, Key<W>* __restrict__ out) {
+                                                      const uint64_t* __restrict__ bstart64, Key<W>* __restrict__ out,
+                                                      unsigned long long out_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Key<W>* stage; uint32_t* cursor; unsigned long long* gbase; uint32_t* scratch;
   scatter_smem_carve<Key<W>>(smem_raw, NT * POS_PER_THREAD, bins, stage, cursor, gbase, scratch);
@@ -208,7 +219,9 @@ __global__ void __launch_bounds__(NT) k_scatter_reads(ReadStore rs, DigitSpec ds
           uint32_t d = spec_digit(ds, c);
           if (d >= ds.lo && d < ds.hi) {
             uint32_t pos = atomicAdd(&cursor[d], 1u);
-            stage[pos] = c;
+            APGK_CHECK(pos < (uint32_t)(NT * POS_PER_THREAD) && d < (uint32_t)bins,
+                       "scatter_reads: tile %u tid %d pos %u d %u bins %d tile_n %u\n", blockIdx.x, threadIdx.x, pos, d, bins, tile_n);
+            if (APGK_OK_OR_SKIP(pos < (uint32_t)(NT * POS_PER_THREAD))) stage[pos] = c;
           }
         }
       });
@@ -218,7 +231,9 @@ __global__ void __launch_bounds__(NT) k_scatter_reads(ReadStore rs, DigitSpec ds
   for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
     Key<W> k = stage[i];
     uint32_t d = spec_digit(ds, k);
-    out[gbase[d] + i] = k;
+    APGK_CHECK(d < (uint32_t)bins && gbase[d < (uint32_t)bins ? d : 0] + i < out_cap,
+               "scatter_reads out: tile %u i %u d %u gbase %llu cap %llu\n", blockIdx.x, i, d, gbase[d < (uint32_t)bins ? d : 0], out_cap);
+    if (APGK_OK_OR_SKIP(d < (uint32_t)bins && gbase[d] + i < out_cap)) out[gbase[d] + i] = k;
   }
 }
 

@@ -148,6 +148,11 @@ void apgk_reset_counters(apgk_ctx* ctx);
 /* Geometry chosen by the last finish: D0, D1, REM bits, element bytes of the level-1 buffer,
  * number of oversize buckets. */
 int apgk_geometry(const apgk_ctx* ctx, int32_t* out5);
+/* Device buffers for callers without their own allocator (e.g. the exchange buffers of the
+ * multi-GPU path in a plain C++ host), and a synchronous device-to-host copy. */
+int apgk_device_alloc(apgk_ctx* ctx, void** p, size_t bytes);
+int apgk_device_free(apgk_ctx* ctx, void* p);
+int apgk_device_copy_to_host(apgk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 /* Pinned host memory helpers for callers that stream batches. */
 int apgk_host_alloc(void** p, size_t bytes);
 int apgk_host_free(void* p);
