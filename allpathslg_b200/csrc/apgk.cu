@@ -64,7 +64,7 @@ struct apgk_ctx {
   uint64_t total_bases = 0, n_reads = 0;
   // ---- pipeline buffers
   DevBuf A, B, cnt16, base32, chunksum, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
-      scratch, stacks, spec_dense, spec_ovf, misc;
+      scratch, stacks, spec_dense, spec_ovf, misc, deferred;
   // ---- results
   DevBuf out_keys, out_cnt;
   bool finished = false, have_table = false;
@@ -73,6 +73,7 @@ struct apgk_ctx {
   uint32_t nb1 = 0;          // number of level-1 buckets
   uint32_t elem_bytes = 0;   // level-1 element size
   uint64_t n_big = 0;
+  uint32_t n_deferred = 0, local_max = 0;
   std::vector<uint64_t> spec_host, sparse_f, sparse_n;
   bool spec_loaded = false;
   // ---- owner partition state
@@ -118,9 +119,10 @@ int words_for(int K) { return (2 * K + 63) / 64; }
 // tile geometry per key width
 template <int W> struct Geo;
 template <> struct Geo<1> { static constexpr int NT0 = 1024; static constexpr int NT1 = 1024; static constexpr uint32_t TILE1 = 16384; static constexpr int LM_KEY = 4096; };
-template <> struct Geo<2> { static constexpr int NT0 = 512;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 8192;  static constexpr int LM_KEY = 3072; };
+template <> struct Geo<2> { static constexpr int NT0 = 512;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 8192;  static constexpr int LM_KEY = 2048; };
 template <> struct Geo<3> { static constexpr int NT0 = 256;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 5120;  static constexpr int LM_KEY = 2048; };
 constexpr int LM_U32 = 4096;
+constexpr int L3_NT = 256;
 constexpr int COL_NT = 1024;
 
 // host-side description of a partition level, mirrored on the device in ctx->plan
@@ -292,7 +294,11 @@ template <int W>
 int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   invalidate_results(c);
   for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
-  const uint64_t upper = dev_keys ? n_keys : c->total_bases;
+  uint64_t upper = dev_keys ? n_keys : c->total_bases;
+  if (!dev_keys) {  // reads shorter than K aside, a read of L bases yields L-K+1 windows
+    const uint64_t lost = c->n_reads * (uint64_t)(c->cfg.K - 1);
+    upper = upper > lost ? upper - lost : 1;
+  }
   // decide element type of the level-1 buffer first (it fixes LOCAL_MAX, which fixes P)
   int P = choose_prefix_bits(c, upper, LM_U32);
   make_geom(c, P);
@@ -311,6 +317,9 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   }
   if (rc) return rc;
   stage_end(c, ST_TOTAL);
+  c->n_deferred = 0;
+  if (c->deferred.p && c->n_instances)
+    CU(cudaMemcpyAsync(&c->n_deferred, c->deferred.p, 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   for (int s = 0; s < APGK_N_STAGES; s++)
     if (c->ev_used[s]) cudaEventElapsedTime(&c->stage_ms[s], c->ev[s][0], c->ev[s][1]);
@@ -329,6 +338,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
   const int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : Geo<W>::LM_KEY;
   c->elem_bytes = sizeof(ElemB);
+  c->local_max = (uint32_t)local_max;
   c->nb1 = (uint32_t)bins0 * (uint32_t)bins1;
   CU(c->spec_dense.ensure((size_t)SPEC_DENSE * 8));
   CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
@@ -485,14 +495,45 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   bt.bsize = c->segtot.as<unsigned long long>();
   bt.nb = c->nb1; bt.local_max = (uint32_t)local_max;
   {
+    // fast kernel over all buckets; buckets it cannot take land on the deferred list ...
+    CU(c->deferred.ensure(((size_t)c->nb1 + 1) * 4));
+    CU(cudaMemsetAsync(c->deferred.p, 0, 4, c->stream));
+    stage_begin(c, ST_LOCAL);
+    bool launched = false;
+    if constexpr (std::is_same<ElemB, uint32_t>::value) {
+      if (g.REM >= 1 && g.REM <= 31) {  // order-preserving hash kernel
+        auto kern3 = k_local3<L3_NT, W>;
+        const size_t sm3 = Local3Smem::bytes(local_max);
+        { int rc = set_smem(c, kern3, sm3); if (rc) return rc; }
+        int occ3 = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kern3, L3_NT, sm3));
+        const uint32_t grid3 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ3, 1)));
+        kern3<<<grid3, L3_NT, sm3, c->stream>>>(c->B.as<uint32_t>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
+                                                c->deferred.as<uint32_t>(), c->nb1);
+        LAUNCHED();
+        launched = true;
+      }
+    }
+    if (!launched) {
+      auto kern2 = k_local2<ElemB, W>;
+      const size_t sm2 = Local2Smem<ElemB>::bytes(local_max);
+      { int rc = set_smem(c, kern2, sm2); if (rc) return rc; }
+      int occ2 = 1;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, L2_NT, sm2));
+      const uint32_t grid2 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ2, 1)));
+      kern2<<<grid2, L2_NT, sm2, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
+                                              c->deferred.as<uint32_t>(), c->nb1);
+      LAUNCHED();
+    }
+    // ... which the barrier-heavy general kernel then walks (normally empty)
     auto kern = k_local<ElemB, W>;
     const size_t sm = LocalSmem<ElemB>::bytes(local_max);
     { int rc = set_smem(c, kern, sm); if (rc) return rc; }
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
     const uint32_t grid = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ, 1)));
-    stage_begin(c, ST_LOCAL);
-    kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>());
+    kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
+                                            c->deferred.as<uint32_t>(), c->nb1);
     LAUNCHED();
     stage_end(c, ST_LOCAL);
   }
@@ -751,7 +792,7 @@ void apgk_destroy(apgk_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->cnt16, &c->base32, &c->chunksum,
                    &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
-                   &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc,
+                   &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc, &c->deferred,
                    &c->out_keys, &c->out_cnt};
   for (DevBuf* b : all) b->release();
   for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
@@ -1014,10 +1055,13 @@ const char* apgk_stage_name(int i) { return (i >= 0 && i < APGK_N_STAGES) ? kSta
 uint64_t apgk_kernel_launches(const apgk_ctx* c) { return c ? c->launches : 0; }
 void apgk_reset_counters(apgk_ctx* c) { if (c) c->launches = 0; }
 
-int apgk_geometry(const apgk_ctx* c, int32_t* out5) {
-  if (!c || !out5) return APGK_E_ARG;
-  out5[0] = c->geom.D0; out5[1] = c->geom.D1; out5[2] = c->geom.REM; out5[3] = (int32_t)c->elem_bytes;
-  out5[4] = (int32_t)std::min<uint64_t>(c->n_big, 0x7fffffff);
+int apgk_geometry(const apgk_ctx* c, int32_t* out8) {
+  if (!c || !out8) return APGK_E_ARG;
+  out8[0] = c->geom.D0; out8[1] = c->geom.D1; out8[2] = c->geom.REM; out8[3] = (int32_t)c->elem_bytes;
+  out8[4] = (int32_t)std::min<uint64_t>(c->n_big, 0x7fffffff);
+  out8[5] = (int32_t)std::min<uint32_t>(c->n_deferred, 0x7fffffff);
+  out8[6] = (int32_t)c->local_max;
+  out8[7] = 0;
   return APGK_OK;
 }
 

@@ -243,15 +243,20 @@ __device__ __forceinline__ void spec_flush(LocalSmem<Elem>& sm, unsigned long lo
 }
 
 // Persistent kernel over all level-1 buckets that fit in shared memory.
+// With list == nullptr it walks all buckets; otherwise the bucket ids list[1 .. 1 + list[0]) (the
+// deferred list k_local2 leaves behind).
 template <typename Elem, int W>
 __global__ void __launch_bounds__(LOCAL_NT) k_local(const Elem* __restrict__ src, BucketTable bt, int sort_bits,
-                                                    EmitCtx<W> ec, uint32_t* __restrict__ nd_out) {
+                                                    EmitCtx<W> ec, uint32_t* __restrict__ nd_out,
+                                                    const uint32_t* __restrict__ list, uint32_t list_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LocalSmem<Elem> sm;
   sm.carve(smem_raw, (int)bt.local_max);
   for (int i = threadIdx.x; i < SPEC_SMEM; i += LOCAL_NT) sm.spec[i] = 0;
   __syncthreads();
-  for (uint32_t b = blockIdx.x; b < bt.nb; b += gridDim.x) {
+  const uint32_t n_iter = list ? (list[0] < list_cap ? list[0] : list_cap) : bt.nb;
+  for (uint32_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    const uint32_t b = list ? list[1 + it] : it;
     const unsigned long long n = bt.bsize[b];
     if (n == 0) {
       if (threadIdx.x == 0) nd_out[b] = 0;

@@ -200,9 +200,9 @@ class KmerCounter:
         self._L.apgk_reset_counters(self._h)
 
     def geometry(self):
-        g = (C.c_int32 * 5)()
+        g = (C.c_int32 * 8)()
         self._ck(self._L.apgk_geometry(self._h, g))
-        return dict(D0=g[0], D1=g[1], REM=g[2], elem_bytes=g[3], n_big=g[4])
+        return dict(D0=g[0], D1=g[1], REM=g[2], elem_bytes=g[3], n_big=g[4], n_deferred=g[5], local_max=g[6])
 
 
 def owner_of(K, kmers, n_ranks):

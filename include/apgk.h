@@ -145,9 +145,9 @@ const char* apgk_stage_name(int i);
 /* Number of kernels this library launched since creation (or the last apgk_reset_counters). */
 uint64_t apgk_kernel_launches(const apgk_ctx* ctx);
 void apgk_reset_counters(apgk_ctx* ctx);
-/* Geometry chosen by the last finish: D0, D1, REM bits, element bytes of the level-1 buffer,
- * number of oversize buckets. */
-int apgk_geometry(const apgk_ctx* ctx, int32_t* out5);
+/* Geometry of the last finish: D0, D1, REM bits, element bytes of the level-1 buffer, number of
+ * oversize buckets (k_big), number of buckets deferred to the general kernel, bucket capacity, 0. */
+int apgk_geometry(const apgk_ctx* ctx, int32_t* out8);
 /* Device buffers for callers without their own allocator (e.g. the exchange buffers of the
  * multi-GPU path in a plain C++ host), and a synchronous device-to-host copy. */
 int apgk_device_alloc(apgk_ctx* ctx, void** p, size_t bytes);
