@@ -121,8 +121,8 @@ template <int W> struct Geo;
 template <> struct Geo<1> { static constexpr int NT0 = 1024; static constexpr int NT1 = 1024; static constexpr uint32_t TILE1 = 16384; static constexpr int LM_KEY = 4096; };
 template <> struct Geo<2> { static constexpr int NT0 = 512;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 8192;  static constexpr int LM_KEY = 2048; };
 template <> struct Geo<3> { static constexpr int NT0 = 256;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 5120;  static constexpr int LM_KEY = 2048; };
-constexpr int LM_U32 = 4096;
-constexpr int L3_NT = 256;
+constexpr int LM_U32 = 5120;
+constexpr int L3_NT = 512;
 constexpr int COL_NT = 1024;
 
 // host-side description of a partition level, mirrored on the device in ctx->plan
@@ -207,7 +207,7 @@ int choose_prefix_bits(const apgk_ctx* c, uint64_t upper, int local_max) {
   if (c->cfg.prefix_bits > 0) return std::max(2, std::min(24, (int)c->cfg.prefix_bits));
   const char* env = getenv("APGK_PREFIX_BITS");
   if (env && atoi(env) > 0) return std::max(2, std::min(24, atoi(env)));
-  double target = local_max / 3.0;
+  double target = local_max / 2.2;  // the densest prefixes (AAAA...) hold ~2x the average bucket
   int P = 2;
   while (P < 24 && (double)upper / (double)(1ull << P) > target) P++;
   return P;

@@ -8,40 +8,47 @@
 // maximal run of occupied slots ("cluster") holds exactly the keys whose homes
 // fall inside it: clusters are already in ascending key order, and only the
 // handful of entries inside a cluster have to be ranked against each other.
+// There is no separate sort.
 //
-//   1. clear the table                                   [block]
-//   2. insert the bucket's keys straight from HBM        [block]   1 LDS + (CAS) + 1 RED per key
-//   3. per-thread occupied-slot counts, one block scan   [block]
-//   4. every thread walks its slots: rank inside the cluster by comparison,
-//      write (k-mer, count) at its final ascending position, update the spectrum
+//   1. clear table + occupancy bitmap (128-bit stores)                        [block]
+//   2. insert the bucket's keys straight from HBM; the thread that claims a
+//      fresh slot sets its bit in the bitmap                                  [block]
+//   3. bitmap words -> dense list of occupied slots in slot order
+//      (popcount + one block scan); two adjacent full words = a cluster too
+//      long to rank cheaply -> the bucket is deferred                         [block]
+//   4. one thread per DISTINCT key: rank inside its cluster by comparison,
+//      write (k-mer, count) at its final ascending position, update the
+//      spectrum                                                               [block, all lanes busy]
 //
-// Against k_local2 (split + warp tables + bin sort, 8.9 warp-instructions per key
-// measured) this needs ~1: there is no separate sort at all.
+// (The first version walked table SLOTS in steps 3-4; ncu showed 10 warp
+// instructions per key with ~3 of 32 lanes active.  Working on the dense list
+// and the bitmap removes that.)
 //
-// A bucket is handed to the general kernel (deferred list) when probing leaves the
-// table or a cluster grows beyond L3_MAXWALK (low-complexity sequence).
+// A bucket goes to the general kernel (deferred list) when probing leaves the
+// table or a cluster is too long (low-complexity sequence).
 #pragma once
 #include "local2.cuh"
 
 namespace apgk {
 
-constexpr int L3_SLACK = 96;     // slots past the last home slot (no wrap-around)
-constexpr int L3_MAXWALK = 64;   // longest cluster walk before the bucket is deferred
+constexpr int L3_SLACK = 96;  // slots past the last home slot (no wrap-around)
 
-// Needs 1 <= REM <= 31 and LM <= 32767 (position and count share a word).
-// shared memory: key[NS] u32 | cnt[NS] u32 | spec[SPEC_SMEM] | wsum[33] | misc[8]      NS = LM + LM/4 + SLACK
+// Needs 1 <= REM <= 31.  Shared memory (NS = slots(LM)):
+//   key[NS] u32 | cnt[NS] u32 | bitmap[NS/32] u32 | list[LM] u16 | spec[SPEC_SMEM] | wsum[40] | misc[8]
 struct Local3Smem {
-  uint32_t* key; uint32_t* cnt; uint32_t* spec; uint32_t* wsum; uint32_t* misc;
-  static __host__ __device__ size_t slots(int LM) { return (size_t)LM + LM / 4 + L3_SLACK + 32; }
+  uint32_t* key; uint32_t* cnt; uint32_t* bitmap; uint16_t* list; uint32_t* spec; uint32_t* wsum; uint32_t* misc;
+  static __host__ __device__ size_t slots(int LM) { return (((size_t)LM + LM / 4 + 1 + L3_SLACK) + 127) & ~(size_t)127; }
   __device__ __forceinline__ void carve(unsigned char* raw, int LM) {
     const size_t ns = slots(LM);
     key = (uint32_t*)raw;
     cnt = key + ns;
-    spec = cnt + ns;
+    bitmap = cnt + ns;
+    spec = bitmap + ns / 32 + 4;
     wsum = spec + SPEC_SMEM;
     misc = wsum + 40;
+    list = (uint16_t*)(misc + 8);
   }
-  static size_t bytes(int LM) { return (slots(LM) * 2 + SPEC_SMEM + 40 + 8) * 4; }
+  static size_t bytes(int LM) { return (slots(LM) * 2 + slots(LM) / 32 + 4 + SPEC_SMEM + 40 + 8) * 4 + (size_t)LM * 2 + 16; }
 };
 
 template <int NT, int W>
@@ -66,69 +73,85 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* src, BucketTable 
     const uint32_t n = (uint32_t)n64;
     const unsigned long long o = bt.bofs[b];
     const uint32_t* s = src + o;
-    const uint32_t m_home = n + (n >> 2) + 1;          // homes lie in [0, m_home)
-    const uint32_t ns = m_home + L3_SLACK;             // probing may run into the slack
+    const uint32_t m_home = n + (n >> 2) + 1;                // homes lie in [0, m_home)
+    const uint32_t ns = m_home + L3_SLACK;                   // probing may run into the slack
+    const uint32_t ns4 = (ns + 3) >> 2;                      // uint4 groups to clear (table is padded to 128 slots)
+    const uint32_t nwords = (ns + 31) >> 5;
     // ---- 1. clear
     __syncthreads();  // previous bucket fully emitted
-    for (uint32_t i = tid; i < ns; i += NT) { sm.key[i] = SLOT_EMPTY; sm.cnt[i] = 0; }
-    if (tid == 0) sm.misc[0] = 0;
-    __syncthreads();
-    // ---- 2. insert
-    for (uint32_t i = tid; i < n; i += NT) {
-      const uint32_t k = s[i];
-      uint32_t slot = __umulhi(k << up, m_home);
-      while (true) {
-        uint32_t cur = vkey[slot];
-        if (cur == SLOT_EMPTY) cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
-        if (cur == SLOT_EMPTY || cur == k) { atomicAdd(&sm.cnt[slot], 1u); break; }
-        if (++slot >= ns) { sm.misc[0] = 1u; break; }
-      }
+    {
+      uint4* k4 = reinterpret_cast<uint4*>(sm.key);
+      uint4* c4 = reinterpret_cast<uint4*>(sm.cnt);
+      const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY), z4 = make_uint4(0, 0, 0, 0);
+      for (uint32_t i = tid; i < ns4; i += NT) { k4[i] = e4; c4[i] = z4; }
+      for (uint32_t i = tid; i < nwords + 2; i += NT) sm.bitmap[i] = 0;
+      if (tid == 0) sm.misc[0] = 0;
     }
     __syncthreads();
-    // ---- 3. occupied slots before each thread's chunk
-    const uint32_t per = (ns + NT - 1) / NT;
-    const uint32_t s0 = tid * per, s1 = min(s0 + per, ns);
-    uint32_t occ = 0;
-    for (uint32_t q = s0; q < s1; q++) occ += (sm.key[q] != SLOT_EMPTY);
-    const uint32_t incl = warp_incl_scan(occ, lane);
-    if (lane == 31) sm.wsum[wid] = incl;
-    __syncthreads();
-    uint32_t before = incl - occ;
-    uint32_t total = 0;
+    // ---- 2. insert (4 independent loads in flight per thread)
+    for (uint32_t i0 = 0; i0 < n; i0 += 4 * NT) {
+      uint32_t kk[4];
 #pragma unroll
-    for (int w = 0; w < NWARP; w++) {
-      const uint32_t v = sm.wsum[w];
-      if (w < wid) before += v;
-      total += v;
-    }
-    // ---- 4. rank inside clusters; the final position is parked next to the count
-    //         (count < 2^16 | position << 16 | 1 << 31) until the whole bucket is known to be good
-    bool bad = false;
-    if (sm.misc[0] == 0) {
-      for (uint32_t q = s0; q < s1; q++) {
-        const uint32_t k = sm.key[q];
-        if (k == SLOT_EMPTY) continue;
-        uint32_t left = 0, smaller = 0;
-        for (int l = (int)q - 1; l >= 0; l--) {
-          const uint32_t kl = sm.key[l];
-          if (kl == SLOT_EMPTY) break;
-          left++;
-          smaller += kl < k;
-          if (left > L3_MAXWALK) { bad = true; break; }
+      for (int u = 0; u < 4; u++) {
+        const uint32_t i = i0 + u * NT + tid;
+        kk[u] = i < n ? s[i] : SLOT_EMPTY;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t k = kk[u];
+        if (k == SLOT_EMPTY) continue;  // remainders are < 2^31
+        uint32_t slot = __umulhi(k << up, m_home);
+        while (true) {
+          uint32_t cur = vkey[slot];
+          if (cur == SLOT_EMPTY) {
+            cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
+            if (cur == SLOT_EMPTY) {
+              atomicOr(&sm.bitmap[slot >> 5], 1u << (slot & 31));
+              cur = k;
+            }
+          }
+          if (cur == k) { atomicAdd(&sm.cnt[slot], 1u); break; }
+          if (++slot >= ns) { sm.misc[0] = 1u; break; }
         }
-        uint32_t right = 0;
-        for (uint32_t r = q + 1; r < ns; r++) {
-          const uint32_t kr = sm.key[r];
-          if (kr == SLOT_EMPTY) break;
-          smaller += kr < k;
-          if (++right > L3_MAXWALK) { bad = true; break; }
-        }
-        const uint32_t pos = before - left + smaller;
-        sm.cnt[q] = sm.cnt[q] | (pos << 16) | 0x80000000u;
-        before++;
       }
     }
-    if (bad) sm.misc[0] = 1u;
+    __syncthreads();
+    // ---- 3. dense list of occupied slots, in slot order
+    uint32_t nd_total;
+    {
+      constexpr int WPT = 2;  // bitmap words per thread; nwords <= NT * WPT is guaranteed by the host (LM vs NT)
+      uint32_t wd[WPT], c = 0;
+      bool long_cluster = false;
+#pragma unroll
+      for (int u = 0; u < WPT; u++) {
+        const uint32_t wi = tid * WPT + u;
+        wd[u] = wi < nwords ? sm.bitmap[wi] : 0u;
+        c += __popc(wd[u]);
+        if (wd[u] == 0xFFFFFFFFu && sm.bitmap[wi + 1] == 0xFFFFFFFFu) long_cluster = true;
+      }
+      if (long_cluster) sm.misc[0] = 1u;
+      const uint32_t incl = warp_incl_scan(c, lane);
+      if (lane == 31) sm.wsum[wid] = incl;
+      __syncthreads();
+      uint32_t base = incl - c;
+      nd_total = 0;
+#pragma unroll
+      for (int w = 0; w < NWARP; w++) {
+        const uint32_t v = sm.wsum[w];
+        if (w < wid) base += v;
+        nd_total += v;
+      }
+#pragma unroll
+      for (int u = 0; u < WPT; u++) {
+        uint32_t w = wd[u];
+        const uint32_t s_base = (tid * WPT + u) << 5;
+        while (w) {
+          const int bit = __ffs((int)w) - 1;
+          w &= w - 1;
+          sm.list[base++] = (uint16_t)(s_base + bit);
+        }
+      }
+    }
     __syncthreads();
     if (sm.misc[0] != 0) {  // hand the bucket to the general kernel; nothing has been written or counted
       if (tid == 0) {
@@ -137,21 +160,43 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* src, BucketTable 
       }
       continue;
     }
-    // ---- 5. emit in ascending key order (counts reuse the bucket's own, fully consumed, input range)
+    // ---- 4. one thread per distinct key: rank inside the cluster, emit (counts reuse the bucket's own,
+    //         fully consumed, input range)
     uint32_t* cnt_dst = const_cast<uint32_t*>(src) + o;
-    for (uint32_t q = s0; q < s1; q++) {
-      const uint32_t v = sm.cnt[q];
-      if (v & 0x80000000u) {
-        const uint32_t f = v & 0xFFFFu, pos = (v >> 16) & 0x7FFFu;
+    for (uint32_t j0 = 0; j0 < nd_total; j0 += NT) {
+      const uint32_t j = j0 + tid;
+      uint32_t f = 0;
+      if (j < nd_total) {
+        const uint32_t q = sm.list[j];
+        const uint32_t k = sm.key[q];
+        uint32_t left = 0, smaller = 0;
+        for (int l = (int)q - 1; l >= 0; l--) {
+          const uint32_t kl = sm.key[l];
+          if (kl == SLOT_EMPTY) break;
+          left++;
+          smaller += kl < k;
+        }
+        for (uint32_t r = q + 1; r < ns; r++) {
+          const uint32_t kr = sm.key[r];
+          if (kr == SLOT_EMPTY) break;
+          smaller += kr < k;
+        }
+        const uint32_t pos = j - left + smaller;
+        f = sm.cnt[q];
         if (ec.want_table) {
-          ec.tmp_keys[o + pos] = rebuild_key<W>(sm.key[q], (uint64_t)b, ec.rem_bits, ec.pad);
+          ec.tmp_keys[o + pos] = rebuild_key<W>(k, (uint64_t)b, ec.rem_bits, ec.pad);
           cnt_dst[pos] = f;
         }
+      }
+      // spectrum: singletons dominate, so they are counted per warp with one ballot
+      const uint32_t ones = __ballot_sync(0xffffffffu, f == 1u);
+      if (lane == 0 && ones) atomicAdd(&sm.spec[1], (uint32_t)__popc(ones));
+      if (f > 1u) {
         if (f < SPEC_SMEM) atomicAdd(&sm.spec[f], 1u);
         else spec_add_global(ec.spec_dense, ec.spec_ovf, ec.spec_ovf_cap, f);
       }
     }
-    if (tid == 0) nd_out[b] = total;
+    if (tid == 0) nd_out[b] = nd_total;
   }
   __syncthreads();
   for (int i = tid; i < SPEC_SMEM; i += NT) {
