@@ -50,6 +50,13 @@ struct DevBuf {
   template <typename T> T* as() const { return (T*)p; }
 };
 
+// host-side description of a partition level, mirrored on the device in ctx->plan
+struct HostPlan {
+  std::vector<uint32_t> seg_tile0, seg_chunk0;
+  std::vector<uint64_t> seg_start;
+  LevelPlan lp{};
+};
+
 }  // namespace
 
 struct apgk_ctx {
@@ -63,7 +70,7 @@ struct apgk_ctx {
   DevBuf bases, starts, staging, off_dev;
   uint64_t total_bases = 0, n_reads = 0;
   // ---- pipeline buffers
-  DevBuf A, B, cnt16, base32, chunksum, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
+  DevBuf A, B, T, chunksum, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
       scratch, stacks, spec_dense, spec_ovf, misc, deferred;
   // ---- results
   DevBuf out_keys, out_cnt;
@@ -80,6 +87,8 @@ struct apgk_ctx {
   uint32_t owner_ranks = 0;
   uint32_t owner_tiles = 0;
   std::vector<uint64_t> owner_counts;
+  HostPlan owner_plan;
+  DevBuf owner_plan_dev;
   // ---- instrumentation
   cudaEvent_t ev[APGK_N_STAGES][2]{};
   bool ev_used[APGK_N_STAGES]{};
@@ -118,19 +127,17 @@ int words_for(int K) { return (2 * K + 63) / 64; }
 
 // tile geometry per key width
 template <int W> struct Geo;
-template <> struct Geo<1> { static constexpr int NT0 = 1024; static constexpr int NT1 = 1024; static constexpr uint32_t TILE1 = 16384; static constexpr int LM_KEY = 4096; };
-template <> struct Geo<2> { static constexpr int NT0 = 512;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 8192;  static constexpr int LM_KEY = 2048; };
-template <> struct Geo<3> { static constexpr int NT0 = 256;  static constexpr int NT1 = 512;  static constexpr uint32_t TILE1 = 5120;  static constexpr int LM_KEY = 2048; };
+// NT0: threads of a level-0 CTA (16 windows each); NT1 / TILE1: threads and keys of a key-array tile
+// (TILE1 == NT1 * TileItems<Key<W>>::N, the keys live in registers during ranking)
+#ifndef APGK_NT
+#define APGK_NT 1024
+#endif
+template <> struct Geo<1> { static constexpr int NT0 = APGK_NT; static constexpr int NT1 = APGK_NT; static constexpr uint32_t TILE1 = APGK_NT * 16; static constexpr int LM_KEY = 4096; };
+template <> struct Geo<2> { static constexpr int NT0 = 512; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 8;  static constexpr int LM_KEY = 2048; };
+template <> struct Geo<3> { static constexpr int NT0 = 256; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 5;  static constexpr int LM_KEY = 2048; };
 constexpr int LM_U32 = 5120;
 constexpr int L3_NT = 512;
 constexpr int COL_NT = 1024;
-
-// host-side description of a partition level, mirrored on the device in ctx->plan
-struct HostPlan {
-  std::vector<uint32_t> seg_tile0, seg_chunk0;
-  std::vector<uint64_t> seg_start;
-  LevelPlan lp{};
-};
 
 void build_plan(HostPlan& hp, const std::vector<uint64_t>& seg_sizes, uint32_t tile_elems, int bins) {
   const int S = (int)seg_sizes.size();
@@ -142,8 +149,10 @@ void build_plan(HostPlan& hp, const std::vector<uint64_t>& seg_sizes, uint32_t t
     hp.seg_start[s + 1] = hp.seg_start[s] + seg_sizes[s];
     max_tiles = std::max(max_tiles, t);
   }
-  int ct = (int)std::ceil(std::sqrt((double)max_tiles));
-  ct = std::max(8, std::min(ct, 2048));
+  // a scatter CTA walks one chunk of tiles; ~4+ chunks per segment keep the CTAs balanced
+  int ct = (int)((max_tiles + 3) / 4);
+  ct = std::max(8, std::min(ct, 128));
+  if (const char* e = getenv("APGK_CT")) { if (atoi(e) > 0) ct = atoi(e); }  // tuning knob
   for (int s = 0; s < S; s++) {
     uint32_t t = hp.seg_tile0[s + 1] - hp.seg_tile0[s];
     hp.seg_chunk0[s + 1] = hp.seg_chunk0[s] + (t + ct - 1) / ct;
@@ -168,22 +177,16 @@ int upload_plan(apgk_ctx* c, HostPlan& hp) {
   return APGK_OK;
 }
 
-// column scan: cnt16 -> base32 (+ segtot, bstart32, optional absolute bucket offsets)
+// per-chunk digit counts (chunksum, written by the hist kernels) -> per-chunk exclusive prefixes,
+// bucket totals (segtot), bucket starts inside their segment (bstart32), optional absolute bucket offsets
 int column_scan(apgk_ctx* c, const HostPlan& hp, int fold, unsigned long long* bofs_out) {
   const LevelPlan& lp = hp.lp;
   if (lp.n_chunks == 0) return APGK_OK;
-  CU(c->chunksum.ensure((size_t)lp.n_chunks * lp.bins * 4));
   CU(c->segtot.ensure((size_t)lp.n_segments * lp.bins * 8));
   CU(c->bstart32.ensure((size_t)lp.n_segments * lp.bins * 4));
-  CU(c->base32.ensure((size_t)lp.n_tiles * lp.bins * 4));
-  k_colsum<COL_NT><<<lp.n_chunks, COL_NT, 0, c->stream>>>(lp, c->cnt16.as<uint16_t>(), c->chunksum.as<uint32_t>());
-  LAUNCHED();
   k_segscan<COL_NT><<<lp.n_segments, COL_NT, 0, c->stream>>>(lp, c->chunksum.as<uint32_t>(),
                                                             c->segtot.as<unsigned long long>(),
-                                                            c->bstart32.as<uint32_t>(), bofs_out);
-  LAUNCHED();
-  k_colapply<COL_NT><<<lp.n_chunks, COL_NT, 0, c->stream>>>(lp, c->cnt16.as<uint16_t>(), c->chunksum.as<uint32_t>(),
-                                                           c->bstart32.as<uint32_t>(), fold, c->base32.as<uint32_t>());
+                                                            c->bstart32.as<uint32_t>(), bofs_out, fold);
   LAUNCHED();
   return APGK_OK;
 }
@@ -300,7 +303,9 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     upper = upper > lost ? upper - lost : 1;
   }
   // decide element type of the level-1 buffer first (it fixes LOCAL_MAX, which fixes P)
-  int P = choose_prefix_bits(c, upper, LM_U32);
+  int lm_u32 = LM_U32;
+  if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) lm_u32 = atoi(e); }
+  int P = choose_prefix_bits(c, upper, lm_u32);
   make_geom(c, P);
   const bool u32 = (W == 1 && c->geom.REM <= 32);
   if (!u32) {
@@ -329,14 +334,20 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
 
 template <typename ElemB, int W>
 struct ScatterSel {  // level-1 scatter kernel: Key<W> in, ElemB out
-  static auto kernel() { return k_scatter_keys<Key<W>, ElemB, Geo<W>::NT1>; }
+  static auto kernel() { return k_scatter_keys<Key<W>, ElemB, Geo<W>::NT1, DIGIT_BITS>; }
 };
 
 template <int W, typename ElemB>
 int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   const KeyGeom g = c->geom;
   const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
-  const int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : Geo<W>::LM_KEY;
+  int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : Geo<W>::LM_KEY;
+  int l3_nt = L3_NT;
+  if (std::is_same<ElemB, uint32_t>::value) {  // tuning knobs
+    if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) local_max = atoi(e); }
+    if (const char* e = getenv("APGK_L3_NT")) { if (atoi(e) == 256 || atoi(e) == 512) l3_nt = atoi(e); }
+  }
+  const bool use_l3 = std::is_same<ElemB, uint32_t>::value && g.REM >= 1 && g.REM <= 31;
   c->elem_bytes = sizeof(ElemB);
   c->local_max = (uint32_t)local_max;
   c->nb1 = (uint32_t)bins0 * (uint32_t)bins1;
@@ -344,7 +355,8 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
 
   // ================= level 0
-  DigitSpec ds0{DIGIT_BITS, g.TB - g.D0, g.D0, g.pad, 0, 0u, (uint32_t)bins0};
+  DigitSpec ds0{DIGIT_BITS, g.TB - g.D0, g.D0, g.pad, 0};
+  const DigitFn<DIGIT_BITS> dg0 = make_digit_fn<DIGIT_BITS>(ds0);
   HostPlan hp0;
   const uint32_t tile0 = dev_keys ? Geo<W>::TILE1 : (uint32_t)Geo<W>::NT0 * POS_PER_THREAD;
   {
@@ -359,14 +371,14 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     return APGK_OK;
   }
   { int rc = upload_plan(c, hp0); if (rc) return rc; }
-  CU(c->cnt16.ensure((size_t)hp0.lp.n_tiles * bins0 * 2));
+  CU(c->chunksum.ensure((size_t)hp0.lp.n_chunks * bins0 * 4));
   stage_begin(c, ST_HIST0);
   if (dev_keys) {
-    k_hist_keys<Key<W>, Geo<W>::NT1><<<hp0.lp.n_tiles, Geo<W>::NT1, bins0 * 4, c->stream>>>(dev_keys, hp0.lp, ds0,
-                                                                                             c->cnt16.as<uint16_t>());
+    k_hist_keys<Key<W>, Geo<W>::NT1, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT1, bins0 * 4, c->stream>>>(
+        dev_keys, hp0.lp, dg0, c->chunksum.as<uint32_t>());
   } else {
-    k_hist_reads<W, Geo<W>::NT0><<<hp0.lp.n_tiles, Geo<W>::NT0, bins0 * 4, c->stream>>>(read_store(c), ds0, bins0,
-                                                                                         c->cnt16.as<uint16_t>());
+    k_hist_reads<W, Geo<W>::NT0, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT0, bins0 * 4, c->stream>>>(
+        read_store(c), dg0, hp0.lp, c->chunksum.as<uint32_t>());
   }
   LAUNCHED();
   stage_end(c, ST_HIST0);
@@ -394,25 +406,24 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   CU(c->A.ensure(std::max<size_t>(N, 1) * sizeof(Key<W>)));
   stage_begin(c, ST_SCATTER0);
   if (dev_keys) {
-    auto kern = k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1>;
+    auto kern = k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS>;
     const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
     { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    kern<<<hp0.lp.n_tiles, Geo<W>::NT1, sm, c->stream>>>(dev_keys, hp0.lp, ds0, c->cnt16.as<uint16_t>(),
-                                                         c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(), 0, 0,
-                                                         c->A.as<Key<W>>());
+    kern<<<hp0.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(dev_keys, hp0.lp, dg0, c->chunksum.as<uint32_t>(),
+                                                          c->bstart64.as<uint64_t>(), 0, 0, c->A.as<Key<W>>());
   } else {
-    auto kern = k_scatter_reads<W, Geo<W>::NT0>;
+    auto kern = k_scatter_reads<W, Geo<W>::NT0, DIGIT_BITS>;
     const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
     { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    kern<<<hp0.lp.n_tiles, Geo<W>::NT0, sm, c->stream>>>(read_store(c), ds0, bins0, c->cnt16.as<uint16_t>(),
-                                                         c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(),
-                                                         c->A.as<Key<W>>(), (unsigned long long)N);
+    kern<<<hp0.lp.n_chunks, Geo<W>::NT0, sm, c->stream>>>(read_store(c), dg0, hp0.lp, c->chunksum.as<uint32_t>(),
+                                                          c->bstart64.as<uint64_t>(), c->A.as<Key<W>>());
   }
   LAUNCHED();
   stage_end(c, ST_SCATTER0);
 
   // ================= level 1
-  DigitSpec ds1{DIGIT_BITS, g.TB - g.D0 - g.D1, g.D1, g.pad, 0, 0u, (uint32_t)bins1};
+  DigitSpec ds1{DIGIT_BITS, g.TB - g.D0 - g.D1, g.D1, g.pad, 0};
+  const DigitFn<DIGIT_BITS> dg1 = make_digit_fn<DIGIT_BITS>(ds1);
   HostPlan hp1;
   build_plan(hp1, tot0, Geo<W>::TILE1, bins1);
   { int rc = upload_plan(c, hp1); if (rc) return rc; }
@@ -420,10 +431,10 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   CU(c->stats.ensure(64));
   CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
   if (hp1.lp.n_tiles) {
-    CU(c->cnt16.ensure((size_t)hp1.lp.n_tiles * bins1 * 2));
+    CU(c->chunksum.ensure((size_t)hp1.lp.n_chunks * bins1 * 4));
     stage_begin(c, ST_HIST1);
-    k_hist_keys<Key<W>, Geo<W>::NT1><<<hp1.lp.n_tiles, Geo<W>::NT1, bins1 * 4, c->stream>>>(
-        c->A.as<Key<W>>(), hp1.lp, ds1, c->cnt16.as<uint16_t>());
+    k_hist_keys<Key<W>, Geo<W>::NT1, DIGIT_BITS><<<hp1.lp.n_chunks, Geo<W>::NT1, bins1 * 4, c->stream>>>(
+        c->A.as<Key<W>>(), hp1.lp, dg1, c->chunksum.as<uint32_t>());
     LAUNCHED();
     stage_end(c, ST_HIST1);
   }
@@ -440,7 +451,8 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   CU(c->big_list.ensure(((size_t)N / local_max + 16) * 4));
   const uint32_t big_cap = (uint32_t)(N / local_max + 16);
   k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
-                                                         (uint32_t)local_max, c->big_list.as<uint32_t>(), big_cap,
+                                                         use_l3 ? 0xFFFFFFFFu : (uint32_t)local_max,
+                                                         c->big_list.as<uint32_t>(), big_cap,
                                                          c->stats.as<unsigned long long>());
   LAUNCHED();
   stage_end(c, ST_SCAN1);
@@ -472,9 +484,8 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     auto kern = ScatterSel<ElemB, W>::kernel();
     const size_t sm = scatter_smem_bytes<Key<W>>(Geo<W>::TILE1, bins1);
     { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    kern<<<hp1.lp.n_tiles, Geo<W>::NT1, sm, c->stream>>>(c->A.as<Key<W>>(), hp1.lp, ds1, c->cnt16.as<uint16_t>(),
-                                                         c->base32.as<uint32_t>(), nullptr, g.pad, g.REM,
-                                                         c->B.as<ElemB>());
+    kern<<<hp1.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(c->A.as<Key<W>>(), hp1.lp, dg1, c->chunksum.as<uint32_t>(),
+                                                          nullptr, g.pad, g.REM, c->B.as<ElemB>());
     LAUNCHED();
     stage_end(c, ST_SCATTER1);
   }
@@ -487,6 +498,8 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   EmitCtx<W> ec;
   ec.want_table = want_table; ec.rem_bits = g.REM; ec.pad = g.pad;
   ec.tmp_keys = c->A.as<Key<W>>();
+  if (want_table) CU(c->T.ensure(std::max<size_t>(N, 1) * 4));
+  ec.tmp_cnt = c->T.as<uint32_t>();
   ec.spec_dense = c->spec_dense.as<unsigned long long>();
   ec.spec_ovf = c->spec_ovf.as<unsigned long long>();
   ec.spec_ovf_cap = (uint32_t)(N / SPEC_DENSE + 8);
@@ -495,26 +508,27 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   bt.bsize = c->segtot.as<unsigned long long>();
   bt.nb = c->nb1; bt.local_max = (uint32_t)local_max;
   {
-    // fast kernel over all buckets; buckets it cannot take land on the deferred list ...
     CU(c->deferred.ensure(((size_t)c->nb1 + 1) * 4));
     CU(cudaMemsetAsync(c->deferred.p, 0, 4, c->stream));
     stage_begin(c, ST_LOCAL);
-    bool launched = false;
-    if constexpr (std::is_same<ElemB, uint32_t>::value) {
-      if (g.REM >= 1 && g.REM <= 31) {  // order-preserving hash kernel
-        auto kern3 = k_local3<L3_NT, W>;
-        const size_t sm3 = Local3Smem::bytes(local_max);
-        { int rc = set_smem(c, kern3, sm3); if (rc) return rc; }
-        int occ3 = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kern3, L3_NT, sm3));
-        const uint32_t grid3 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ3, 1)));
-        kern3<<<grid3, L3_NT, sm3, c->stream>>>(c->B.as<uint32_t>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
-                                                c->deferred.as<uint32_t>(), c->nb1);
+    if (use_l3) {
+      // 32-bit remainders: order-preserving hash kernel; it takes every bucket size (range splitting)
+      if constexpr (std::is_same<ElemB, uint32_t>::value) {
+        auto launch3 = [&](auto kern3, int nt) -> int {
+          const size_t sm3 = Local3Smem::bytes(local_max);
+          { int rc = set_smem(c, kern3, sm3); if (rc) return rc; }
+          int occ3 = 1;
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kern3, nt, sm3));
+          const uint32_t grid3 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ3, 1)));
+          kern3<<<grid3, nt, sm3, c->stream>>>(c->B.as<uint32_t>(), bt, g.REM, ec, c->nd.as<uint32_t>());
+          return APGK_OK;
+        };
+        int rc3 = l3_nt == 256 ? launch3(k_local3<256, W>, 256) : launch3(k_local3<512, W>, 512);
+        if (rc3) return rc3;
         LAUNCHED();
-        launched = true;
       }
-    }
-    if (!launched) {
+    } else {
+      // general element types: warp-table kernel; buckets it cannot take land on the deferred list ...
       auto kern2 = k_local2<ElemB, W>;
       const size_t sm2 = Local2Smem<ElemB>::bytes(local_max);
       { int rc = set_smem(c, kern2, sm2); if (rc) return rc; }
@@ -524,17 +538,17 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
       kern2<<<grid2, L2_NT, sm2, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
                                               c->deferred.as<uint32_t>(), c->nb1);
       LAUNCHED();
+      // ... which the barrier-heavy general kernel then walks (normally empty)
+      auto kern = k_local<ElemB, W>;
+      const size_t sm = LocalSmem<ElemB>::bytes(local_max);
+      { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+      int occ = 1;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
+      const uint32_t grid = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ, 1)));
+      kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
+                                              c->deferred.as<uint32_t>(), c->nb1);
+      LAUNCHED();
     }
-    // ... which the barrier-heavy general kernel then walks (normally empty)
-    auto kern = k_local<ElemB, W>;
-    const size_t sm = LocalSmem<ElemB>::bytes(local_max);
-    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
-    const uint32_t grid = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ, 1)));
-    kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
-                                            c->deferred.as<uint32_t>(), c->nb1);
-    LAUNCHED();
     stage_end(c, ST_LOCAL);
   }
   if (c->n_big) {
@@ -583,7 +597,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     if (want_table) {
       CU(c->out_keys.ensure(std::max<size_t>(total, 1) * sizeof(Key<W>)));
       CU(c->out_cnt.ensure(std::max<size_t>(total, 1) * 4));
-      k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(c->A.as<Key<W>>(), c->B.as<unsigned char>(), (uint32_t)sizeof(ElemB),
+      k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(c->A.as<Key<W>>(), c->T.as<uint32_t>(),
                                                        c->bofs.as<unsigned long long>(),
                                                        c->out_off.as<unsigned long long>(), c->nb1,
                                                        c->out_keys.as<Key<W>>(), c->out_cnt.as<uint32_t>());
@@ -679,19 +693,29 @@ int read_freqs_impl(apgk_ctx* c, uint64_t first, uint64_t n, uint32_t* out) {
 // ---------------------------------------------------------------- owner partition (multi-GPU shuffle, sender side)
 template <int W>
 int owner_plan_impl(apgk_ctx* c, uint32_t n_ranks, uint64_t* counts_out) {
-  DigitSpec ds{DIGIT_OWNER, 0, 0, 0, n_ranks, 0u, n_ranks};
+  DigitSpec ds{DIGIT_OWNER, 0, 0, 0, n_ranks};
+  const DigitFn<DIGIT_OWNER> dg = make_digit_fn<DIGIT_OWNER>(ds);
   const uint32_t tile0 = (uint32_t)Geo<W>::NT0 * POS_PER_THREAD;
-  HostPlan hp;
+  HostPlan& hp = c->owner_plan;
   std::vector<uint64_t> one{c->total_bases};
   build_plan(hp, one, tile0, (int)n_ranks);
   c->owner_counts.assign(n_ranks, 0);
   c->owner_ranks = n_ranks; c->owner_tiles = hp.lp.n_tiles;
   if (hp.lp.n_tiles) {
-    { int rc = upload_plan(c, hp); if (rc) return rc; }
-    CU(c->cnt16.ensure((size_t)hp.lp.n_tiles * n_ranks * 2));
+    // the owner plan keeps its own device copy: apgk_owner_scatter runs later
+    const size_t S1 = hp.seg_tile0.size();
+    CU(c->owner_plan_dev.ensure(S1 * 16 + 64));
+    unsigned char* d = c->owner_plan_dev.as<unsigned char>();
+    CU(cudaMemcpyAsync(d, hp.seg_start.data(), S1 * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + S1 * 8, hp.seg_tile0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + S1 * 12, hp.seg_chunk0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
+    hp.lp.seg_start = (const uint64_t*)d;
+    hp.lp.seg_tile0 = (const uint32_t*)(d + S1 * 8);
+    hp.lp.seg_chunk0 = (const uint32_t*)(d + S1 * 12);
+    CU(c->chunksum.ensure((size_t)hp.lp.n_chunks * n_ranks * 4));
     stage_begin(c, ST_OWNER);
-    k_hist_reads<W, Geo<W>::NT0><<<hp.lp.n_tiles, Geo<W>::NT0, n_ranks * 4, c->stream>>>(read_store(c), ds, (int)n_ranks,
-                                                                                          c->cnt16.as<uint16_t>());
+    k_hist_reads<W, Geo<W>::NT0, DIGIT_OWNER><<<hp.lp.n_chunks, Geo<W>::NT0, n_ranks * 4, c->stream>>>(
+        read_store(c), dg, hp.lp, c->chunksum.as<uint32_t>());
     LAUNCHED();
     { int rc = column_scan(c, hp, 0, nullptr); if (rc) return rc; }
     CU(cudaMemcpyAsync(c->owner_counts.data(), c->segtot.p, (size_t)n_ranks * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -708,17 +732,18 @@ template <int W>
 int owner_scatter_impl(apgk_ctx* c, uint64_t* d_out) {
   const uint32_t n_ranks = c->owner_ranks;
   if (!c->owner_tiles) return APGK_OK;
-  DigitSpec ds{DIGIT_OWNER, 0, 0, 0, n_ranks, 0u, n_ranks};
+  DigitSpec ds{DIGIT_OWNER, 0, 0, 0, n_ranks};
+  const DigitFn<DIGIT_OWNER> dg = make_digit_fn<DIGIT_OWNER>(ds);
   std::vector<uint64_t> bstart(n_ranks + 1, 0);
   for (uint32_t r = 0; r < n_ranks; r++) bstart[r + 1] = bstart[r] + c->owner_counts[r];
   CU(c->bstart64.ensure(((size_t)n_ranks + 1) * 8));
   CU(cudaMemcpyAsync(c->bstart64.p, bstart.data(), ((size_t)n_ranks + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  auto kern = k_scatter_reads<W, Geo<W>::NT0>;
+  auto kern = k_scatter_reads<W, Geo<W>::NT0, DIGIT_OWNER>;
   const size_t sm = scatter_smem_bytes<Key<W>>((uint32_t)Geo<W>::NT0 * POS_PER_THREAD, (int)n_ranks);
   { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-  kern<<<c->owner_tiles, Geo<W>::NT0, sm, c->stream>>>(read_store(c), ds, (int)n_ranks, c->cnt16.as<uint16_t>(),
-                                                       c->base32.as<uint32_t>(), c->bstart64.as<uint64_t>(),
-                                                       (Key<W>*)d_out, (unsigned long long)bstart[n_ranks]);
+  kern<<<c->owner_plan.lp.n_chunks, Geo<W>::NT0, sm, c->stream>>>(read_store(c), dg, c->owner_plan.lp,
+                                                                  c->chunksum.as<uint32_t>(), c->bstart64.as<uint64_t>(),
+                                                                  (Key<W>*)d_out);
   LAUNCHED();
   stage_end(c, ST_OWNER);
   CU(cudaStreamSynchronize(c->stream));
@@ -790,10 +815,10 @@ void apgk_destroy(apgk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->cnt16, &c->base32, &c->chunksum,
+  DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum,
                    &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
                    &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc, &c->deferred,
-                   &c->out_keys, &c->out_cnt};
+                   &c->out_keys, &c->out_cnt, &c->owner_plan_dev};
   for (DevBuf* b : all) b->release();
   for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
   cudaStreamDestroy(c->stream);

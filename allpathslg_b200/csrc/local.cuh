@@ -52,6 +52,7 @@ struct EmitCtx {
   int want_table;
   int rem_bits, pad;            // to rebuild a full key from (bucket prefix, remainder)
   Key<W>* tmp_keys;             // temp keys, indexed by element offset (the dead level-0 buffer)
+  uint32_t* tmp_cnt;            // temp counts, same indexing (own buffer: passes may re-read their input)
   unsigned long long* spec_dense;  // [SPEC_DENSE] device spectrum
   unsigned long long* spec_ovf;    // overflow list: [0] = count, then values
   uint32_t spec_ovf_cap;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(LOCAL_NT) k_local(const Elem* __restrict__ src
     }
     if (n > bt.local_max) continue;  // k_big's job
     const unsigned long long o = bt.bofs[b];
-    uint32_t* cnt_dst = (uint32_t*)((unsigned char*)src + o * sizeof(Elem));
+    uint32_t* cnt_dst = ec.tmp_cnt + o;
     uint32_t nd = local_bucket<Elem, W>(sm, src + o, (uint32_t)n, sort_bits, (uint64_t)b, ec, o, cnt_dst);
     if (threadIdx.x == 0) nd_out[b] = nd;
   }
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(LOCAL_NT) k_big(Elem* __restrict__ src, Bucket
     __syncthreads();
     const unsigned long long so = (unsigned long long)sm.misc[2] | ((unsigned long long)sm.misc[3] << 32);
     Elem* bufs[2] = {src + o, (Elem*)bp.scratch + so};
-    uint32_t* cnt_base = (uint32_t*)((unsigned char*)src + o * sizeof(Elem));
+    uint32_t* cnt_base = ec.tmp_cnt + o;
     unsigned long long run_nd = 0;
     while (true) {
       const uint32_t sp = sm.misc[1];

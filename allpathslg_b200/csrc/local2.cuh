@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(L2_NT) k_local2(const Elem* __restrict__ src, 
       }
     }
     __syncthreads();
-    uint32_t* cnt_dst = (uint32_t*)((unsigned char*)src + o * sizeof(Elem));
+    uint32_t* cnt_dst = ec.tmp_cnt + o;
     for (int q = wid; q < S; q += L2_NW) {
       const uint32_t base = sm.sstart[q], nd = sm.snd[q], ro = sm.roff[q];
       for (uint32_t j = lane; j < nd; j += 32) {

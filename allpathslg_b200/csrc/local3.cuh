@@ -2,7 +2,7 @@
 //
 // Keys of one bucket share their leading bits, so the remainder r (< 2^REM) of a
 // random-looking genome is spread evenly.  The home slot of a key is therefore
-// chosen MONOTONE in the key:   home(r) = floor(r * M / 2^REM),  M ~ 1.25 n.
+// chosen MONOTONE in the key:   home(r) = floor(r * M / 2^REM).
 // Insertion is plain linear probing without wrap-around (one CAS + one ADD per
 // key instance groups identical keys), and because the hash is monotone every
 // maximal run of occupied slots ("cluster") holds exactly the keys whose homes
@@ -10,33 +10,38 @@
 // handful of entries inside a cluster have to be ranked against each other.
 // There is no separate sort.
 //
+// A bucket is processed as a stack of DYADIC KEY RANGES (d, i) = "the keys whose
+// top d remainder bits equal i", starting with the whole bucket (0, 0).  For one range:
+//
 //   1. clear table + occupancy bitmap (128-bit stores)                        [block]
-//   2. insert the bucket's keys straight from HBM; the thread that claims a
-//      fresh slot sets its bit in the bitmap                                  [block]
+//   2. insert the range's keys straight from HBM/L2 (monotone home of the bits
+//      below the range prefix); the thread that claims a fresh slot sets its
+//      bit in the bitmap                                                      [block]
 //   3. bitmap words -> dense list of occupied slots in slot order
-//      (popcount + one block scan); two adjacent full words = a cluster too
-//      long to rank cheaply -> the bucket is deferred                         [block]
+//      (popcount + one block scan)                                            [block]
 //   4. one thread per DISTINCT key: rank inside its cluster by comparison,
 //      write (k-mer, count) at its final ascending position, update the
 //      spectrum                                                               [block, all lanes busy]
 //
-// (The first version walked table SLOTS in steps 3-4; ncu showed 10 warp
-// instructions per key with ~3 of 32 lanes active.  Working on the dense list
-// and the bitmap removes that.)
-//
-// A bucket goes to the general kernel (deferred list) when probing leaves the
-// table or a cluster is too long (low-complexity sequence).
+// If the table overflows (too many distinct keys for its M slots) or a cluster
+// gets too long to rank cheaply, nothing has been written yet and the range is
+// split into its two halves (d+1, 2i), (d+1, 2i+1) -- so oversize and skewed
+// buckets take more passes instead of a different kernel.  A range of one key
+// value (d == REM) always fits.  (The first version walked table SLOTS in steps
+// 3-4: ncu showed 10 warp instructions per key with ~3 of 32 lanes active.)
 #pragma once
 #include "local2.cuh"
 
 namespace apgk {
 
-constexpr int L3_SLACK = 96;  // slots past the last home slot (no wrap-around)
+constexpr int L3_SLACK = 96;    // slots past the last home slot (no wrap-around)
+constexpr int L3_STACK = 72;    // >= 2 * 32 pending ranges
 
 // Needs 1 <= REM <= 31.  Shared memory (NS = slots(LM)):
-//   key[NS] u32 | cnt[NS] u32 | bitmap[NS/32] u32 | list[LM] u16 | spec[SPEC_SMEM] | wsum[40] | misc[8]
+//   key[NS] u32 | cnt[NS] u32 | bitmap[NS/32] u32 | spec[SPEC_SMEM] | wsum[40] | misc[8] | stack[2*L3_STACK] | list[LM] u16
 struct Local3Smem {
   uint32_t* key; uint32_t* cnt; uint32_t* bitmap; uint16_t* list; uint32_t* spec; uint32_t* wsum; uint32_t* misc;
+  uint32_t* stack;
   static __host__ __device__ size_t slots(int LM) { return (((size_t)LM + LM / 4 + 1 + L3_SLACK) + 127) & ~(size_t)127; }
   __device__ __forceinline__ void carve(unsigned char* raw, int LM) {
     const size_t ns = slots(LM);
@@ -46,157 +51,186 @@ struct Local3Smem {
     spec = bitmap + ns / 32 + 4;
     wsum = spec + SPEC_SMEM;
     misc = wsum + 40;
-    list = (uint16_t*)(misc + 8);
+    stack = misc + 8;
+    list = (uint16_t*)(stack + 2 * L3_STACK);
   }
-  static size_t bytes(int LM) { return (slots(LM) * 2 + slots(LM) / 32 + 4 + SPEC_SMEM + 40 + 8) * 4 + (size_t)LM * 2 + 16; }
+  static size_t bytes(int LM) {
+    return (slots(LM) * 2 + slots(LM) / 32 + 4 + SPEC_SMEM + 40 + 8 + 2 * L3_STACK) * 4 + ((size_t)LM + LM / 4 + 128) * 2 + 16;
+  }
 };
 
 template <int NT, int W>
-__global__ void __launch_bounds__(NT) k_local3(const uint32_t* src, BucketTable bt, int rem_bits, EmitCtx<W> ec,
-                                               uint32_t* __restrict__ nd_out, uint32_t* __restrict__ deferred,
-                                               uint32_t deferred_cap) {
+__global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src, BucketTable bt, int rem_bits, EmitCtx<W> ec,
+                                               uint32_t* __restrict__ nd_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Local3Smem sm;
-  sm.carve(smem_raw, (int)bt.local_max);
+  const int LM = (int)bt.local_max;
+  sm.carve(smem_raw, LM);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NWARP = NT / 32;
   for (int i = tid; i < SPEC_SMEM; i += NT) sm.spec[i] = 0;
-  volatile uint32_t* vkey = sm.key;
-  const int up = 32 - rem_bits;  // remainder left-aligned in 32 bits
+  const int up = 32 - rem_bits;                       // remainder left-aligned in 32 bits
+  const uint32_t m_cap = (uint32_t)LM + (uint32_t)LM / 4 + 1;  // homes of a full-size pass
   for (uint32_t b = blockIdx.x; b < bt.nb; b += gridDim.x) {
     const unsigned long long n64 = bt.bsize[b];
     if (n64 == 0) {
       if (tid == 0) nd_out[b] = 0;
       continue;
     }
-    if (n64 > bt.local_max) continue;  // k_big's job
-    const uint32_t n = (uint32_t)n64;
     const unsigned long long o = bt.bofs[b];
     const uint32_t* s = src + o;
-    const uint32_t m_home = n + (n >> 2) + 1;                // homes lie in [0, m_home)
-    const uint32_t ns = m_home + L3_SLACK;                   // probing may run into the slack
-    const uint32_t ns4 = (ns + 3) >> 2;                      // uint4 groups to clear (table is padded to 128 slots)
+    // a pass over a small bucket only needs a small table
+    const uint32_t m_home = n64 < (unsigned long long)LM ? (uint32_t)n64 + ((uint32_t)n64 >> 2) + 1 : m_cap;
+    const uint32_t ns = m_home + L3_SLACK;             // probing may run into the slack
+    const uint32_t ns4 = (ns + 3) >> 2;                // uint4 groups to clear (table is padded to 128 slots)
     const uint32_t nwords = (ns + 31) >> 5;
-    // ---- 1. clear
-    __syncthreads();  // previous bucket fully emitted
-    {
-      uint4* k4 = reinterpret_cast<uint4*>(sm.key);
-      uint4* c4 = reinterpret_cast<uint4*>(sm.cnt);
-      const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY), z4 = make_uint4(0, 0, 0, 0);
-      for (uint32_t i = tid; i < ns4; i += NT) { k4[i] = e4; c4[i] = z4; }
-      for (uint32_t i = tid; i < nwords + 2; i += NT) sm.bitmap[i] = 0;
-      if (tid == 0) sm.misc[0] = 0;
-    }
-    __syncthreads();
-    // ---- 2. insert (4 independent loads in flight per thread)
-    for (uint32_t i0 = 0; i0 < n; i0 += 4 * NT) {
-      uint32_t kk[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t i = i0 + u * NT + tid;
-        kk[u] = i < n ? s[i] : SLOT_EMPTY;
+    volatile uint32_t* vmisc = sm.misc;
+    uint32_t run_nd = 0;                               // records already emitted for this bucket
+    bool first = true;                                 // the first range is the whole bucket: (d=0, i=0)
+    while (true) {
+      __syncthreads();  // previous pass / previous bucket fully emitted (table, stack and misc are reused)
+      uint32_t sp = 1, rd = 0, ri = 0;
+      if (!first) {
+        sp = sm.misc[1];
+        if (sp == 0) break;
+        rd = sm.stack[2 * (sp - 1)];
+        ri = sm.stack[2 * (sp - 1) + 1];
       }
+      first = false;
+      // ---- 1. clear
+      {
+        uint4* k4 = reinterpret_cast<uint4*>(sm.key);
+        uint4* c4 = reinterpret_cast<uint4*>(sm.cnt);
+        const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY), z4 = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < ns4; i += NT) { k4[i] = e4; c4[i] = z4; }
+        for (uint32_t i = tid; i < nwords + 2; i += NT) sm.bitmap[i] = 0;
+        if (tid == 0) sm.misc[0] = 0;   // "this pass failed" flag; nobody touches it between the two barriers
+      }
+      __syncthreads();
+      if (tid == 0) sm.misc[1] = sp - 1;  // pop (every thread has read sp and the range before the barrier)
+      // ---- 2. insert the keys of range (rd, ri); 4 independent loads in flight per thread
+      const uint32_t pshift = 32 - rd;                 // x >> pshift = top rd bits (rd == 0: everything matches)
+      for (unsigned long long i0 = 0; i0 < n64; i0 += 4ull * NT) {
+        uint32_t kk[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t k = kk[u];
-        if (k == SLOT_EMPTY) continue;  // remainders are < 2^31
-        uint32_t slot = __umulhi(k << up, m_home);
-        while (true) {
-          uint32_t cur = vkey[slot];
-          if (cur == SLOT_EMPTY) {
+        for (int u = 0; u < 4; u++) {
+          const unsigned long long i = i0 + (unsigned long long)u * NT + tid;
+          kk[u] = i < n64 ? s[i] : SLOT_EMPTY;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t k = kk[u];
+          if (k == SLOT_EMPTY) continue;               // remainders are < 2^31
+          const uint32_t x = k << up;
+          if (rd && (x >> pshift) != ri) continue;     // not in this range
+          uint32_t slot = __umulhi(x << rd, m_home);   // monotone in the bits below the range prefix
+          // first probe, branch-light: one unconditional CAS answers "empty, mine, or someone else's"
+          uint32_t cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
+          if (cur == SLOT_EMPTY) atomicOr(&sm.bitmap[slot >> 5], 1u << (slot & 31));
+          bool placed = (cur == SLOT_EMPTY) | (cur == k);
+          while (!placed) {                            // ~10 % of the keys: linear probing
+            if (++slot >= ns) { sm.misc[0] = 1u; break; }
             cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
-            if (cur == SLOT_EMPTY) {
-              atomicOr(&sm.bitmap[slot >> 5], 1u << (slot & 31));
-              cur = k;
+            if (cur == SLOT_EMPTY) atomicOr(&sm.bitmap[slot >> 5], 1u << (slot & 31));
+            placed = (cur == SLOT_EMPTY) | (cur == k);
+          }
+          if (placed) atomicAdd(&sm.cnt[slot], 1u);
+        }
+        if (n64 > (unsigned long long)LM && vmisc[0]) break;  // big bucket: stop reading once the pass has failed
+      }
+      __syncthreads();
+      // ---- 3. dense list of occupied slots, in slot order
+      uint32_t nd_total;
+      {
+        constexpr int WPT = 2;  // bitmap words per thread; nwords <= NT * WPT (host: LM vs NT)
+        uint32_t wd[WPT], c = 0;
+        bool long_cluster = false;
+#pragma unroll
+        for (int u = 0; u < WPT; u++) {
+          const uint32_t wi = tid * WPT + u;
+          wd[u] = wi < nwords ? sm.bitmap[wi] : 0u;
+          c += __popc(wd[u]);
+          if (wd[u] == 0xFFFFFFFFu && sm.bitmap[wi + 1] == 0xFFFFFFFFu) long_cluster = true;
+        }
+        if (long_cluster) sm.misc[0] = 1u;
+        const uint32_t incl = warp_incl_scan(c, lane);
+        if (lane == 31) sm.wsum[wid] = incl;
+        __syncthreads();
+        uint32_t base = incl - c;
+        nd_total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) {
+          const uint32_t v = sm.wsum[w];
+          if (w < wid) base += v;
+          nd_total += v;
+        }
+        const bool failed = sm.misc[0] != 0;
+        if (!failed) {
+#pragma unroll
+          for (int u = 0; u < WPT; u++) {
+            uint32_t w = wd[u];
+            const uint32_t s_base = (tid * WPT + u) << 5;
+            while (w) {
+              const int bit = __ffs((int)w) - 1;
+              w &= w - 1;
+              sm.list[base++] = (uint16_t)(s_base + bit);
             }
           }
-          if (cur == k) { atomicAdd(&sm.cnt[slot], 1u); break; }
-          if (++slot >= ns) { sm.misc[0] = 1u; break; }
         }
       }
-    }
-    __syncthreads();
-    // ---- 3. dense list of occupied slots, in slot order
-    uint32_t nd_total;
-    {
-      constexpr int WPT = 2;  // bitmap words per thread; nwords <= NT * WPT is guaranteed by the host (LM vs NT)
-      uint32_t wd[WPT], c = 0;
-      bool long_cluster = false;
-#pragma unroll
-      for (int u = 0; u < WPT; u++) {
-        const uint32_t wi = tid * WPT + u;
-        wd[u] = wi < nwords ? sm.bitmap[wi] : 0u;
-        c += __popc(wd[u]);
-        if (wd[u] == 0xFFFFFFFFu && sm.bitmap[wi + 1] == 0xFFFFFFFFu) long_cluster = true;
-      }
-      if (long_cluster) sm.misc[0] = 1u;
-      const uint32_t incl = warp_incl_scan(c, lane);
-      if (lane == 31) sm.wsum[wid] = incl;
       __syncthreads();
-      uint32_t base = incl - c;
-      nd_total = 0;
-#pragma unroll
-      for (int w = 0; w < NWARP; w++) {
-        const uint32_t v = sm.wsum[w];
-        if (w < wid) base += v;
-        nd_total += v;
+      if (sm.misc[0] != 0) {
+        // nothing was written or counted: split the range (a one-value range cannot fail)
+        if (tid == 0) {
+          uint32_t top = sm.misc[1];
+          if ((int)rd < rem_bits && top + 2 <= L3_STACK) {
+            sm.stack[2 * top] = rd + 1; sm.stack[2 * top + 1] = 2 * ri + 1; top++;   // upper half, popped second
+            sm.stack[2 * top] = rd + 1; sm.stack[2 * top + 1] = 2 * ri; top++;       // lower half, popped first
+            sm.misc[1] = top;
+          } else {
+            sm.misc[2] = 1u;  // cannot happen for valid input; surfaces as a count mismatch rather than a hang
+          }
+        }
+        continue;
       }
-#pragma unroll
-      for (int u = 0; u < WPT; u++) {
-        uint32_t w = wd[u];
-        const uint32_t s_base = (tid * WPT + u) << 5;
-        while (w) {
-          const int bit = __ffs((int)w) - 1;
-          w &= w - 1;
-          sm.list[base++] = (uint16_t)(s_base + bit);
+      // ---- 4. one thread per distinct key: rank inside the cluster, emit
+      for (uint32_t j0 = 0; j0 < nd_total; j0 += NT) {
+        const uint32_t j = j0 + tid;
+        uint32_t f = 0;
+        if (j < nd_total) {
+          const uint32_t q = sm.list[j];
+          const uint32_t k = sm.key[q];
+          uint32_t left = 0, smaller = 0;
+          for (int l = (int)q - 1; l >= 0; l--) {
+            const uint32_t kl = sm.key[l];
+            if (kl == SLOT_EMPTY) break;
+            left++;
+            smaller += kl < k;
+          }
+          for (uint32_t r = q + 1; r < ns; r++) {
+            const uint32_t kr = sm.key[r];
+            if (kr == SLOT_EMPTY) break;
+            smaller += kr < k;
+          }
+          const unsigned long long pos = o + run_nd + (j - left + smaller);
+          f = sm.cnt[q];
+          if (ec.want_table) {
+            ec.tmp_keys[pos] = rebuild_key<W>(k, (uint64_t)b, ec.rem_bits, ec.pad);
+            ec.tmp_cnt[pos] = f;
+          }
+        }
+        // spectrum: singletons dominate, so they are counted per warp with one ballot
+        const uint32_t ones = __ballot_sync(0xffffffffu, f == 1u);
+        if (lane == 0 && ones) atomicAdd(&sm.spec[1], (uint32_t)__popc(ones));
+        if (f > 1u) {
+          if (f < SPEC_SMEM) atomicAdd(&sm.spec[f], 1u);
+          else spec_add_global(ec.spec_dense, ec.spec_ovf, ec.spec_ovf_cap, f);
         }
       }
+      run_nd += nd_total;
+      if (sm.misc[1] == 0) break;  // stack empty (written by thread 0 before the last barriers): bucket done
     }
-    __syncthreads();
-    if (sm.misc[0] != 0) {  // hand the bucket to the general kernel; nothing has been written or counted
-      if (tid == 0) {
-        const uint32_t i = atomicAdd(&deferred[0], 1u);
-        if (i < deferred_cap) deferred[1 + i] = b;
-      }
-      continue;
-    }
-    // ---- 4. one thread per distinct key: rank inside the cluster, emit (counts reuse the bucket's own,
-    //         fully consumed, input range)
-    uint32_t* cnt_dst = const_cast<uint32_t*>(src) + o;
-    for (uint32_t j0 = 0; j0 < nd_total; j0 += NT) {
-      const uint32_t j = j0 + tid;
-      uint32_t f = 0;
-      if (j < nd_total) {
-        const uint32_t q = sm.list[j];
-        const uint32_t k = sm.key[q];
-        uint32_t left = 0, smaller = 0;
-        for (int l = (int)q - 1; l >= 0; l--) {
-          const uint32_t kl = sm.key[l];
-          if (kl == SLOT_EMPTY) break;
-          left++;
-          smaller += kl < k;
-        }
-        for (uint32_t r = q + 1; r < ns; r++) {
-          const uint32_t kr = sm.key[r];
-          if (kr == SLOT_EMPTY) break;
-          smaller += kr < k;
-        }
-        const uint32_t pos = j - left + smaller;
-        f = sm.cnt[q];
-        if (ec.want_table) {
-          ec.tmp_keys[o + pos] = rebuild_key<W>(k, (uint64_t)b, ec.rem_bits, ec.pad);
-          cnt_dst[pos] = f;
-        }
-      }
-      // spectrum: singletons dominate, so they are counted per warp with one ballot
-      const uint32_t ones = __ballot_sync(0xffffffffu, f == 1u);
-      if (lane == 0 && ones) atomicAdd(&sm.spec[1], (uint32_t)__popc(ones));
-      if (f > 1u) {
-        if (f < SPEC_SMEM) atomicAdd(&sm.spec[f], 1u);
-        else spec_add_global(ec.spec_dense, ec.spec_ovf, ec.spec_ovf_cap, f);
-      }
-    }
-    if (tid == 0) nd_out[b] = nd_total;
+    if (tid == 0) nd_out[b] = run_nd;
   }
   __syncthreads();
   for (int i = tid; i < SPEC_SMEM; i += NT) {

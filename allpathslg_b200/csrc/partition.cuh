@@ -6,17 +6,19 @@
 // Here a parcel is a bucket of the key's leading digits and a pass is three
 // kernels with no global atomics and no spin-waits:
 //
-//   k_hist_*    per tile, a shared-memory histogram of the digit -> cnt16[tile][bin]
-//   k_colsum / k_segscan / k_colapply
-//               column-wise exclusive scan over tiles, per segment
-//               -> base32[tile][bin] (offset of the tile's first key of that bin)
-//   k_scatter_* per tile: keys are ranked into a shared-memory stage with one
-//               shared-memory atomic each (ranking order inside a bin is
-//               irrelevant for an MSD pass), then written out as coalesced runs.
+//   k_hist_*    one CTA per CHUNK of tiles: shared-memory histogram of the digit
+//               -> chunksum[chunk][bin]
+//   k_segscan   per segment, exclusive scan over its chunks and over its bins
+//               -> chunksum becomes "first output offset of this chunk's keys of bin d"
+//   k_scatter_* one CTA per chunk, tile after tile: the tile's keys stay in registers,
+//               take their rank inside (tile, bin) from ONE shared-memory atomic each
+//               (order inside a bin is irrelevant for an MSD pass), a block scan turns
+//               the counts into stage slots, the keys are placed in bin order in a
+//               shared-memory stage and leave as coalesced runs.
 //
-// HBM traffic per key and pass: 1 read (hist) + 1 read + 1 write (scatter) plus
-// (2+4)*2 bytes of table per tile-bin.  Output placement is a pure function of
-// the input, so results are reproducible run to run.
+// HBM traffic per key and pass: 1 read (hist) + 1 read + 1 write (scatter); the only
+// table is one row of 4-byte counters per chunk (< 1 % of the key bytes).  Output
+// placement is a pure function of the input, so results are reproducible run to run.
 #pragma once
 #include "extract.cuh"
 #include <cstdio>
@@ -35,20 +37,49 @@ namespace apgk {
 constexpr int DIGIT_BITS = 0;   // digit = key bits [pos, pos+len)
 constexpr int DIGIT_OWNER = 1;  // digit = owner rank of the canonical k-mer (multi-GPU shuffle)
 
+// Host-side description of a digit; the kernels take it as a DigitFn<MODE>.
 struct DigitSpec {
   int mode;
   int pos, len, pad;
   uint32_t n_ranks;
-  uint32_t lo, hi;  // keep only digits in [lo, hi) (k-mer space rounds); others are dropped
 };
 
-template <int W>
-__device__ __forceinline__ uint32_t spec_digit(const DigitSpec& ds, const Key<W>& k) {
-  if (ds.mode == DIGIT_OWNER) return key_owner(k, ds.n_ranks);
-  return digit_of(k, ds.pos, ds.len, ds.pad);
-}
-__device__ __forceinline__ uint32_t spec_digit(const DigitSpec& ds, uint32_t e) {
-  return (e >> ds.pos) & lowmask32(ds.len);
+// Device functor.  For one-word keys the digit is two uniform shifts and a mask
+// (the generic pad/mode/lowmask code cost ~25 of 59 instructions per position in the first profile).
+template <int MODE>
+struct DigitFn {
+  int kind;          // W == 1: 0 = bits straddle/below word 1 (funnel shift), 1 = bits in the high word, 2 = left shift (tiny K)
+  int sh;            // shift amount for `kind`
+  uint32_t mask;
+  int rsh;           // 32-bit elements: (e >> rsh) & mask
+  int pos, len;      // W > 1: key_bits(k, pos, len)
+  uint32_t n_ranks;  // MODE == DIGIT_OWNER
+  template <int W>
+  __device__ __forceinline__ uint32_t operator()(const Key<W>& k) const {
+    if constexpr (MODE == DIGIT_OWNER) return key_owner(k, n_ranks);
+    else if constexpr (W == 1) {
+      // 32-bit formulation: a 64-bit shift by a register amount costs 4-5 instructions, this costs 2
+      const uint32_t lo = (uint32_t)k.w[0], hi = (uint32_t)(k.w[0] >> 32);
+      uint32_t d;
+      if (kind == 0) d = __funnelshift_r(lo, hi, sh);
+      else if (kind == 1) d = hi >> sh;
+      else d = lo << sh;
+      return d & mask;
+    } else return key_bits(k, pos, len);
+  }
+  __device__ __forceinline__ uint32_t operator()(uint32_t e) const { return (e >> rsh) & mask; }
+};
+template <int MODE>
+inline DigitFn<MODE> make_digit_fn(const DigitSpec& ds) {
+  DigitFn<MODE> f;
+  const int eff = ds.pos - ds.pad;  // position of the digit inside the real (unpadded) one-word key
+  if (eff >= 32) { f.kind = 1; f.sh = eff - 32; }
+  else if (eff >= 0) { f.kind = 0; f.sh = eff; }
+  else { f.kind = 2; f.sh = -eff; }
+  f.mask = lowmask32(ds.len);
+  f.rsh = ds.pos;
+  f.pos = ds.pos; f.len = ds.len; f.n_ranks = ds.n_ranks;
+  return f;
 }
 
 // ---------------------------------------------------------------- block scan
@@ -80,29 +111,28 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_s
   return incl - v + warp_scratch[wid];
 }
 
-// Exclusive scan, in place, of arr[0..n) in shared memory by the whole block.
-// Returns the total.  Every thread must call.
+// One-barrier variant: every warp re-scans the warp totals itself.  The caller guarantees the
+// scratch words are not being read by an earlier use (a barrier since then).  total_out = block total.
 template <int NT>
-__device__ __forceinline__ uint32_t block_scan_array(uint32_t* arr, int n, uint32_t* warp_scratch) {
-  const int per = (n + NT - 1) / NT;
-  const int b0 = threadIdx.x * per;
-  uint32_t sum = 0;
-  for (int j = 0; j < per; j++) {
-    int b = b0 + j;
-    if (b < n) sum += arr[b];
+__device__ __forceinline__ uint32_t block_excl_scan1(uint32_t v, uint32_t* warp_scratch, uint32_t& total_out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
   }
-  uint32_t excl = block_excl_scan<NT>(sum, warp_scratch);
-  for (int j = 0; j < per; j++) {
-    int b = b0 + j;
-    if (b < n) {
-      uint32_t v = arr[b];
-      arr[b] = excl;
-      excl += v;
-    }
-  }
-  uint32_t total = warp_scratch[32];
+  if (lane == 31) warp_scratch[wid] = incl;
   __syncthreads();
-  return total;
+  uint32_t t = lane < NT / 32 ? warp_scratch[lane] : 0u, it = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t u = __shfl_up_sync(0xffffffffu, it, o);
+    if (lane >= o) it += u;
+  }
+  total_out = __shfl_sync(0xffffffffu, it, 31);
+  const uint32_t wbase = __shfl_sync(0xffffffffu, it - t, wid);
+  return incl - v + wbase;
 }
 
 // ---------------------------------------------------------------- level plan
@@ -127,7 +157,15 @@ __device__ __forceinline__ int seg_of(const uint32_t* __restrict__ arr, int n, u
   return lo;
 }
 
-// ---------------------------------------------------------------- hist / scatter from packed reads
+// chunk c of segment s covers tiles [seg_tile0[s] + (c - seg_chunk0[s]) * CT, ...).
+__device__ __forceinline__ void chunk_tiles(const LevelPlan& lp, uint32_t c, int& s, uint32_t& t0, uint32_t& t1) {
+  s = seg_of(lp.seg_chunk0, lp.n_segments, c);
+  t0 = lp.seg_tile0[s] + (c - lp.seg_chunk0[s]) * (uint32_t)lp.chunk_tiles;
+  t1 = t0 + (uint32_t)lp.chunk_tiles;
+  if (t1 > lp.seg_tile0[s + 1]) t1 = lp.seg_tile0[s + 1];
+}
+
+// ---------------------------------------------------------------- hist from packed reads
 struct ReadStore {
   const uint32_t* bases32;   // 16 bases per word, zero padded
   const uint32_t* starts32;  // 1 bit per base: a read starts here
@@ -135,105 +173,159 @@ struct ReadStore {
   int K;
 };
 
-template <int W, int NT>
-__global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitSpec ds, int bins, uint16_t* __restrict__ cnt16) {
+// One CTA per CHUNK of tiles: shared-memory histogram over the whole chunk -> one row of chunksum.
+template <int W, int NT, int MODE>
+__global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp,
+                                                   uint32_t* __restrict__ chunksum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* hist = (uint32_t*)smem_raw;
+  const int bins = lp.bins;
   for (int i = threadIdx.x; i < bins; i += NT) hist[i] = 0;
   __syncthreads();
-  const uint64_t p = ((uint64_t)blockIdx.x * NT + threadIdx.x) * POS_PER_THREAD;
-  if (p < rs.total_bases) {
-    const uint32_t valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
-    if (valid) {
-      Window16<W> win;
-      load_window16<W>(rs.bases32, p, rs.K, win);
-      extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
-        if ((valid >> j) & 1u) {
-          uint32_t d = spec_digit(ds, c);
-          if (d >= ds.lo && d < ds.hi) atomicAdd(&hist[d], 1u);
-        }
-      });
+  int s; uint32_t t0, t1;
+  chunk_tiles(lp, blockIdx.x, s, t0, t1);
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint64_t p = ((uint64_t)t * NT + threadIdx.x) * POS_PER_THREAD;
+    if (p < rs.total_bases) {
+      const uint32_t valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
+      if (valid) {
+        Window16<W> win;
+        load_window16<W>(rs.bases32, p, rs.K, win);
+        extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
+          if ((valid >> j) & 1u) atomicAdd(&hist[dg(c)], 1u);
+        });
+      }
     }
   }
   __syncthreads();
-  uint16_t* row = cnt16 + (size_t)blockIdx.x * bins;
-  for (int i = threadIdx.x; i < bins; i += NT) row[i] = (uint16_t)hist[i];
+  uint32_t* row = chunksum + (size_t)blockIdx.x * bins;
+  for (int i = threadIdx.x; i < bins; i += NT) row[i] = hist[i];
 }
 
-// Shared layout of a scatter CTA: stage[tile_elems] | cursor[bins] u32 | gbase[bins] u64 | scratch[33]
+// ---------------------------------------------------------------- scatter: one CTA per CHUNK of tiles
+// Shared layout: stage[tile_elems] | G[bins] u64 | Gabs[bins] u64 | cnt[2][bins] u32 | scratch[40]
+//   Gabs[d] absolute output index of the chunk's next key of bin d (advanced tile by tile)
+//   G[d]    Gabs[d] minus the first stage slot of bin d in the current tile:  out index = G[d] + stage slot
+//   cnt[t&1][d]  phase 1: keys of bin d in tile t (each key learns its rank from the atomic);
+//                after the scan: first stage slot of bin d.  The other buffer is cleared for tile t+1.
+// Ranking is two-phase with the tile's keys held in registers, so no per-tile table exists in HBM.
 template <typename Elem>
 __device__ __forceinline__ void scatter_smem_carve(unsigned char* raw, uint32_t tile_elems, int bins, Elem*& stage,
-                                                   uint32_t*& cursor, unsigned long long*& gbase, uint32_t*& scratch) {
+                                                   uint32_t*& cnt, unsigned long long*& G, unsigned long long*& Gabs,
+                                                   uint32_t*& scratch) {
   stage = (Elem*)raw;
   size_t off = ((size_t)tile_elems * sizeof(Elem) + 15) & ~(size_t)15;
-  gbase = (unsigned long long*)(raw + off);
+  G = (unsigned long long*)(raw + off);
   off += (size_t)bins * 8;
-  cursor = (uint32_t*)(raw + off);
-  off += (size_t)bins * 4;
+  Gabs = (unsigned long long*)(raw + off);
+  off += (size_t)bins * 8;
+  cnt = (uint32_t*)(raw + off);
+  off += (size_t)bins * 8;
   scratch = (uint32_t*)(raw + off);
 }
 template <typename Elem>
 inline size_t scatter_smem_bytes(uint32_t tile_elems, int bins) {
-  return (((size_t)tile_elems * sizeof(Elem) + 15) & ~(size_t)15) + (size_t)bins * 12 + 34 * 4;
+  return (((size_t)tile_elems * sizeof(Elem) + 15) & ~(size_t)15) + (size_t)bins * 24 + 40 * 4;
 }
 
-// Prologue shared by both scatter kernels: cursor[] <- exclusive scan of the tile's
-// counts; gbase[d] <- absolute output index of stage slot 0 if it belonged to bin d.
+// Thread-contiguous ownership of bins: thread t owns bins [t*per, (t+1)*per).
+// chunk start: Gabs[d] = first output index of bin d for this chunk, both counter buffers = 0.
 template <int NT>
-__device__ __forceinline__ uint32_t scatter_prologue(const uint16_t* __restrict__ cnt_row,
-                                                     const uint32_t* __restrict__ base_row,
-                                                     const uint64_t* __restrict__ bstart64, uint64_t seg_base, int bins,
-                                                     uint32_t* cursor, unsigned long long* gbase, uint32_t* scratch) {
-  for (int i = threadIdx.x; i < bins; i += NT) cursor[i] = cnt_row[i];
-  __syncthreads();
-  uint32_t total = block_scan_array<NT>(cursor, bins, scratch);
-  for (int i = threadIdx.x; i < bins; i += NT) {
-    unsigned long long g = seg_base + base_row[i] - cursor[i];
-    if (bstart64) g += bstart64[i];
-    gbase[i] = g;
+__device__ __forceinline__ void chunk_begin(const uint32_t* __restrict__ chunk_row, const uint64_t* __restrict__ bstart64,
+                                            uint64_t seg_base, int bins, unsigned long long* Gabs, uint32_t* cnt) {
+  const int per = (bins + NT - 1) / NT;
+  for (int j = 0; j < per; j++) {
+    const int d = threadIdx.x * per + j;
+    if (d < bins) {
+      unsigned long long g = seg_base + chunk_row[d];
+      if (bstart64) g += bstart64[d];
+      Gabs[d] = g;
+      cnt[d] = 0;
+      cnt[bins + d] = 0;
+    }
+  }
+}
+// After phase 1 (+ a barrier): cur[] holds the tile's counts.  Turns them into stage slots, sets G for
+// the write-out, advances Gabs past the tile, clears the other counter buffer for the next tile, and
+// returns the tile's key count.  One barrier inside, one at the end.
+template <int NT>
+__device__ __forceinline__ uint32_t tile_scan(int bins, unsigned long long* G, unsigned long long* Gabs, uint32_t* cur,
+                                              uint32_t* nxt, uint32_t* scratch) {
+  const int per = (bins + NT - 1) / NT;
+  const int d0 = threadIdx.x * per;
+  uint32_t sum = 0;
+  for (int j = 0; j < per; j++) {
+    const int d = d0 + j;
+    if (d < bins) sum += cur[d];
+  }
+  uint32_t total;
+  uint32_t excl = block_excl_scan1<NT>(sum, scratch, total);
+  for (int j = 0; j < per; j++) {
+    const int d = d0 + j;
+    if (d < bins) {
+      const uint32_t c = cur[d];
+      const unsigned long long ga = Gabs[d];
+      cur[d] = excl;       // first stage slot of bin d
+      G[d] = ga - excl;    // out = G[d] + slot
+      Gabs[d] = ga + c;
+      nxt[d] = 0;
+      excl += c;
+    }
   }
   __syncthreads();
   return total;
 }
 
-template <int W, int NT>
-__global__ void __launch_bounds__(NT) k_scatter_reads(ReadStore rs, DigitSpec ds, int bins,
-                                                      const uint16_t* __restrict__ cnt16,
-                                                      const uint32_t* __restrict__ base32,
-                                                      const uint64_t* __restrict__ bstart64, Key<W>* __restrict__ out,
-                                                      unsigned long long out_cap) {
+template <int W, int NT, int MODE>
+__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp,
+                                                      const uint32_t* __restrict__ chunkpref,
+                                                      const uint64_t* __restrict__ bstart64, Key<W>* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Key<W>* stage; uint32_t* cursor; unsigned long long* gbase; uint32_t* scratch;
-  scatter_smem_carve<Key<W>>(smem_raw, NT * POS_PER_THREAD, bins, stage, cursor, gbase, scratch);
-  const size_t row = (size_t)blockIdx.x * bins;
-  const uint32_t tile_n = scatter_prologue<NT>(cnt16 + row, base32 + row, bstart64, 0ull, bins, cursor, gbase, scratch);
-  if (tile_n == 0) return;
-  const uint64_t p = ((uint64_t)blockIdx.x * NT + threadIdx.x) * POS_PER_THREAD;
-  if (p < rs.total_bases) {
-    const uint32_t valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
+  Key<W>* stage; uint32_t* cnt2; unsigned long long* G; unsigned long long* Gabs; uint32_t* scratch;
+  const int bins = lp.bins;
+  scatter_smem_carve<Key<W>>(smem_raw, NT * POS_PER_THREAD, bins, stage, cnt2, G, Gabs, scratch);
+  int s; uint32_t t0, t1;
+  chunk_tiles(lp, blockIdx.x, s, t0, t1);
+  chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, 0ull, bins, Gabs, cnt2);
+  __syncthreads();
+  for (uint32_t t = t0; t < t1; t++) {
+    uint32_t* cnt = cnt2 + ((t - t0) & 1u) * bins;
+    uint32_t* cnt_next = cnt2 + (((t - t0) & 1u) ^ 1u) * bins;
+    // ---- phase 1: extract 16 windows into registers; each key takes its rank inside (tile, bin)
+    Key<W> key[POS_PER_THREAD];
+    uint32_t rk[POS_PER_THREAD / 2];  // two 16-bit ranks per register
+    uint32_t valid = 0;
+    const uint64_t p = ((uint64_t)t * NT + threadIdx.x) * POS_PER_THREAD;
+    if (p < rs.total_bases) valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
+#pragma unroll
+    for (int j = 0; j < POS_PER_THREAD / 2; j++) rk[j] = 0;
     if (valid) {
       Window16<W> win;
       load_window16<W>(rs.bases32, p, rs.K, win);
       extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
+        key[j] = c;
         if ((valid >> j) & 1u) {
-          uint32_t d = spec_digit(ds, c);
-          if (d >= ds.lo && d < ds.hi) {
-            uint32_t pos = atomicAdd(&cursor[d], 1u);
-            APGK_CHECK(pos < (uint32_t)(NT * POS_PER_THREAD) && d < (uint32_t)bins,
-                       "scatter_reads: tile %u tid %d pos %u d %u bins %d tile_n %u\n", blockIdx.x, threadIdx.x, pos, d, bins, tile_n);
-            if (APGK_OK_OR_SKIP(pos < (uint32_t)(NT * POS_PER_THREAD))) stage[pos] = c;
-          }
+          const uint32_t r = atomicAdd(&cnt[dg(c)], 1u);
+          rk[j >> 1] |= r << ((j & 1) * 16);
         }
       });
     }
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
-    Key<W> k = stage[i];
-    uint32_t d = spec_digit(ds, k);
-    APGK_CHECK(d < (uint32_t)bins && gbase[d < (uint32_t)bins ? d : 0] + i < out_cap,
-               "scatter_reads out: tile %u i %u d %u gbase %llu cap %llu\n", blockIdx.x, i, d, gbase[d < (uint32_t)bins ? d : 0], out_cap);
-    if (APGK_OK_OR_SKIP(d < (uint32_t)bins && gbase[d] + i < out_cap)) out[gbase[d] + i] = k;
+    __syncthreads();
+    const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
+    // ---- phase 2: place the keys in bin order in the stage
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < POS_PER_THREAD; j++) {
+        if ((valid >> j) & 1u) stage[cnt[dg(key[j])] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu)] = key[j];
+      }
+    }
+    __syncthreads();
+    // ---- coalesced runs out
+    for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
+      const Key<W> k = stage[i];
+      out[G[dg(k)] + i] = k;
+    }
+    __syncthreads();  // stage and G are reused by the next tile
   }
 }
 
@@ -252,94 +344,105 @@ struct ElemCvt<uint32_t, Key<1>> {  // keep only the REM low bits of the virtual
   }
 };
 
-template <typename Elem, int NT>
-__global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, LevelPlan lp, DigitSpec ds,
-                                                  uint16_t* __restrict__ cnt16) {
+// elements a thread holds in registers per tile
+template <typename Elem> struct TileItems { static constexpr int N = sizeof(Elem) <= 8 ? 16 : (sizeof(Elem) <= 16 ? 8 : 5); };
+
+template <typename Elem, int NT, int MODE>
+__global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, LevelPlan lp, DigitFn<MODE> dg,
+                                                  uint32_t* __restrict__ chunksum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* hist = (uint32_t*)smem_raw;
   const int bins = lp.bins;
   for (int i = threadIdx.x; i < bins; i += NT) hist[i] = 0;
   __syncthreads();
-  const uint32_t tile = blockIdx.x;
-  const int s = seg_of(lp.seg_tile0, lp.n_segments, tile);
+  int s; uint32_t t0, t1;
+  chunk_tiles(lp, blockIdx.x, s, t0, t1);
   const uint64_t seg_lo = lp.seg_start[s], seg_hi = lp.seg_start[s + 1];
-  const uint64_t e0 = seg_lo + (uint64_t)(tile - lp.seg_tile0[s]) * lp.tile_elems;
-  const uint64_t e1 = e0 + lp.tile_elems < seg_hi ? e0 + lp.tile_elems : seg_hi;
-  for (uint64_t i = e0 + threadIdx.x; i < e1; i += NT) {
-    Elem e = src[i];
-    uint32_t d = spec_digit(ds, e);
-    if (d >= ds.lo && d < ds.hi) atomicAdd(&hist[d], 1u);
-  }
-  __syncthreads();
-  uint16_t* row = cnt16 + (size_t)tile * bins;
-  for (int i = threadIdx.x; i < bins; i += NT) row[i] = (uint16_t)hist[i];
-}
-
-template <typename ElemIn, typename ElemOut, int NT>
-__global__ void __launch_bounds__(NT) k_scatter_keys(const ElemIn* __restrict__ src, LevelPlan lp, DigitSpec ds,
-                                                     const uint16_t* __restrict__ cnt16,
-                                                     const uint32_t* __restrict__ base32,
-                                                     const uint64_t* __restrict__ bstart64, int out_pad, int out_rem,
-                                                     ElemOut* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ElemIn* stage; uint32_t* cursor; unsigned long long* gbase; uint32_t* scratch;
-  const int bins = lp.bins;
-  scatter_smem_carve<ElemIn>(smem_raw, lp.tile_elems, bins, stage, cursor, gbase, scratch);
-  const uint32_t tile = blockIdx.x;
-  const int s = seg_of(lp.seg_tile0, lp.n_segments, tile);
-  const uint64_t seg_lo = lp.seg_start[s], seg_hi = lp.seg_start[s + 1];
-  const size_t row = (size_t)tile * bins;
-  const uint32_t tile_n =
-      scatter_prologue<NT>(cnt16 + row, base32 + row, bstart64, bstart64 ? 0ull : seg_lo, bins, cursor, gbase, scratch);
-  if (tile_n == 0) return;
-  const uint64_t e0 = seg_lo + (uint64_t)(tile - lp.seg_tile0[s]) * lp.tile_elems;
-  const uint64_t e1 = e0 + lp.tile_elems < seg_hi ? e0 + lp.tile_elems : seg_hi;
-  for (uint64_t i = e0 + threadIdx.x; i < e1; i += NT) {
-    ElemIn e = src[i];
-    uint32_t d = spec_digit(ds, e);
-    if (d >= ds.lo && d < ds.hi) {
-      uint32_t pos = atomicAdd(&cursor[d], 1u);
-      stage[pos] = e;
+  const uint64_t e0 = seg_lo + (uint64_t)(t0 - lp.seg_tile0[s]) * lp.tile_elems;
+  uint64_t e1 = seg_lo + (uint64_t)(t1 - lp.seg_tile0[s]) * lp.tile_elems;
+  if (e1 > seg_hi) e1 = seg_hi;
+  constexpr int U = 4;
+  for (uint64_t base = e0; base < e1; base += (uint64_t)NT * U) {
+    Elem r[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t i = base + (uint64_t)u * NT + threadIdx.x;
+      if (i < e1) r[u] = src[i];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t i = base + (uint64_t)u * NT + threadIdx.x;
+      if (i < e1) atomicAdd(&hist[dg(r[u])], 1u);
     }
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
-    ElemIn e = stage[i];
-    uint32_t d = spec_digit(ds, e);
-    out[gbase[d] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
+  uint32_t* row = chunksum + (size_t)blockIdx.x * bins;
+  for (int i = threadIdx.x; i < bins; i += NT) row[i] = hist[i];
+}
+
+template <typename ElemIn, typename ElemOut, int NT, int MODE>
+__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const ElemIn* __restrict__ src, LevelPlan lp, DigitFn<MODE> dg,
+                                                     const uint32_t* __restrict__ chunkpref,
+                                                     const uint64_t* __restrict__ bstart64, int out_pad, int out_rem,
+                                                     ElemOut* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ElemIn* stage; uint32_t* cnt2; unsigned long long* G; unsigned long long* Gabs; uint32_t* scratch;
+  const int bins = lp.bins;
+  scatter_smem_carve<ElemIn>(smem_raw, lp.tile_elems, bins, stage, cnt2, G, Gabs, scratch);
+  int s; uint32_t t0, t1;
+  chunk_tiles(lp, blockIdx.x, s, t0, t1);
+  const uint64_t seg_lo = lp.seg_start[s], seg_hi = lp.seg_start[s + 1];
+  chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, bstart64 ? 0ull : seg_lo, bins, Gabs, cnt2);
+  __syncthreads();
+  constexpr int ITEMS = TileItems<ElemIn>::N;  // lp.tile_elems == NT * ITEMS
+  for (uint32_t t = t0; t < t1; t++) {
+    uint32_t* cnt = cnt2 + ((t - t0) & 1u) * bins;
+    uint32_t* cnt_next = cnt2 + (((t - t0) & 1u) ^ 1u) * bins;
+    const uint64_t e0 = seg_lo + (uint64_t)(t - lp.seg_tile0[s]) * lp.tile_elems;
+    const uint64_t e1 = e0 + lp.tile_elems < seg_hi ? e0 + lp.tile_elems : seg_hi;
+    ElemIn r[ITEMS];
+    uint32_t rk[(ITEMS + 1) / 2];
+#pragma unroll
+    for (int u = 0; u < ITEMS; u++) {
+      const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+      if (i < e1) r[u] = src[i];
+    }
+#pragma unroll
+    for (int u = 0; u < (ITEMS + 1) / 2; u++) rk[u] = 0;
+#pragma unroll
+    for (int u = 0; u < ITEMS; u++) {
+      const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+      if (i < e1) {
+        const uint32_t rr = atomicAdd(&cnt[dg(r[u])], 1u);
+        rk[u >> 1] |= rr << ((u & 1) * 16);
+      }
+    }
+    __syncthreads();
+    const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
+#pragma unroll
+    for (int u = 0; u < ITEMS; u++) {
+      const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+      if (i < e1) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
+      const ElemIn e = stage[i];
+      out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
+    }
+    __syncthreads();  // stage and G are reused by the next tile
   }
 }
 
 // ---------------------------------------------------------------- column scan over tiles
-// chunk c of segment s covers tiles [seg_tile0[s] + (c - seg_chunk0[s]) * CT, ...).
-__device__ __forceinline__ void chunk_tiles(const LevelPlan& lp, uint32_t c, int& s, uint32_t& t0, uint32_t& t1) {
-  s = seg_of(lp.seg_chunk0, lp.n_segments, c);
-  t0 = lp.seg_tile0[s] + (c - lp.seg_chunk0[s]) * (uint32_t)lp.chunk_tiles;
-  t1 = t0 + (uint32_t)lp.chunk_tiles;
-  if (t1 > lp.seg_tile0[s + 1]) t1 = lp.seg_tile0[s + 1];
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT) k_colsum(LevelPlan lp, const uint16_t* __restrict__ cnt16,
-                                               uint32_t* __restrict__ chunksum) {
-  int s; uint32_t t0, t1;
-  chunk_tiles(lp, blockIdx.x, s, t0, t1);
-  const int bins = lp.bins;
-  for (int d = threadIdx.x; d < bins; d += NT) {
-    uint32_t sum = 0;
-    for (uint32_t t = t0; t < t1; t++) sum += cnt16[(size_t)t * bins + d];
-    chunksum[(size_t)blockIdx.x * bins + d] = sum;
-  }
-}
-
-// One CTA per segment: chunk sums -> exclusive chunk prefixes (in place); bucket
-// totals -> segtot64; exclusive scan of the totals -> bstart32 (offset of the
-// bucket inside its segment) and, optionally, absolute bucket offsets.
+// One CTA per segment: chunk sums -> exclusive chunk prefixes (in place); bucket totals -> segtot64;
+// exclusive scan of the totals -> bstart32 (offset of the bucket inside its segment) and, optionally,
+// absolute bucket offsets.  With fold != 0 the bucket's start inside the segment is added to every
+// chunk prefix, so a scatter CTA finds "offset of my chunk's first key of bin d inside the segment".
 template <int NT>
 __global__ void __launch_bounds__(NT) k_segscan(LevelPlan lp, uint32_t* __restrict__ chunksum,
                                                 unsigned long long* __restrict__ segtot64,
                                                 uint32_t* __restrict__ bstart32,
-                                                unsigned long long* __restrict__ bofs /* may be null */) {
+                                                unsigned long long* __restrict__ bofs /* may be null */, int fold) {
   __shared__ uint32_t scratch[34];
   __shared__ unsigned long long carry_s;
   const int s = blockIdx.x;
@@ -351,42 +454,26 @@ __global__ void __launch_bounds__(NT) k_segscan(LevelPlan lp, uint32_t* __restri
     const int d = d0 + threadIdx.x;
     unsigned long long run = 0;
     if (d < bins) {
-      for (uint32_t c = c0; c < c1; c++) {
-        uint32_t v = chunksum[(size_t)c * bins + d];
-        chunksum[(size_t)c * bins + d] = (uint32_t)run;
-        run += v;
-      }
+      for (uint32_t c = c0; c < c1; c++) run += chunksum[(size_t)c * bins + d];
       segtot64[(size_t)s * bins + d] = run;
     }
     // exclusive scan of this slab's totals (32-bit is enough inside a segment < 2^32; host checks)
     uint32_t excl = block_excl_scan<NT>((uint32_t)run, scratch);
     unsigned long long carry = carry_s;
     if (d < bins) {
-      bstart32[(size_t)s * bins + d] = (uint32_t)(carry + excl);
+      const uint32_t bs = (uint32_t)(carry + excl);
+      bstart32[(size_t)s * bins + d] = bs;
       if (bofs) bofs[(size_t)s * bins + d] = lp.seg_start[s] + carry + excl;
+      uint32_t pre = fold ? bs : 0u;
+      for (uint32_t c = c0; c < c1; c++) {
+        const uint32_t v = chunksum[(size_t)c * bins + d];
+        chunksum[(size_t)c * bins + d] = pre;
+        pre += v;
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) carry_s = carry + scratch[32];
     __syncthreads();
-  }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT) k_colapply(LevelPlan lp, const uint16_t* __restrict__ cnt16,
-                                                 const uint32_t* __restrict__ chunksum,
-                                                 const uint32_t* __restrict__ bstart32, int fold,
-                                                 uint32_t* __restrict__ base32) {
-  int s; uint32_t t0, t1;
-  chunk_tiles(lp, blockIdx.x, s, t0, t1);
-  const int bins = lp.bins;
-  for (int d = threadIdx.x; d < bins; d += NT) {
-    uint32_t run = chunksum[(size_t)blockIdx.x * bins + d];
-    if (fold) run += bstart32[(size_t)s * bins + d];
-    for (uint32_t t = t0; t < t1; t++) {
-      uint32_t v = cnt16[(size_t)t * bins + d];
-      base32[(size_t)t * bins + d] = run;
-      run += v;
-    }
   }
 }
 

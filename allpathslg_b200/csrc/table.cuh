@@ -74,11 +74,10 @@ __global__ void k_classify(const unsigned long long* __restrict__ bsize, uint32_
 }
 
 // ---------------------------------------------------------------- compaction: temp records -> final table
-// One warp per bucket.  Temp keys live at element offset bofs[b] of the level-0
-// buffer; temp counts at BYTE offset bofs[b] * elem_bytes of the level-1 buffer.
+// One warp per bucket.  Temp keys / counts live at element offset bofs[b] of the temp buffers.
 template <int W>
-__global__ void k_compact(const Key<W>* __restrict__ tmp_keys, const unsigned char* __restrict__ tmp_cnt_base,
-                          uint32_t elem_bytes, const unsigned long long* __restrict__ bofs,
+__global__ void k_compact(const Key<W>* __restrict__ tmp_keys, const uint32_t* __restrict__ tmp_cnt,
+                          const unsigned long long* __restrict__ bofs,
                           const unsigned long long* __restrict__ out_off, uint32_t nb, Key<W>* __restrict__ out_keys,
                           uint32_t* __restrict__ out_cnt) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -87,10 +86,9 @@ __global__ void k_compact(const Key<W>* __restrict__ tmp_keys, const unsigned ch
     const unsigned long long o0 = out_off[b], nd = out_off[b + 1] - o0;
     if (!nd) continue;
     const unsigned long long src = bofs[b];
-    const uint32_t* c = (const uint32_t*)(tmp_cnt_base + src * elem_bytes);
     for (unsigned long long j = lane; j < nd; j += 32) {
       out_keys[o0 + j] = tmp_keys[src + j];
-      out_cnt[o0 + j] = c[j];
+      out_cnt[o0 + j] = tmp_cnt[src + j];
     }
   }
 }

@@ -107,11 +107,12 @@ def cpu_baseline(reads, genome_len, threads=0):
     A.build()
     sp = A.synth_params(genome_len, READ_LEN)
     packed, off = A.synth_reads(sp, 0, reads)
+    threads = threads or (os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1: ask for all host cores explicitly
     t0 = time.perf_counter()
     _, cnt, n_inst = A.count(packed, off, K, n_threads=threads)
     A.spectrum(cnt)
     dt = time.perf_counter() - t0
-    return n_inst, dt, A.num_threads()
+    return n_inst, dt, threads
 
 
 def run_reference(args):

@@ -116,7 +116,8 @@ def test_low_complexity_oversize_buckets(oracle, K, prefix_bits):
     reads = ["A" * 200] * 400 + ["ACGTACGTAC" * 20] * 300 + ["".join(rnd.choice("AC") for _ in range(120)) for _ in range(500)]
     p, o = oracle.pack_strings(reads)
     kc = _run(p, o, K, prefix_bits=prefix_bits)
-    assert kc.geometry()["n_big"] > 0
+    g = kc.geometry()
+    assert g["n_big"] > 0 or g["elem_bytes"] == 4  # the 32-bit-remainder kernel splits ranges instead of using k_big
     _assert_equal_to_oracle(oracle, kc, p, o, K)
     kc.close()
 
@@ -127,6 +128,36 @@ def test_huge_multiplicity_single_kmer(oracle):
     p, o = oracle.pack_strings(reads)
     for K in (25, 33):
         kc = _run(p, o, K)
+        _assert_equal_to_oracle(oracle, kc, p, o, K)
+        kc.close()
+
+
+@pytest.mark.parametrize("K,prefix_bits", [(16, 2), (16, 6), (13, 4), (10, 2)])
+def test_range_splitting_big_distinct_buckets(oracle, K, prefix_bits):
+    """32-bit-remainder path with buckets far larger than the shared-memory table and almost all keys
+    distinct: k_local3 has to split key ranges repeatedly (and still emit in ascending order)."""
+    rnd = np.random.RandomState(K * 31 + prefix_bits)
+    n_reads, L = 6000, 150
+    bases = rnd.randint(0, 4, size=n_reads * L).astype(np.uint8)
+    packed = np.zeros((n_reads * L + 31) // 32 * 8 + 8, dtype=np.uint8)
+    for sh in range(4):
+        part = bases[sh::4]
+        packed[: len(part)] |= part << (2 * sh)
+    off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(L)
+    kc = _run(packed, off, K, prefix_bits=prefix_bits, uniform=(n_reads, L))
+    g = kc.geometry()
+    assert g["elem_bytes"] == 4 and g["n_big"] == 0
+    _assert_equal_to_oracle(oracle, kc, packed, off, K)
+    kc.close()
+
+
+def test_huge_multiplicity_32bit_path(oracle):
+    """poly-A / poly-C floods on the 32-bit-remainder path: one key holds > 65535 instances of a bucket."""
+    reads = ["A" * 1000] * 300 + ["C" * 700] * 11 + ["ACGTTGCA" * 50] * 40
+    p, o = oracle.pack_strings(reads)
+    for K, P in ((13, 0), (12, 4), (16, 8)):
+        kc = _run(p, o, K, prefix_bits=P)
+        assert kc.geometry()["elem_bytes"] == 4
         _assert_equal_to_oracle(oracle, kc, p, o, K)
         kc.close()
 
