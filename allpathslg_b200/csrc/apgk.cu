@@ -206,11 +206,14 @@ ReadStore read_store(const apgk_ctx* c) {
   return rs;
 }
 
-int choose_prefix_bits(const apgk_ctx* c, uint64_t upper, int local_max) {
+int choose_prefix_bits(const apgk_ctx* c, uint64_t upper, int local_max, bool l3) {
   if (c->cfg.prefix_bits > 0) return std::max(2, std::min(24, (int)c->cfg.prefix_bits));
   const char* env = getenv("APGK_PREFIX_BITS");
   if (env && atoi(env) > 0) return std::max(2, std::min(24, atoi(env)));
-  double target = local_max / 2.2;  // the densest prefixes (AAAA...) hold ~2x the average bucket
+  // k_local3 (32-bit remainders) likes the average bucket near its table's key capacity: duplicates share a
+  // slot and oversize ranges are split (measured best on B200: P=20 for 4.56 G k-mers, profiles/r01_sweeps.txt).  The general kernels cannot
+  // split, and the densest prefixes (AAAA...) hold ~2x the average bucket, so they aim at capacity / 2.2.
+  double target = l3 ? local_max * 1.0 : local_max / 2.2;
   int P = 2;
   while (P < 24 && (double)upper / (double)(1ull << P) > target) P++;
   return P;
@@ -222,7 +225,9 @@ void make_geom(apgk_ctx* c, int P) {
   g.K = c->cfg.K; g.W = c->W;
   g.TB = std::max(2 * g.K, P);
   g.pad = g.TB - 2 * g.K;
-  g.D0 = (P + 1) / 2; g.D1 = P - g.D0;
+  g.D0 = (P + 1) / 2;
+  if (const char* e = getenv("APGK_D0")) { if (atoi(e) >= 1 && atoi(e) < P && atoi(e) <= 12 && P - atoi(e) <= 12) g.D0 = atoi(e); }  // tuning knob
+  g.D1 = P - g.D0;
   g.REM = g.TB - P;
   g.topbits = 2 * g.K - 64 * (g.W - 1);
 }
@@ -305,11 +310,15 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   // decide element type of the level-1 buffer first (it fixes LOCAL_MAX, which fixes P)
   int lm_u32 = LM_U32;
   if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) lm_u32 = atoi(e); }
-  int P = choose_prefix_bits(c, upper, lm_u32);
+  // try the 32-bit-remainder geometry first: one-word keys whose remainder below the prefix fits 31 bits
+  int P = choose_prefix_bits(c, upper, lm_u32, true);
   make_geom(c, P);
+  if (W == 1 && c->cfg.prefix_bits <= 0 && !getenv("APGK_PREFIX_BITS")) {
+    while (c->geom.REM > 31 && c->geom.REM <= 34 && P < 24) make_geom(c, ++P);  // a few more prefix bits buy the fast path
+  }
   const bool u32 = (W == 1 && c->geom.REM <= 32);
   if (!u32) {
-    P = choose_prefix_bits(c, upper, Geo<W>::LM_KEY);
+    P = choose_prefix_bits(c, upper, Geo<W>::LM_KEY, false);
     make_geom(c, P);
   }
   stage_begin(c, ST_TOTAL);

@@ -1,14 +1,16 @@
 // local3.cuh -- sort-and-count for 32-bit remainders by ORDER-PRESERVING hashing.
 //
 // Keys of one bucket share their leading bits, so the remainder r (< 2^REM) of a
-// random-looking genome is spread evenly.  The home slot of a key is therefore
-// chosen MONOTONE in the key:   home(r) = floor(r * M / 2^REM).
-// Insertion is plain linear probing without wrap-around (one CAS + one ADD per
-// key instance groups identical keys), and because the hash is monotone every
-// maximal run of occupied slots ("cluster") holds exactly the keys whose homes
-// fall inside it: clusters are already in ascending key order, and only the
-// handful of entries inside a cluster have to be ranked against each other.
-// There is no separate sort.
+// random-looking genome is spread evenly.  The table is cut into ROWS of 16 slots and
+// the row of a key is chosen MONOTONE in the key:   row(r) = floor(r * nrows / 2^REM);
+// inside its row a key probes from a scrambled start (multiplicative hash), wrapping
+// inside the row.  One CAS + one ADD per key instance groups identical keys.  Rows
+// are in ascending key order by construction, so only the <= 16 entries of a row have
+// to be ranked against each other: there is no separate sort.
+// (A fully monotone slot hash was tried first: sequencing-error variants of a genomic
+// k-mer differ in their low bits, land on the same home slot and build clusters right
+// where the 45x-covered k-mer lives -- ncu showed 6.5 warp instructions per key in
+// the probing loop.  The scrambled in-row start removes that.)
 //
 // A bucket is processed as a stack of DYADIC KEY RANGES (d, i) = "the keys whose
 // top d remainder bits equal i", starting with the whole bucket (0, 0).  For one range:
@@ -23,8 +25,8 @@
 //      write (k-mer, count) at its final ascending position, update the
 //      spectrum                                                               [block, all lanes busy]
 //
-// If the table overflows (too many distinct keys for its M slots) or a cluster
-// gets too long to rank cheaply, nothing has been written yet and the range is
+// If a row fills up (too many distinct keys for the table, or a skewed range),
+// nothing has been written yet and the range is
 // split into its two halves (d+1, 2i), (d+1, 2i+1) -- so oversize and skewed
 // buckets take more passes instead of a different kernel.  A range of one key
 // value (d == REM) always fits.  (The first version walked table SLOTS in steps
@@ -34,7 +36,8 @@
 
 namespace apgk {
 
-constexpr int L3_SLACK = 96;    // slots past the last home slot (no wrap-around)
+constexpr int L3_ROW = 16;      // slots per row (a row is half a bitmap word)
+constexpr int L3_SLACK = 96;    // table padding
 constexpr int L3_STACK = 72;    // >= 2 * 32 pending ranges
 
 // Needs 1 <= REM <= 31.  Shared memory (NS = slots(LM)):
@@ -80,8 +83,9 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src,
     const unsigned long long o = bt.bofs[b];
     const uint32_t* s = src + o;
     // a pass over a small bucket only needs a small table
-    const uint32_t m_home = n64 < (unsigned long long)LM ? (uint32_t)n64 + ((uint32_t)n64 >> 2) + 1 : m_cap;
-    const uint32_t ns = m_home + L3_SLACK;             // probing may run into the slack
+    const uint32_t m_want = n64 < (unsigned long long)LM ? (uint32_t)n64 + ((uint32_t)n64 >> 2) + 1 : m_cap;
+    const uint32_t nrows = (m_want + L3_ROW - 1) / L3_ROW;
+    const uint32_t ns = nrows * L3_ROW;                // slots in use
     const uint32_t ns4 = (ns + 3) >> 2;                // uint4 groups to clear (table is padded to 128 slots)
     const uint32_t nwords = (ns + 31) >> 5;
     volatile uint32_t* vmisc = sm.misc;
@@ -120,23 +124,32 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src,
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const uint32_t k = kk[u];
-          if (k == SLOT_EMPTY) continue;               // remainders are < 2^31
           const uint32_t x = k << up;
-          if (rd && (x >> pshift) != ri) continue;     // not in this range
-          uint32_t slot = __umulhi(x << rd, m_home);   // monotone in the bits below the range prefix
-          // first probe, branch-light: one unconditional CAS answers "empty, mine, or someone else's"
-          uint32_t cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
-          if (cur == SLOT_EMPTY) atomicOr(&sm.bitmap[slot >> 5], 1u << (slot & 31));
-          bool placed = (cur == SLOT_EMPTY) | (cur == k);
-          while (!placed) {                            // ~10 % of the keys: linear probing
-            if (++slot >= ns) { sm.misc[0] = 1u; break; }
-            cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
+          // in range?  (k == EMPTY marks the tail of the bucket; remainders are < 2^31)
+          if (k != SLOT_EMPTY && (rd == 0 || (x >> pshift) == ri)) {
+            const uint32_t row = __umulhi(x << rd, nrows) * L3_ROW;  // monotone in the bits below the range prefix
+            uint32_t h = (k * 0x9E3779B1u) >> 28;                    // scrambled start inside the row
+            // first probe, branch-light: one unconditional CAS answers "empty, mine, or someone else's"
+            uint32_t slot = row + h;
+            uint32_t cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
             if (cur == SLOT_EMPTY) atomicOr(&sm.bitmap[slot >> 5], 1u << (slot & 31));
-            placed = (cur == SLOT_EMPTY) | (cur == k);
+            bool placed = (cur == SLOT_EMPTY) | (cur == k);
+            for (int pr = 1; !placed; pr++) {          // a few % of the keys: probe on, wrapping inside the row
+              if (pr == L3_ROW) { sm.misc[0] = 1u; break; }          // row full: this range needs splitting
+              h = (h + 1) & (L3_ROW - 1);
+              slot = row + h;
+              cur = atomicCAS(&sm.key[slot], SLOT_EMPTY, k);
+              if (cur == SLOT_EMPTY) atomicOr(&sm.bitmap[slot >> 5], 1u << (slot & 31));
+              placed = (cur == SLOT_EMPTY) | (cur == k);
+            }
+            if (placed) atomicAdd(&sm.cnt[slot], 1u);
           }
-          if (placed) atomicAdd(&sm.cnt[slot], 1u);
+          // Reconverge the warp after every key: without this the lanes that finish probing early run
+          // ahead on their own (independent thread scheduling) and the whole loop executes with ~14 of
+          // 32 lanes active (ncu: LDG of the next batch issued 3x more often than needed).
+          __syncwarp();
         }
-        if (n64 > (unsigned long long)LM && vmisc[0]) break;  // big bucket: stop reading once the pass has failed
+        if (n64 > (unsigned long long)LM && __any_sync(0xffffffffu, vmisc[0] != 0)) break;  // failed pass of a big bucket
       }
       __syncthreads();
       // ---- 3. dense list of occupied slots, in slot order
@@ -144,15 +157,12 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src,
       {
         constexpr int WPT = 2;  // bitmap words per thread; nwords <= NT * WPT (host: LM vs NT)
         uint32_t wd[WPT], c = 0;
-        bool long_cluster = false;
 #pragma unroll
         for (int u = 0; u < WPT; u++) {
           const uint32_t wi = tid * WPT + u;
           wd[u] = wi < nwords ? sm.bitmap[wi] : 0u;
           c += __popc(wd[u]);
-          if (wd[u] == 0xFFFFFFFFu && sm.bitmap[wi + 1] == 0xFFFFFFFFu) long_cluster = true;
         }
-        if (long_cluster) sm.misc[0] = 1u;
         const uint32_t incl = warp_incl_scan(c, lane);
         if (lane == 31) sm.wsum[wid] = incl;
         __syncthreads();
@@ -200,19 +210,17 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src,
         if (j < nd_total) {
           const uint32_t q = sm.list[j];
           const uint32_t k = sm.key[q];
-          uint32_t left = 0, smaller = 0;
-          for (int l = (int)q - 1; l >= 0; l--) {
-            const uint32_t kl = sm.key[l];
-            if (kl == SLOT_EMPTY) break;
-            left++;
-            smaller += kl < k;
+          // the row's occupancy is one half of a bitmap word; rank k among the row's keys
+          const uint32_t rbase = q & ~(uint32_t)(L3_ROW - 1);
+          uint32_t rowbits = (sm.bitmap[q >> 5] >> (rbase & 31)) & 0xFFFFu;
+          const uint32_t before = __popc(rowbits & ((1u << (q & (L3_ROW - 1))) - 1u));
+          uint32_t smaller = 0;
+          while (rowbits) {
+            const int bit = __ffs((int)rowbits) - 1;
+            rowbits &= rowbits - 1;
+            smaller += sm.key[rbase + bit] < k;
           }
-          for (uint32_t r = q + 1; r < ns; r++) {
-            const uint32_t kr = sm.key[r];
-            if (kr == SLOT_EMPTY) break;
-            smaller += kr < k;
-          }
-          const unsigned long long pos = o + run_nd + (j - left + smaller);
+          const unsigned long long pos = o + run_nd + (j - before + smaller);
           f = sm.cnt[q];
           if (ec.want_table) {
             ec.tmp_keys[pos] = rebuild_key<W>(k, (uint64_t)b, ec.rem_bits, ec.pad);

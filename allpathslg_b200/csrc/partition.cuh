@@ -403,31 +403,57 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
     ElemIn r[ITEMS];
     uint32_t rk[(ITEMS + 1) / 2];
 #pragma unroll
-    for (int u = 0; u < ITEMS; u++) {
-      const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-      if (i < e1) r[u] = src[i];
-    }
-#pragma unroll
     for (int u = 0; u < (ITEMS + 1) / 2; u++) rk[u] = 0;
+    const bool full = (e1 - e0) == (uint64_t)lp.tile_elems;  // uniform; the common case needs no bounds checks
+    if (full) {
+      const ElemIn* __restrict__ p = src + e0 + threadIdx.x;
 #pragma unroll
-    for (int u = 0; u < ITEMS; u++) {
-      const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-      if (i < e1) {
+      for (int u = 0; u < ITEMS; u++) r[u] = p[u * NT];
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
         const uint32_t rr = atomicAdd(&cnt[dg(r[u])], 1u);
         rk[u >> 1] |= rr << ((u & 1) * 16);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
+        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+        if (i < e1) r[u] = src[i];
+      }
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
+        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+        if (i < e1) {
+          const uint32_t rr = atomicAdd(&cnt[dg(r[u])], 1u);
+          rk[u >> 1] |= rr << ((u & 1) * 16);
+        }
       }
     }
     __syncthreads();
     const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
+    if (full) {
 #pragma unroll
-    for (int u = 0; u < ITEMS; u++) {
-      const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-      if (i < e1) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
+      for (int u = 0; u < ITEMS; u++) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
+    } else {
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
+        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+        if (i < e1) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
+      }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
-      const ElemIn e = stage[i];
-      out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
+    if (full) {
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
+        const uint32_t i = u * NT + threadIdx.x;
+        const ElemIn e = stage[i];
+        out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
+        const ElemIn e = stage[i];
+        out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
+      }
     }
     __syncthreads();  // stage and G are reused by the next tile
   }
