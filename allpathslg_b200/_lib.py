@@ -18,7 +18,7 @@ MAX_K = 96
 
 class Config(C.Structure):
     _fields_ = [("K", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("prefix_bits", C.c_int32),
-                ("reserve_bases", C.c_uint64)]
+                ("reserve_bases", C.c_uint64), ("max_round_keys", C.c_uint64)]
 
 
 class SynthParams(C.Structure):
@@ -51,6 +51,7 @@ SYMBOLS = {
     "apgk_read_freqs": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "apgk_owner_plan": (C.c_int, [_vp, C.c_uint32, _vp]),
     "apgk_owner_scatter": (C.c_int, [_vp, _vp]),
+    "apgk_key_buffer": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "apgk_owner_of": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, _vp]),
     "apgk_finish_keys_device": (C.c_int, [_vp, _vp, C.c_uint64]),
     "apgk_spectrum_device": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),

@@ -70,7 +70,7 @@ struct apgk_ctx {
   DevBuf bases, starts, staging, off_dev;
   uint64_t total_bases = 0, n_reads = 0;
   // ---- pipeline buffers
-  DevBuf A, B, T, chunksum, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
+  DevBuf A, B, T, chunksum, chunksum0, plan0, out_off_local, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
       scratch, stacks, spec_dense, spec_ovf, misc, deferred;
   // ---- results
   DevBuf out_keys, out_cnt;
@@ -80,7 +80,7 @@ struct apgk_ctx {
   uint32_t nb1 = 0;          // number of level-1 buckets
   uint32_t elem_bytes = 0;   // level-1 element size
   uint64_t n_big = 0;
-  uint32_t n_deferred = 0, local_max = 0;
+  uint32_t n_deferred = 0, local_max = 0, n_rounds = 0;
   std::vector<uint64_t> spec_host, sparse_f, sparse_n;
   bool spec_loaded = false;
   // ---- owner partition state
@@ -343,8 +343,27 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
 
 template <typename ElemB, int W>
 struct ScatterSel {  // level-1 scatter kernel: Key<W> in, ElemB out
-  static auto kernel() { return k_scatter_keys<Key<W>, ElemB, Geo<W>::NT1, DIGIT_BITS>; }
+  static auto kernel() { return k_scatter_keys<Key<W>, ElemB, Geo<W>::NT1, DIGIT_BITS, false>; }
 };
+
+// u64 accumulate: dst[i] += src[i]   (global bucket index = sum of the rounds' local prefixes)
+__global__ void k_accumulate_u64(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+// grow a result buffer, keeping its first keep_bytes
+int ensure_preserve(apgk_ctx* c, DevBuf& b, size_t bytes, size_t keep_bytes) {
+  if (bytes <= b.cap) return APGK_OK;
+  if (!keep_bytes || !b.p) { CU(b.ensure(bytes)); return APGK_OK; }
+  DevBuf nb;
+  CU(nb.ensure(std::max(bytes, b.cap + b.cap / 2)));
+  CU(cudaMemcpyAsync(nb.p, b.p, keep_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  b.release();
+  b = nb;
+  return APGK_OK;
+}
 
 template <int W, typename ElemB>
 int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
@@ -357,15 +376,19 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     if (const char* e = getenv("APGK_L3_NT")) { if (atoi(e) == 256 || atoi(e) == 512) l3_nt = atoi(e); }
   }
   const bool use_l3 = std::is_same<ElemB, uint32_t>::value && g.REM >= 1 && g.REM <= 31;
+  const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
   c->elem_bytes = sizeof(ElemB);
   c->local_max = (uint32_t)local_max;
   c->nb1 = (uint32_t)bins0 * (uint32_t)bins1;
+  c->n_rounds = 0; c->n_big = 0; c->n_distinct = 0;
   CU(c->spec_dense.ensure((size_t)SPEC_DENSE * 8));
   CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
+  CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
+  CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
 
-  // ================= level 0
+  // ================= level 0: one histogram pass over everything (all rounds share it)
   DigitSpec ds0{DIGIT_BITS, g.TB - g.D0, g.D0, g.pad, 0};
-  const DigitFn<DIGIT_BITS> dg0 = make_digit_fn<DIGIT_BITS>(ds0);
+  DigitFn<DIGIT_BITS> dg0 = make_digit_fn<DIGIT_BITS>(ds0);
   HostPlan hp0;
   const uint32_t tile0 = dev_keys ? Geo<W>::TILE1 : (uint32_t)Geo<W>::NT0 * POS_PER_THREAD;
   {
@@ -373,150 +396,185 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     build_plan(hp0, one, tile0, bins0);
   }
   if (hp0.lp.n_tiles == 0) {  // nothing to count
-    c->n_instances = 0; c->n_distinct = 0; c->n_big = 0;
-    CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
-    CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
-    c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
+    c->n_instances = 0;
+    c->have_table = want_table != 0;
     return APGK_OK;
   }
-  { int rc = upload_plan(c, hp0); if (rc) return rc; }
-  CU(c->chunksum.ensure((size_t)hp0.lp.n_chunks * bins0 * 4));
+  {  // the level-0 plan must outlive the level-1 uploads of every round: it gets its own device copy
+    const size_t S1 = hp0.seg_tile0.size();
+    CU(c->plan0.ensure(S1 * 16 + 64));
+    unsigned char* d = c->plan0.as<unsigned char>();
+    CU(cudaMemcpyAsync(d, hp0.seg_start.data(), S1 * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + S1 * 8, hp0.seg_tile0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + S1 * 12, hp0.seg_chunk0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    hp0.lp.seg_start = (const uint64_t*)d;
+    hp0.lp.seg_tile0 = (const uint32_t*)(d + S1 * 8);
+    hp0.lp.seg_chunk0 = (const uint32_t*)(d + S1 * 12);
+  }
+  CU(c->chunksum0.ensure((size_t)hp0.lp.n_chunks * bins0 * 4));
   stage_begin(c, ST_HIST0);
   if (dev_keys) {
     k_hist_keys<Key<W>, Geo<W>::NT1, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT1, bins0 * 4, c->stream>>>(
-        dev_keys, hp0.lp, dg0, c->chunksum.as<uint32_t>());
+        dev_keys, hp0.lp, dg0, c->chunksum0.as<uint32_t>());
   } else {
     k_hist_reads<W, Geo<W>::NT0, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT0, bins0 * 4, c->stream>>>(
-        read_store(c), dg0, hp0.lp, c->chunksum.as<uint32_t>());
+        read_store(c), dg0, hp0.lp, c->chunksum0.as<uint32_t>());
   }
   LAUNCHED();
   stage_end(c, ST_HIST0);
   stage_begin(c, ST_SCAN0);
-  { int rc = column_scan(c, hp0, 0, nullptr); if (rc) return rc; }
+  CU(c->segtot.ensure((size_t)bins0 * 8));
+  CU(c->bstart32.ensure((size_t)bins0 * 4));
+  k_segscan<COL_NT><<<1, COL_NT, 0, c->stream>>>(hp0.lp, c->chunksum0.as<uint32_t>(), c->segtot.as<unsigned long long>(),
+                                                 c->bstart32.as<uint32_t>(), nullptr, 0);
+  LAUNCHED();
   stage_end(c, ST_SCAN0);
-  std::vector<uint64_t> tot0(bins0), bstart0(bins0 + 1, 0);
+  std::vector<uint64_t> tot0(bins0);
   CU(cudaMemcpyAsync(tot0.data(), c->segtot.p, (size_t)bins0 * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  uint64_t N = 0;
   for (int d = 0; d < bins0; d++) {
     if (tot0[d] >= (1ull << 32)) FAIL(APGK_E_RANGE, "level-0 bucket %d holds %llu k-mers (>= 2^32)", d, (unsigned long long)tot0[d]);
-    bstart0[d + 1] = bstart0[d] + tot0[d];
+    N += tot0[d];
   }
-  const uint64_t N = bstart0[bins0];
   c->n_instances = N;
   if (N == 0) {
-    c->n_distinct = 0; c->n_big = 0;
-    CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
-    CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
-    c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
+    c->have_table = want_table != 0;
     return APGK_OK;
   }
-  CU(c->bstart64.ensure(((size_t)bins0 + 1) * 8));
-  CU(cudaMemcpyAsync(c->bstart64.p, bstart0.data(), ((size_t)bins0 + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(c->A.ensure(std::max<size_t>(N, 1) * sizeof(Key<W>)));
-  stage_begin(c, ST_SCATTER0);
-  if (dev_keys) {
-    auto kern = k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS>;
-    const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
-    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    kern<<<hp0.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(dev_keys, hp0.lp, dg0, c->chunksum.as<uint32_t>(),
-                                                          c->bstart64.as<uint64_t>(), 0, 0, c->A.as<Key<W>>());
-  } else {
-    auto kern = k_scatter_reads<W, Geo<W>::NT0, DIGIT_BITS>;
-    const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
-    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    kern<<<hp0.lp.n_chunks, Geo<W>::NT0, sm, c->stream>>>(read_store(c), dg0, hp0.lp, c->chunksum.as<uint32_t>(),
-                                                          c->bstart64.as<uint64_t>(), c->A.as<Key<W>>());
-  }
-  LAUNCHED();
-  stage_end(c, ST_SCATTER0);
 
-  // ================= level 1
+  // ================= rounds over k-mer space (SortKmers "passes" / KmerParcels "parcels"): consecutive
+  // level-0 buckets whose keys, with their level-1 copy and temp counts, fit the device memory budget
+  const size_t bytes_per_key = sizeof(Key<W>) + sizeof(ElemB) + (want_table ? 4 : 0);
+  uint64_t cap_keys = c->cfg.max_round_keys;
+  if (const char* e = getenv("APGK_ROUND_KEYS")) { if (atoll(e) > 0) cap_keys = (uint64_t)atoll(e); }
+  if (!cap_keys) {
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    const size_t held = c->A.cap + c->B.cap + c->T.cap;  // reusable
+    // temp buffers may take ~60 % of what is available; the result table gets the rest
+    cap_keys = (uint64_t)((double)(fr + held) * 0.60 / (double)bytes_per_key);
+  }
+  std::vector<std::pair<int, int>> rounds;  // [lo, hi) level-0 buckets
+  {
+    int lo = 0; uint64_t acc = 0;
+    for (int d = 0; d < bins0; d++) {
+      if (acc && acc + tot0[d] > cap_keys) { rounds.push_back({lo, d}); lo = d; acc = 0; }
+      acc += tot0[d];
+    }
+    rounds.push_back({lo, bins0});
+  }
+  c->n_rounds = (uint32_t)rounds.size();
+
+  CU(c->spec_ovf.ensure(((size_t)N / SPEC_DENSE + 16) * 8));
+  CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
+  CU(c->bofs.ensure(((size_t)c->nb1 + 1) * 8));
+  CU(c->nd.ensure(((size_t)c->nb1 + 1) * 4));
+  CU(c->out_off_local.ensure(((size_t)c->nb1 + 1) * 8));
+  CU(c->stats.ensure(64));
+  CU(c->bstart64.ensure(((size_t)bins0 + 1) * 8));
   DigitSpec ds1{DIGIT_BITS, g.TB - g.D0 - g.D1, g.D1, g.pad, 0};
   const DigitFn<DIGIT_BITS> dg1 = make_digit_fn<DIGIT_BITS>(ds1);
-  HostPlan hp1;
-  build_plan(hp1, tot0, Geo<W>::TILE1, bins1);
-  { int rc = upload_plan(c, hp1); if (rc) return rc; }
-  CU(c->bofs.ensure(((size_t)c->nb1 + 1) * 8));
-  CU(c->stats.ensure(64));
-  CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
-  if (hp1.lp.n_tiles) {
-    CU(c->chunksum.ensure((size_t)hp1.lp.n_chunks * bins1 * 4));
+  uint64_t n_prev = 0;  // records already in the result table
+
+  for (size_t r = 0; r < rounds.size(); r++) {
+    const int lo = rounds[r].first, hi = rounds[r].second;
+    const bool filter = rounds.size() > 1;
+    std::vector<uint64_t> tot_r(bins0, 0), bstart_r(bins0 + 1, 0);
+    uint64_t Nr = 0;
+    for (int d = 0; d < bins0; d++) {
+      bstart_r[d] = Nr;
+      if (d >= lo && d < hi) { tot_r[d] = tot0[d]; Nr += tot0[d]; }
+    }
+    bstart_r[bins0] = Nr;
+    if (Nr == 0) continue;
+    CU(cudaMemcpyAsync(c->bstart64.p, bstart_r.data(), ((size_t)bins0 + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(c->A.ensure(std::max<size_t>(Nr, 1) * sizeof(Key<W>)));
+    dg0.flo = (uint32_t)lo; dg0.fwidth = (uint32_t)(hi - lo);
+
+    // ---- level-0 scatter of this round's buckets
+    stage_begin(c, ST_SCATTER0);
+    {
+      const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
+      if (dev_keys) {
+        auto launch = [&](auto kern) -> int {
+          { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+          kern<<<hp0.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(dev_keys, hp0.lp, dg0, c->chunksum0.as<uint32_t>(),
+                                                                c->bstart64.as<uint64_t>(), 0, 0, c->A.as<Key<W>>());
+          return APGK_OK;
+        };
+        int rc = filter ? launch(k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS, true>)
+                        : launch(k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS, false>);
+        if (rc) return rc;
+      } else {
+        auto launch = [&](auto kern) -> int {
+          { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+          kern<<<hp0.lp.n_chunks, Geo<W>::NT0, sm, c->stream>>>(read_store(c), dg0, hp0.lp, c->chunksum0.as<uint32_t>(),
+                                                                c->bstart64.as<uint64_t>(), c->A.as<Key<W>>());
+          return APGK_OK;
+        };
+        int rc = filter ? launch(k_scatter_reads<W, Geo<W>::NT0, DIGIT_BITS, true>)
+                        : launch(k_scatter_reads<W, Geo<W>::NT0, DIGIT_BITS, false>);
+        if (rc) return rc;
+      }
+      LAUNCHED();
+    }
+    stage_end(c, ST_SCATTER0);
+
+    // ---- level 1
+    HostPlan hp1;
+    build_plan(hp1, tot_r, Geo<W>::TILE1, bins1);
+    { int rc = upload_plan(c, hp1); if (rc) return rc; }
+    CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
+    CU(c->chunksum.ensure((size_t)std::max<uint32_t>(hp1.lp.n_chunks, 1) * bins1 * 4));
     stage_begin(c, ST_HIST1);
     k_hist_keys<Key<W>, Geo<W>::NT1, DIGIT_BITS><<<hp1.lp.n_chunks, Geo<W>::NT1, bins1 * 4, c->stream>>>(
         c->A.as<Key<W>>(), hp1.lp, dg1, c->chunksum.as<uint32_t>());
     LAUNCHED();
     stage_end(c, ST_HIST1);
-  }
-  stage_begin(c, ST_SCAN1);
-  if (hp1.lp.n_chunks == 0) {
-    CU(c->segtot.ensure((size_t)c->nb1 * 8));
-    CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
-  } else {
-    // segments with no tiles still need their bucket rows written: k_segscan runs one CTA per segment
-    int rc = column_scan(c, hp1, 1, c->bofs.as<unsigned long long>());
-    if (rc) return rc;
-  }
-  // bucket classification (oversize list)
-  CU(c->big_list.ensure(((size_t)N / local_max + 16) * 4));
-  const uint32_t big_cap = (uint32_t)(N / local_max + 16);
-  k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
-                                                         use_l3 ? 0xFFFFFFFFu : (uint32_t)local_max,
-                                                         c->big_list.as<uint32_t>(), big_cap,
-                                                         c->stats.as<unsigned long long>());
-  LAUNCHED();
-  stage_end(c, ST_SCAN1);
-  unsigned long long stats[2] = {0, 0};
-  CU(cudaMemcpyAsync(stats, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  c->n_big = stats[0];
-  if (getenv("APGK_DEBUG")) {
-    std::vector<unsigned long long> bs(c->nb1), bo(c->nb1);
-    cudaMemcpyAsync(bs.data(), c->segtot.p, (size_t)c->nb1 * 8, cudaMemcpyDeviceToHost, c->stream);
-    cudaMemcpyAsync(bo.data(), c->bofs.p, (size_t)c->nb1 * 8, cudaMemcpyDeviceToHost, c->stream);
-    cudaStreamSynchronize(c->stream);
-    unsigned long long mx = 0, sum = 0; uint32_t am = 0, bad_ofs = 0;
-    unsigned long long run = 0;
-    for (uint32_t b = 0; b < c->nb1; b++) {
-      if (bs[b] > mx) { mx = bs[b]; am = b; }
-      if (bo[b] != run) bad_ofs++;
-      run += bs[b]; sum += bs[b];
-    }
-    uint64_t mx0 = 0; int am0 = 0;
-    for (int d = 0; d < bins0; d++) if (tot0[d] > mx0) { mx0 = tot0[d]; am0 = d; }
-    fprintf(stderr, "[apgk] K=%d W=%d P=%d+%d REM=%d N=%llu tiles0=%u tiles1=%u chunks1=%u ct1=%d | L0 max %llu @%d | L1 max %llu @%u sum %llu bad_ofs %u | n_big %llu big_total %llu\n",
-            g.K, W, g.D0, g.D1, g.REM, (unsigned long long)N, hp0.lp.n_tiles, hp1.lp.n_tiles, hp1.lp.n_chunks, hp1.lp.chunk_tiles,
-            (unsigned long long)mx0, am0, mx, am, sum, bad_ofs, stats[0], stats[1]);
-  }
-  CU(c->B.ensure(std::max<size_t>(N, 1) * sizeof(ElemB) + 16));
-  if (hp1.lp.n_tiles) {
-    stage_begin(c, ST_SCATTER1);
-    auto kern = ScatterSel<ElemB, W>::kernel();
-    const size_t sm = scatter_smem_bytes<Key<W>>(Geo<W>::TILE1, bins1);
-    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    kern<<<hp1.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(c->A.as<Key<W>>(), hp1.lp, dg1, c->chunksum.as<uint32_t>(),
-                                                          nullptr, g.pad, g.REM, c->B.as<ElemB>());
+    stage_begin(c, ST_SCAN1);
+    { int rc = column_scan(c, hp1, 1, c->bofs.as<unsigned long long>()); if (rc) return rc; }
+    // bucket classification (oversize list)
+    const uint32_t big_cap = (uint32_t)(Nr / local_max + 16);
+    CU(c->big_list.ensure((size_t)big_cap * 4));
+    k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
+                                                           use_l3 ? 0xFFFFFFFFu : (uint32_t)local_max,
+                                                           c->big_list.as<uint32_t>(), big_cap,
+                                                           c->stats.as<unsigned long long>());
     LAUNCHED();
+    stage_end(c, ST_SCAN1);
+    unsigned long long stats[2] = {0, 0};
+    CU(cudaMemcpyAsync(stats, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint64_t n_big = stats[0];
+    c->n_big += n_big;
+    CU(c->B.ensure(std::max<size_t>(Nr, 1) * sizeof(ElemB) + 16));
+    stage_begin(c, ST_SCATTER1);
+    {
+      auto kern = ScatterSel<ElemB, W>::kernel();
+      const size_t sm = scatter_smem_bytes<Key<W>>(Geo<W>::TILE1, bins1);
+      { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+      kern<<<hp1.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(c->A.as<Key<W>>(), hp1.lp, dg1, c->chunksum.as<uint32_t>(),
+                                                            nullptr, g.pad, g.REM, c->B.as<ElemB>());
+      LAUNCHED();
+    }
     stage_end(c, ST_SCATTER1);
-  }
 
-  // ================= local sort + count
-  const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
-  CU(c->nd.ensure(((size_t)c->nb1 + 1) * 4));
-  CU(c->spec_ovf.ensure(((size_t)N / SPEC_DENSE + 16) * 8));
-  CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
-  EmitCtx<W> ec;
-  ec.want_table = want_table; ec.rem_bits = g.REM; ec.pad = g.pad;
-  ec.tmp_keys = c->A.as<Key<W>>();
-  if (want_table) CU(c->T.ensure(std::max<size_t>(N, 1) * 4));
-  ec.tmp_cnt = c->T.as<uint32_t>();
-  ec.spec_dense = c->spec_dense.as<unsigned long long>();
-  ec.spec_ovf = c->spec_ovf.as<unsigned long long>();
-  ec.spec_ovf_cap = (uint32_t)(N / SPEC_DENSE + 8);
-  BucketTable bt;
-  bt.bofs = c->bofs.as<unsigned long long>();
-  bt.bsize = c->segtot.as<unsigned long long>();
-  bt.nb = c->nb1; bt.local_max = (uint32_t)local_max;
-  {
+    // ---- per-bucket sort + count
+    EmitCtx<W> ec;
+    ec.want_table = want_table; ec.rem_bits = g.REM; ec.pad = g.pad;
+    ec.tmp_keys = c->A.as<Key<W>>();
+    if (want_table) CU(c->T.ensure(std::max<size_t>(Nr, 1) * 4));
+    ec.tmp_cnt = c->T.as<uint32_t>();
+    ec.spec_dense = c->spec_dense.as<unsigned long long>();
+    ec.spec_ovf = c->spec_ovf.as<unsigned long long>();
+    ec.spec_ovf_cap = (uint32_t)(N / SPEC_DENSE + 8);
+    BucketTable bt;
+    bt.bofs = c->bofs.as<unsigned long long>();
+    bt.bsize = c->segtot.as<unsigned long long>();
+    bt.nb = c->nb1; bt.local_max = (uint32_t)local_max;
     CU(c->deferred.ensure(((size_t)c->nb1 + 1) * 4));
     CU(cudaMemsetAsync(c->deferred.p, 0, 4, c->stream));
     stage_begin(c, ST_LOCAL);
@@ -559,62 +617,66 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
       LAUNCHED();
     }
     stage_end(c, ST_LOCAL);
-  }
-  if (c->n_big) {
-    if (c->n_big > big_cap) FAIL(APGK_E_RANGE, "internal: oversize bucket list overflow");
-    auto kern = k_big<ElemB, W>;
-    const size_t sm = LocalSmem<ElemB>::bytes(local_max);
-    { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-    int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(c->n_big, (uint64_t)c->n_sm * std::max(occ, 1));
-    CU(c->scratch.ensure((size_t)stats[1] * sizeof(ElemB) + 16));
-    CU(c->stacks.ensure((size_t)grid * BIG_STACK * 16));
-    CU(c->misc.ensure(64));
-    CU(cudaMemsetAsync(c->misc.p, 0, 64, c->stream));
-    BigParams bp;
-    bp.big_list = c->big_list.as<uint32_t>();
-    bp.n_big = (const uint32_t*)c->stats.p;  // low word of stats[0]
-    bp.ticket = c->misc.as<unsigned int>();
-    bp.scratch_cursor = (unsigned long long*)(c->misc.as<unsigned char>() + 8);
-    bp.scratch = c->scratch.p;
-    bp.stacks = c->stacks.as<unsigned long long>();
-    stage_begin(c, ST_BIG);
-    kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(), bp);
-    LAUNCHED();
-    stage_end(c, ST_BIG);
-  }
-
-  // ================= table
-  stage_begin(c, ST_TABLE);
-  {
-    const uint64_t n = c->nb1;
-    const uint32_t nblocks = (uint32_t)((n + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    CU(c->blocksum.ensure(((size_t)nblocks + 1) * 8));
-    CU(c->out_off.ensure(((size_t)n + 1) * 8));
-    k_scan_blocksum<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>());
-    LAUNCHED();
-    k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks);
-    LAUNCHED();
-    k_scan_apply<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>(),
-                                                     c->out_off.as<unsigned long long>());
-    LAUNCHED();
-    unsigned long long total = 0;
-    CU(cudaMemcpyAsync(&total, c->blocksum.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    c->n_distinct = total;
-    if (want_table) {
-      CU(c->out_keys.ensure(std::max<size_t>(total, 1) * sizeof(Key<W>)));
-      CU(c->out_cnt.ensure(std::max<size_t>(total, 1) * 4));
-      k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(c->A.as<Key<W>>(), c->T.as<uint32_t>(),
-                                                       c->bofs.as<unsigned long long>(),
-                                                       c->out_off.as<unsigned long long>(), c->nb1,
-                                                       c->out_keys.as<Key<W>>(), c->out_cnt.as<uint32_t>());
+    if (n_big) {
+      if (n_big > big_cap) FAIL(APGK_E_RANGE, "internal: oversize bucket list overflow");
+      auto kern = k_big<ElemB, W>;
+      const size_t sm = LocalSmem<ElemB>::bytes(local_max);
+      { int rc = set_smem(c, kern, sm); if (rc) return rc; }
+      int occ = 1;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
+      const uint32_t grid = (uint32_t)std::min<uint64_t>(n_big, (uint64_t)c->n_sm * std::max(occ, 1));
+      CU(c->scratch.ensure((size_t)stats[1] * sizeof(ElemB) + 16));
+      CU(c->stacks.ensure((size_t)grid * BIG_STACK * 16));
+      CU(c->misc.ensure(64));
+      CU(cudaMemsetAsync(c->misc.p, 0, 64, c->stream));
+      BigParams bp;
+      bp.big_list = c->big_list.as<uint32_t>();
+      bp.n_big = (const uint32_t*)c->stats.p;  // low word of stats[0]
+      bp.ticket = c->misc.as<unsigned int>();
+      bp.scratch_cursor = (unsigned long long*)(c->misc.as<unsigned char>() + 8);
+      bp.scratch = c->scratch.p;
+      bp.stacks = c->stacks.as<unsigned long long>();
+      stage_begin(c, ST_BIG);
+      kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(), bp);
       LAUNCHED();
-      c->have_table = true;
+      stage_end(c, ST_BIG);
     }
+
+    // ---- table: this round's records are appended (rounds ascend in k-mer space, so the table stays sorted)
+    stage_begin(c, ST_TABLE);
+    {
+      const uint64_t n = c->nb1;
+      const uint32_t nblocks = (uint32_t)((n + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
+      CU(c->blocksum.ensure(((size_t)nblocks + 1) * 8));
+      k_scan_blocksum<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>());
+      LAUNCHED();
+      k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks);
+      LAUNCHED();
+      k_scan_apply<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>(),
+                                                       c->out_off_local.as<unsigned long long>());
+      LAUNCHED();
+      unsigned long long total = 0;
+      CU(cudaMemcpyAsync(&total, c->blocksum.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      // global prefix index = sum over rounds of the local prefixes (buckets outside a round add 0 / its total)
+      k_accumulate_u64<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(c->out_off.as<unsigned long long>(),
+                                                                              c->out_off_local.as<unsigned long long>(), n + 1);
+      LAUNCHED();
+      if (want_table) {
+        { int rc = ensure_preserve(c, c->out_keys, std::max<size_t>(n_prev + total, 1) * sizeof(Key<W>), n_prev * sizeof(Key<W>)); if (rc) return rc; }
+        { int rc = ensure_preserve(c, c->out_cnt, std::max<size_t>(n_prev + total, 1) * 4, n_prev * 4); if (rc) return rc; }
+        k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(c->A.as<Key<W>>(), c->T.as<uint32_t>(),
+                                                         c->bofs.as<unsigned long long>(),
+                                                         c->out_off_local.as<unsigned long long>(), c->nb1,
+                                                         c->out_keys.as<Key<W>>() + n_prev, c->out_cnt.as<uint32_t>() + n_prev);
+        LAUNCHED();
+      }
+      n_prev += total;
+    }
+    stage_end(c, ST_TABLE);
   }
-  stage_end(c, ST_TABLE);
+  c->n_distinct = n_prev;
+  c->have_table = want_table != 0;
   return APGK_OK;
 }
 
@@ -747,7 +809,7 @@ int owner_scatter_impl(apgk_ctx* c, uint64_t* d_out) {
   for (uint32_t r = 0; r < n_ranks; r++) bstart[r + 1] = bstart[r] + c->owner_counts[r];
   CU(c->bstart64.ensure(((size_t)n_ranks + 1) * 8));
   CU(cudaMemcpyAsync(c->bstart64.p, bstart.data(), ((size_t)n_ranks + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  auto kern = k_scatter_reads<W, Geo<W>::NT0, DIGIT_OWNER>;
+  auto kern = k_scatter_reads<W, Geo<W>::NT0, DIGIT_OWNER, false>;
   const size_t sm = scatter_smem_bytes<Key<W>>((uint32_t)Geo<W>::NT0 * POS_PER_THREAD, (int)n_ranks);
   { int rc = set_smem(c, kern, sm); if (rc) return rc; }
   kern<<<c->owner_plan.lp.n_chunks, Geo<W>::NT0, sm, c->stream>>>(read_store(c), dg, c->owner_plan.lp,
@@ -824,7 +886,7 @@ void apgk_destroy(apgk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum,
+  DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum, &c->chunksum0, &c->plan0, &c->out_off_local,
                    &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
                    &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc, &c->deferred,
                    &c->out_keys, &c->out_cnt, &c->owner_plan_dev};
@@ -1054,6 +1116,15 @@ int apgk_owner_scatter(apgk_ctx* c, uint64_t* d_keys_out) {
   return APGK_E_ARG;
 }
 
+int apgk_key_buffer(apgk_ctx* c, uint64_t n_keys, uint64_t** d_ptr) {
+  if (!c || !d_ptr) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(c->A.ensure(std::max<size_t>(n_keys, 1) * (size_t)c->W * 8));
+  *d_ptr = c->A.as<uint64_t>();
+  return APGK_OK;
+}
+
 int apgk_owner_of(int K, const uint64_t* kmers, uint64_t n, uint32_t n_ranks, uint32_t* owner_out) {
   if (K < 1 || K > APGK_MAX_K || !kmers || !owner_out || !n_ranks) return APGK_E_ARG;
   const int W = words_for(K);
@@ -1095,7 +1166,7 @@ int apgk_geometry(const apgk_ctx* c, int32_t* out8) {
   out8[4] = (int32_t)std::min<uint64_t>(c->n_big, 0x7fffffff);
   out8[5] = (int32_t)std::min<uint32_t>(c->n_deferred, 0x7fffffff);
   out8[6] = (int32_t)c->local_max;
-  out8[7] = 0;
+  out8[7] = (int32_t)c->n_rounds;
   return APGK_OK;
 }
 

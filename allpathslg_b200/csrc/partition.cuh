@@ -54,6 +54,7 @@ struct DigitFn {
   int rsh;           // 32-bit elements: (e >> rsh) & mask
   int pos, len;      // W > 1: key_bits(k, pos, len)
   uint32_t n_ranks;  // MODE == DIGIT_OWNER
+  uint32_t flo, fwidth;  // FILTER kernels keep only digits d with d - flo < fwidth (one k-mer-space round)
   template <int W>
   __device__ __forceinline__ uint32_t operator()(const Key<W>& k) const {
     if constexpr (MODE == DIGIT_OWNER) return key_owner(k, n_ranks);
@@ -79,6 +80,7 @@ inline DigitFn<MODE> make_digit_fn(const DigitSpec& ds) {
   f.mask = lowmask32(ds.len);
   f.rsh = ds.pos;
   f.pos = ds.pos; f.len = ds.len; f.n_ranks = ds.n_ranks;
+  f.flo = 0; f.fwidth = 0xFFFFFFFFu;
   return f;
 }
 
@@ -164,6 +166,9 @@ __device__ __forceinline__ void chunk_tiles(const LevelPlan& lp, uint32_t c, int
   t1 = t0 + (uint32_t)lp.chunk_tiles;
   if (t1 > lp.seg_tile0[s + 1]) t1 = lp.seg_tile0[s + 1];
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- hist from packed reads
 struct ReadStore {
@@ -276,7 +281,7 @@ __device__ __forceinline__ uint32_t tile_scan(int bins, unsigned long long* G, u
   return total;
 }
 
-template <int W, int NT, int MODE>
+template <int W, int NT, int MODE, bool FILTER>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp,
                                                       const uint32_t* __restrict__ chunkpref,
                                                       const uint64_t* __restrict__ bstart64, Key<W>* __restrict__ out) {
@@ -299,14 +304,26 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
     if (p < rs.total_bases) valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
 #pragma unroll
     for (int j = 0; j < POS_PER_THREAD / 2; j++) rk[j] = 0;
+    if (t + 1 < t1) {  // the next tile's bases / start bits: pull them into L1 while this tile is ranked and written
+      const uint64_t pn = p + (uint64_t)NT * POS_PER_THREAD;
+      if (pn < rs.total_bases) {
+        if ((threadIdx.x & 7) == 0) prefetch_l1(rs.bases32 + (pn >> 4));   // 8 threads share a 32-byte sector
+        if ((threadIdx.x & 15) == 0) prefetch_l1(rs.starts32 + (pn >> 5));
+      }
+    }
     if (valid) {
       Window16<W> win;
       load_window16<W>(rs.bases32, p, rs.K, win);
       extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
         key[j] = c;
         if ((valid >> j) & 1u) {
-          const uint32_t r = atomicAdd(&cnt[dg(c)], 1u);
-          rk[j >> 1] |= r << ((j & 1) * 16);
+          const uint32_t d = dg(c);
+          if (FILTER && (d - dg.flo) >= dg.fwidth) {
+            valid &= ~(1u << j);  // belongs to another round
+          } else {
+            const uint32_t r = atomicAdd(&cnt[d], 1u);
+            rk[j >> 1] |= r << ((j & 1) * 16);
+          }
         }
       });
     }
@@ -321,9 +338,18 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
     }
     __syncthreads();
     // ---- coalesced runs out
-    for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
-      const Key<W> k = stage[i];
-      out[G[dg(k)] + i] = k;
+    for (uint32_t i0 = 0; i0 < tile_n; i0 += 4 * NT) {  // 4 independent LDS -> digit -> LDS -> STG chains in flight
+      Key<W> kq[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t i = i0 + u * NT + threadIdx.x;
+        if (i < tile_n) kq[u] = stage[i];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t i = i0 + u * NT + threadIdx.x;
+        if (i < tile_n) out[G[dg(kq[u])] + i] = kq[u];
+      }
     }
     __syncthreads();  // stage and G are reused by the next tile
   }
@@ -380,7 +406,7 @@ __global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, 
   for (int i = threadIdx.x; i < bins; i += NT) row[i] = hist[i];
 }
 
-template <typename ElemIn, typename ElemOut, int NT, int MODE>
+template <typename ElemIn, typename ElemOut, int NT, int MODE, bool FILTER>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const ElemIn* __restrict__ src, LevelPlan lp, DigitFn<MODE> dg,
                                                      const uint32_t* __restrict__ chunkpref,
                                                      const uint64_t* __restrict__ bstart64, int out_pad, int out_rem,
@@ -405,7 +431,17 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
 #pragma unroll
     for (int u = 0; u < (ITEMS + 1) / 2; u++) rk[u] = 0;
     const bool full = (e1 - e0) == (uint64_t)lp.tile_elems;  // uniform; the common case needs no bounds checks
-    if (full) {
+    if (t + 1 < t1) {  // next tile's keys toward L2 while this tile is ranked, placed and written
+      constexpr int PER_LINE = 128 / (int)sizeof(ElemIn) > 0 ? 128 / (int)sizeof(ElemIn) : 1;
+      if ((threadIdx.x % PER_LINE) == 0) {
+#pragma unroll
+        for (int u = 0; u < ITEMS; u++) {
+          const uint64_t i = e1 + (uint64_t)u * NT + threadIdx.x;
+          if (i < seg_hi) prefetch_l2(src + i);
+        }
+      }
+    }
+    if (full && !FILTER) {
       const ElemIn* __restrict__ p = src + e0 + threadIdx.x;
 #pragma unroll
       for (int u = 0; u < ITEMS; u++) r[u] = p[u * NT];
@@ -414,35 +450,11 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
         const uint32_t rr = atomicAdd(&cnt[dg(r[u])], 1u);
         rk[u >> 1] |= rr << ((u & 1) * 16);
       }
-    } else {
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-        if (i < e1) r[u] = src[i];
-      }
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-        if (i < e1) {
-          const uint32_t rr = atomicAdd(&cnt[dg(r[u])], 1u);
-          rk[u >> 1] |= rr << ((u & 1) * 16);
-        }
-      }
-    }
-    __syncthreads();
-    const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
-    if (full) {
+      __syncthreads();
+      tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
 #pragma unroll
       for (int u = 0; u < ITEMS; u++) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
-    } else {
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-        if (i < e1) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
-      }
-    }
-    __syncthreads();
-    if (full) {
+      __syncthreads();
 #pragma unroll
       for (int u = 0; u < ITEMS; u++) {
         const uint32_t i = u * NT + threadIdx.x;
@@ -450,6 +462,31 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
         out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
       }
     } else {
+      uint32_t live = 0;  // bit u: item u exists and belongs to this round
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
+        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+        if (i < e1) { r[u] = src[i]; live |= 1u << u; }
+      }
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
+        if ((live >> u) & 1u) {
+          const uint32_t d = dg(r[u]);
+          if (FILTER && (d - dg.flo) >= dg.fwidth) {
+            live &= ~(1u << u);
+          } else {
+            const uint32_t rr = atomicAdd(&cnt[d], 1u);
+            rk[u >> 1] |= rr << ((u & 1) * 16);
+          }
+        }
+      }
+      __syncthreads();
+      const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
+#pragma unroll
+      for (int u = 0; u < ITEMS; u++) {
+        if ((live >> u) & 1u) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
+      }
+      __syncthreads();
       for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
         const ElemIn e = stage[i];
         out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);

@@ -36,11 +36,19 @@ def sharded_count(kc, rank, world, group=None, timings=None):
     e0.record()
     send_counts = kc.owner_plan(world)
     n_send = int(send_counts.sum())
-    send = torch.empty(max(n_send, 1) * W, dtype=torch.int64, device=dev)
+    # send buffer = the library's own level-0 key buffer (it is rewritten by the count below anyway);
+    # receive buffer = one torch tensor kept on the counter and reused from step to step
+    send = _wrap_u64(kc.key_buffer(n_send), max(n_send, 1) * W, dev)
     kc.owner_scatter(send.data_ptr())  # synchronous: the library's stream is drained on return
     recv_counts = exchange_plan(send_counts, world, group, dev)
     n_recv = int(recv_counts.sum())
-    recv = torch.empty(max(n_recv, 1) * W, dtype=torch.int64, device=dev)
+    recv = getattr(kc, "_recv_buf", None)
+    if recv is None or recv.numel() < n_recv * W:
+        kc._recv_buf = None
+        del recv
+        torch.cuda.empty_cache()
+        recv = torch.empty(int(max(n_recv, 1) * W * 1.02) + 1024, dtype=torch.int64, device=dev)
+        kc._recv_buf = recv
     e1.record()
     dist.all_to_all_single(recv[: n_recv * W], send[: n_send * W],
                            output_split_sizes=[int(c) * W for c in recv_counts],
@@ -49,7 +57,6 @@ def sharded_count(kc, rank, world, group=None, timings=None):
     torch.cuda.current_stream().synchronize()
     del send
     kc.finish_keys_device(recv.data_ptr(), n_recv)
-    del recv
     # sum the dense spectra in place on the device, then reload on the host side of the library
     ptr, n = kc.spectrum_device()
     spec = _wrap_u64(ptr, n, dev)

@@ -44,12 +44,12 @@ def synth_params(genome_len, read_len, errors=True, **seeds):
 class KmerCounter:
     """One engine context on one GPU."""
 
-    def __init__(self, K, device=0, want_counts=True, prefix_bits=0, reserve_bases=0):
+    def __init__(self, K, device=0, want_counts=True, prefix_bits=0, reserve_bases=0, max_round_keys=0):
         self._L = _lib.lib()
         self.K = int(K)
         self.W = words_per_kmer(self.K)
         cfg = Config(K=self.K, device=device, flags=WANT_SPECTRUM | (WANT_COUNTS if want_counts else 0),
-                     prefix_bits=prefix_bits, reserve_bases=reserve_bases)
+                     prefix_bits=prefix_bits, reserve_bases=reserve_bases, max_round_keys=max_round_keys)
         h = C.c_void_p()
         rc = self._L.apgk_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -178,6 +178,12 @@ class KmerCounter:
     def owner_scatter(self, d_ptr):
         self._ck(self._L.apgk_owner_scatter(self._h, d_ptr))
 
+    def key_buffer(self, n_keys):
+        """device pointer of the library's level-0 key buffer, sized for n_keys k-mers"""
+        p = C.c_void_p()
+        self._ck(self._L.apgk_key_buffer(self._h, n_keys, C.byref(p)))
+        return p.value
+
     def spectrum_device(self):
         p = C.c_void_p()
         n = C.c_uint64()
@@ -202,7 +208,8 @@ class KmerCounter:
     def geometry(self):
         g = (C.c_int32 * 8)()
         self._ck(self._L.apgk_geometry(self._h, g))
-        return dict(D0=g[0], D1=g[1], REM=g[2], elem_bytes=g[3], n_big=g[4], n_deferred=g[5], local_max=g[6])
+        return dict(D0=g[0], D1=g[1], REM=g[2], elem_bytes=g[3], n_big=g[4], n_deferred=g[5], local_max=g[6],
+                    n_rounds=g[7])
 
 
 def owner_of(K, kmers, n_ranks):

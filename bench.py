@@ -41,6 +41,18 @@ CPU_SAMPLE_READS = int(os.environ.get("APGK_BENCH_CPU_READS", 10_000_000))
 B_ALG_K25 = 136.0  # 8 * (2*7 + 3) bytes per instance for the 7-pass LSD model
 
 
+def ncu_traffic(stage):
+    """DRAM bytes per launch of a stage's kernel from the committed full-size ncu capture
+    (profiles/r01_traffic.json: same workload as the N=1 bench), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            k = json.load(f)["kernels"][stage]
+        t = (k["dram_read_GB"] + k["dram_write_GB"]) * 1e9
+        return t if t == t else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -203,6 +215,7 @@ def run_ours(args):
         sampler.start()
     kc.reset_counters()
     stage_acc = {}
+    shard_acc = {}
     barrier()
     t0 = time.perf_counter()
     n_inst_total = 0
@@ -210,6 +223,8 @@ def run_ours(args):
         n_inst_total, tm = step_resident()
         for k_, v in kc.stage_ms().items():
             stage_acc[k_] = stage_acc.get(k_, 0.0) + v
+        for k_, v in (tm or {}).items():
+            shard_acc[k_] = shard_acc.get(k_, 0.0) + v
     barrier()
     dt = time.perf_counter() - t0
     launches = kc.kernel_launches()
@@ -269,15 +284,16 @@ def run_ours(args):
     peak, peak_kind = measured_peaks()
     eb = geo["elem_bytes"]
     alg_bytes = {
-        "hist0": total_bases * 0.375,
-        "scatter0": total_bases * 0.375 + n_local * 8.0,
+        "hist0": n_local * 8.0 if world > 1 else total_bases * 0.375,
+        "scatter0": n_local * 16.0 if world > 1 else total_bases * 0.375 + n_local * 8.0,
         "hist1": n_local * 8.0,
         "scatter1": n_local * (8.0 + eb),
         "local": n_local * float(eb) + nd_local * 12.0,
         "table": nd_local * 24.0,
     }
-    kern_names = {"hist0": "k_hist_reads", "scatter0": "k_scatter_reads", "hist1": "k_hist_keys",
-                  "scatter1": "k_scatter_keys", "local": "k_local", "table": "k_compact(+scan)"}
+    kern_names = {"hist0": "k_hist_keys" if world > 1 else "k_hist_reads",
+                  "scatter0": "k_scatter_keys(level 0)" if world > 1 else "k_scatter_reads", "hist1": "k_hist_keys",
+                  "scatter1": "k_scatter_keys", "local": "k_local3", "table": "k_compact(+scan)"}
     dom = max(alg_bytes, key=lambda s: stage_ms.get(s, 0.0))
     dom_ms = stage_ms.get(dom, 0.0)
     achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -285,8 +301,12 @@ def run_ours(args):
                      "alg_GBps": round(alg_bytes[s] / (stage_ms[s] * 1e-3) / 1e9, 1) if stage_ms.get(s, 0) > 0 else None}
                  for s in alg_bytes}
     pipeline_ms = stage_ms.get("total", ms_step)
+    # measured DRAM bytes of that kernel: one ncu --set full capture of the N=1 workload, committed under profiles/
+    traffic = ncu_traffic(dom) if (n_gpus == 1 and READS_PER_GPU == 60_000_000) else None
     roofline = {"bound": "hbm", "kernel": kern_names[dom], "achieved": round(achieved, 1), "peak": peak,
-                "peak_source": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "peak_source": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_source": "profiles/r01_traffic.json (ncu, separate run)" if traffic else None,
+                "algorithmic_bytes": int(alg_bytes[dom]),
                 "stages": per_stage,
                 "pipeline_model": {"B_alg_bytes_per_kmer": B_ALG_K25,
                                    "lsd_model_equivalent_GBps": round(n_local * B_ALG_K25 / (pipeline_ms * 1e-3) / 1e9, 1),
@@ -304,7 +324,8 @@ def run_ours(args):
         "cpu_baseline": {"value": round(cb_inst / cb_dt / 1e9, 4), "unit": "Gk-mers/s", "cores": cores, "kind": "port",
                          "sample": "first %d reads (%d k-mer instances) of the workload, oracle port "
                                    "(not the reference's code: parity unpinned)" % (CPU_SAMPLE_READS, cb_inst)},
-        "geometry": geo, "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
+        "geometry": geo, "shard_ms": {k_: round(v / args.steps, 2) for k_, v in shard_acc.items()} if shard_acc else None,
+        "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }
     print(json.dumps(line))

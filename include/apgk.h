@@ -66,6 +66,8 @@ typedef struct {
   uint32_t flags;       /* APGK_WANT_* */
   int32_t prefix_bits;  /* 0 = auto; else total bits of the two partition levels (2..24) */
   uint64_t reserve_bases; /* 0 or a hint: pre-size the device read store for this many bases */
+  uint64_t max_round_keys; /* 0 = auto (from free device memory); else the most k-mer instances one
+                              k-mer-space round may hold -- more rounds, less memory */
 } apgk_config;
 
 /* Parameters of the synthetic read generator; identical in the oracle. */
@@ -128,6 +130,10 @@ int apgk_owner_plan(apgk_ctx* ctx, uint32_t n_ranks, uint64_t* counts_out);
 /* Pass 2: write this rank's canonical k-mers grouped by owner (owner 0 first) into the DEVICE
  * buffer d_keys_out (sum(counts) * W words). */
 int apgk_owner_scatter(apgk_ctx* ctx, uint64_t* d_keys_out);
+/* The library's own level-0 key buffer, sized for n_keys k-mers: a caller may use it as the
+ * d_keys_out of apgk_owner_scatter (and as the send buffer of its exchange) instead of allocating
+ * another N*W words.  Its contents are overwritten by the next apgk_finish* call. */
+int apgk_key_buffer(apgk_ctx* ctx, uint64_t n_keys, uint64_t** d_ptr);
 /* Owner hash of k-mers (host arrays), for tests. */
 int apgk_owner_of(int K, const uint64_t* kmers, uint64_t n, uint32_t n_ranks, uint32_t* owner_out);
 /* Sort + count a DEVICE array of n canonical k-mers (W words each) instead of the read store. */
@@ -146,7 +152,8 @@ const char* apgk_stage_name(int i);
 uint64_t apgk_kernel_launches(const apgk_ctx* ctx);
 void apgk_reset_counters(apgk_ctx* ctx);
 /* Geometry of the last finish: D0, D1, REM bits, element bytes of the level-1 buffer, number of
- * oversize buckets (k_big), number of buckets deferred to the general kernel, bucket capacity, 0. */
+ * oversize buckets (k_big), number of buckets deferred to the general kernel, bucket capacity,
+ * number of k-mer-space rounds. */
 int apgk_geometry(const apgk_ctx* ctx, int32_t* out8);
 /* Device buffers for callers without their own allocator (e.g. the exchange buffers of the
  * multi-GPU path in a plain C++ host), and a synchronous device-to-host copy. */

@@ -162,6 +162,30 @@ def test_huge_multiplicity_32bit_path(oracle):
         kc.close()
 
 
+@pytest.mark.parametrize("K", [20, 25, 31, 48, 96])
+def test_kmer_space_rounds(oracle, K):
+    """A small per-round budget forces several k-mer-space rounds (the SortKmers 'passes' / KmerParcels
+    'parcels' mechanism): results, table order, lookup index and spectrum must not change."""
+    from allpathslg_b200 import KmerCounter
+
+    sp = oracle.synth_params(400_000, 150)
+    p, o = oracle.synth_reads(sp, 0, 20_000)
+    ek, ec, en = oracle.count(p, o, K)
+    for budget in (en // 5 + 1, en // 2 + 1):
+        kc = KmerCounter(K, max_round_keys=budget)
+        kc.add_reads_uniform(p, 20_000, 150)
+        kc.finish()
+        assert kc.geometry()["n_rounds"] >= 2
+        _assert_equal_to_oracle(oracle, kc, p, o, K)
+        idx = np.random.RandomState(K).randint(0, len(ek), size=2000)
+        assert (kc.lookup(ek[idx], canonicalise=False).astype(np.uint64) == ec[idx]).all()
+        rf = kc.read_freqs(0, 30_000)
+        erf = oracle.read_freqs(p, o[:201], K, ek, ec)
+        erf32 = np.where(erf == np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0xFFFFFFFF), erf).astype(np.uint32)
+        assert (rf == erf32).all()
+        kc.close()
+
+
 def test_empty_and_short_inputs(oracle):
     from allpathslg_b200 import KmerCounter
 
@@ -358,7 +382,7 @@ def test_owner_partition_and_key_ingest(oracle, K, world):
     for r in range(world):
         grp = host[start:start + int(cnts[r])]
         assert (owner_of(K, grp, world) == r).all()
-        kr = KmerCounter(K)
+        kr = KmerCounter(K, max_round_keys=(int(cnts[r]) // 3 + 1) if r == 0 else 0)  # rank 0's shard in 3+ rounds
         kr.finish_keys_device(buf.data_ptr() + start * W * 8, int(cnts[r]))
         gk, gc = kr.counts()
         sel = own == r

@@ -114,7 +114,7 @@ def test_create_fails_loudly_without_gpu(apgk_lib):
 
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    cfg = _lib.Config(K=25, device=0, flags=3, prefix_bits=0, reserve_bases=0)
+    cfg = _lib.Config(K=25, device=0, flags=3, prefix_bits=0, reserve_bases=0, max_round_keys=0)
     h = C.c_void_p()
     assert apgk_lib.apgk_create(C.byref(cfg), C.byref(h)) == _lib.E_CUDA
     assert not h.value
@@ -124,7 +124,7 @@ def test_create_rejects_bad_k(apgk_lib):
     from allpathslg_b200 import _lib
 
     for K in (0, -3, 97):
-        cfg = _lib.Config(K=K, device=0, flags=3, prefix_bits=0, reserve_bases=0)
+        cfg = _lib.Config(K=K, device=0, flags=3, prefix_bits=0, reserve_bases=0, max_round_keys=0)
         h = C.c_void_p()
         assert apgk_lib.apgk_create(C.byref(cfg), C.byref(h)) == _lib.E_ARG
 
