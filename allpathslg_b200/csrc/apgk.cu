@@ -120,7 +120,15 @@ namespace {
 static const bool kSyncDebug = getenv("APGK_SYNC_DEBUG") != nullptr;  // sync after every launch to localise faults
 #define LAUNCHED() do { c->launches++; CU(cudaGetLastError()); if (kSyncDebug) CU(cudaStreamSynchronize(c->stream)); } while (0)
 
-void stage_begin(apgk_ctx* c, int s) { cudaEventRecord(c->ev[s][0], c->stream); c->ev_used[s] = true; }
+// A stage may run once per round: its previous interval is folded into stage_ms before the events are reused.
+void stage_flush(apgk_ctx* c, int s) {
+  if (!c->ev_used[s]) return;
+  float ms = 0;
+  if (cudaEventSynchronize(c->ev[s][1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev[s][0], c->ev[s][1]) == cudaSuccess)
+    c->stage_ms[s] += ms;
+  c->ev_used[s] = false;
+}
+void stage_begin(apgk_ctx* c, int s) { stage_flush(c, s); cudaEventRecord(c->ev[s][0], c->stream); c->ev_used[s] = true; }
 void stage_end(apgk_ctx* c, int s) { cudaEventRecord(c->ev[s][1], c->stream); }
 
 int words_for(int K) { return (2 * K + 63) / 64; }
@@ -335,8 +343,7 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   if (c->deferred.p && c->n_instances)
     CU(cudaMemcpyAsync(&c->n_deferred, c->deferred.p, 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  for (int s = 0; s < APGK_N_STAGES; s++)
-    if (c->ev_used[s]) cudaEventElapsedTime(&c->stage_ms[s], c->ev[s][0], c->ev[s][1]);
+  for (int s = 0; s < APGK_N_STAGES; s++) stage_flush(c, s);
   c->finished = true;
   return APGK_OK;
 }
@@ -418,8 +425,10 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     k_hist_keys<Key<W>, Geo<W>::NT1, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT1, bins0 * 4, c->stream>>>(
         dev_keys, hp0.lp, dg0, c->chunksum0.as<uint32_t>());
   } else {
+    // cheap formulation when the digit is a clean prefix of the real k-mer (no left padding, <= 8 bases)
+    const int top_bits = (g.pad == 0 && g.D0 <= 16 && c->cfg.K >= (g.D0 + 1) / 2 && !getenv("APGK_NO_TOPDIGITS")) ? g.D0 : 0;
     k_hist_reads<W, Geo<W>::NT0, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT0, bins0 * 4, c->stream>>>(
-        read_store(c), dg0, hp0.lp, c->chunksum0.as<uint32_t>());
+        read_store(c), dg0, hp0.lp, top_bits, c->chunksum0.as<uint32_t>());
   }
   LAUNCHED();
   stage_end(c, ST_HIST0);
@@ -786,7 +795,7 @@ int owner_plan_impl(apgk_ctx* c, uint32_t n_ranks, uint64_t* counts_out) {
     CU(c->chunksum.ensure((size_t)hp.lp.n_chunks * n_ranks * 4));
     stage_begin(c, ST_OWNER);
     k_hist_reads<W, Geo<W>::NT0, DIGIT_OWNER><<<hp.lp.n_chunks, Geo<W>::NT0, n_ranks * 4, c->stream>>>(
-        read_store(c), dg, hp.lp, c->chunksum.as<uint32_t>());
+        read_store(c), dg, hp.lp, 0, c->chunksum.as<uint32_t>());
     LAUNCHED();
     { int rc = column_scan(c, hp, 0, nullptr); if (rc) return rc; }
     CU(cudaMemcpyAsync(c->owner_counts.data(), c->segtot.p, (size_t)n_ranks * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1208,6 +1217,22 @@ int apgk_debug_host_extract(const uint8_t* packed, const uint64_t* off, uint64_t
     case 2: host_extract<2>(packed, off, n_reads, K, kmers_out, valid_out); break;
     case 3: host_extract<3>(packed, off, n_reads, K, kmers_out, valid_out); break;
   }
+  return APGK_OK;
+}
+
+int apgk_debug_host_topdigits(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, int D,
+                              uint32_t* digits_out) {
+  if (!packed || !off || !digits_out || K < 1 || K > APGK_MAX_K || D < 1 || D > 16 || K < (D + 1) / 2 || 2 * K < D)
+    return APGK_E_ARG;
+  if (!n_reads) return APGK_OK;
+  const uint64_t b0 = off[0], total = off[n_reads] - b0;
+  std::vector<uint32_t> bases((total + 15) / 16 + 16, 0);
+  for (uint64_t q = 0; q < total; q++) {
+    const uint64_t s = b0 + q;
+    bases[q >> 4] |= (uint32_t)((packed[s >> 2] >> ((s & 3) * 2)) & 3u) << ((q & 15) * 2);
+  }
+  for (uint64_t p = 0; p < total; p += 16)
+    top_digits16(bases.data(), p, K, D, [&](int j, uint32_t d) { if (p + j < total) digits_out[p + j] = d; });
   return APGK_OK;
 }
 

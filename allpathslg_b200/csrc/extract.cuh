@@ -91,6 +91,38 @@ APGK_HD void extract16(const Window16<W>& win, int K, F&& f) {
   }
 }
 
+// Level-0 digits without building the k-mers.  The top D bits of canonical = min(fw, rc) are
+// min(top D bits of fw, top D bits of rc): if the tops differ they decide the comparison, if they are
+// equal both candidates share them.  The top bits of fw are the window's FIRST nb = ceil(D/2) bases,
+// those of rc the complement of its LAST nb bases -- which, the stream being little-endian, is just
+// ~(stream >> 2(p+K-nb)) & mask.  ~12 instructions per position instead of ~40 for the full k-mers.
+// Requires nb <= 8 and K >= nb; one-word and multi-word k-mers alike.  f(j, digit) for j = 0..15.
+template <typename F>
+APGK_HD void top_digits16(const uint32_t* __restrict__ bases32, uint64_t p, int K, int D, F&& f) {
+  const int nb = (D + 1) >> 1;
+  const uint32_t mask = lowmask32(2 * nb);
+  const uint64_t wi = p >> 4;
+  // forward side: bases p .. p+15+nb-1 (at most 24 of them) live in two words
+  const uint32_t f0 = bases32[wi], f1 = bases32[wi + 1];
+  const uint64_t wf = ((uint64_t)f0 | ((uint64_t)f1 << 32)) >> (2 * nb);  // base (p + nb + j) at bits [2j, 2j+2)
+  uint32_t x = f0 & mask;                                                  // first nb bases, little-endian
+  x = (uint32_t)(swap_pairs(brev64((uint64_t)x)) >> (64 - 2 * nb));        // -> first base most significant
+  // reverse side: the stream from base p + K - nb on, word-aligned in registers
+  const uint64_t q = p + (uint64_t)(K - nb);
+  const uint64_t ri = q >> 4;
+  const uint32_t rs = 2u * (uint32_t)(q & 15);
+  const uint32_t r0 = bases32[ri], r1 = bases32[ri + 1], r2 = bases32[ri + 2];
+  const uint32_t u0 = funnel_r(r0, r1, rs), u1 = funnel_r(r1, r2, rs);
+  const int drop = 2 * nb - D;  // 1 when D is odd
+#pragma unroll
+  for (int j = 0; j < POS_PER_THREAD; j++) {
+    const uint32_t rc_top = ~funnel_r(u0, u1, 2 * j) & mask;
+    const uint32_t d = (x < rc_top ? x : rc_top) >> drop;
+    f(j, d);
+    if (j + 1 < POS_PER_THREAD) x = ((x << 2) | ((uint32_t)(wf >> (2 * j)) & 3u)) & mask;
+  }
+}
+
 // Bit j of the result is set iff window [p+j, p+j+K) lies inside one read:
 // p+j+K <= total_bases and no read starts strictly inside the window.
 // starts32: 1 bit per base (bit q of the bitmap = "a read starts at base q"),

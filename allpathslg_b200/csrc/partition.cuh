@@ -179,8 +179,10 @@ struct ReadStore {
 };
 
 // One CTA per CHUNK of tiles: shared-memory histogram over the whole chunk -> one row of chunksum.
+// top_bits > 0 selects the cheap level-0 formulation (top_digits16): the digit is the top `top_bits`
+// bits of the canonical k-mer and nothing else of the k-mer is needed.
 template <int W, int NT, int MODE>
-__global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp,
+__global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp, int top_bits,
                                                    uint32_t* __restrict__ chunksum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* hist = (uint32_t*)smem_raw;
@@ -194,11 +196,17 @@ __global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> d
     if (p < rs.total_bases) {
       const uint32_t valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
       if (valid) {
-        Window16<W> win;
-        load_window16<W>(rs.bases32, p, rs.K, win);
-        extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
-          if ((valid >> j) & 1u) atomicAdd(&hist[dg(c)], 1u);
-        });
+        if (MODE == DIGIT_BITS && top_bits > 0) {
+          top_digits16(rs.bases32, p, rs.K, top_bits, [&](int j, uint32_t d) {
+            if ((valid >> j) & 1u) atomicAdd(&hist[d], 1u);
+          });
+        } else {
+          Window16<W> win;
+          load_window16<W>(rs.bases32, p, rs.K, win);
+          extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
+            if ((valid >> j) & 1u) atomicAdd(&hist[dg(c)], 1u);
+          });
+        }
       }
     }
   }

@@ -169,6 +169,9 @@ int apgk_host_free(void* p);
 int apgk_debug_host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K,
                             uint64_t* kmers_out /* total_bases * W */, uint8_t* valid_out /* total_bases */);
 int apgk_debug_host_canonical(int K, const uint64_t* kmers, uint64_t n, uint64_t* out);
+/* level-0 digit (top D bits of the canonical k-mer) of every window start, via the cheap top-bits identity */
+int apgk_debug_host_topdigits(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, int D,
+                              uint32_t* digits_out /* total_bases */);
 int apgk_debug_host_synth(const apgk_synth_params* p, uint64_t r0, uint64_t n_reads, uint8_t* packed_out);
 
 #ifdef __cplusplus

@@ -45,6 +45,23 @@ def test_extract_helpers_match_oracle_b(apgk_lib, oracle, K):
     assert (exp_valid == va).all()
 
 
+@pytest.mark.parametrize("K,D", [(25, 10), (25, 11), (25, 12), (20, 9), (33, 12), (64, 11), (96, 12), (8, 10), (6, 12), (13, 1)])
+def test_top_digit_identity(apgk_lib, oracle, K, D):
+    """top_digits16 (cheap level-0 histogram): top D bits of canonical == min(top D of fw, top D of rc),
+    computed from the first / last ceil(D/2) bases only -- against the full extraction, window by window."""
+    rnd = random.Random(K * 100 + D)
+    reads = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([K, K + 1, K + 20, 130]))) for _ in range(40)]
+    reads += ["A" * (K + 20), "ACGT" * 30, "T" * (K + 5), "AAAAAAAAAAAAAAAACCCCCCCCCCCCCCCCGGGGGGGGGGGGGGGGTTTTTTTTTTTTTTTT" * 3]
+    p, o = oracle.pack_strings(reads)
+    km, va = _host_extract(apgk_lib, p, o, K)
+    W = (2 * K + 63) // 64
+    dig = np.zeros(int(o[-1]), dtype=np.uint32)
+    assert apgk_lib.apgk_debug_host_topdigits(p.ctypes.data, o.ctypes.data, len(o) - 1, K, D, dig.ctypes.data) == 0
+    for pos in np.nonzero(va)[0]:
+        full = sum(int(km[pos, j]) << (64 * (W - 1 - j)) for j in range(W))
+        assert int(dig[pos]) == full >> (2 * K - D), (K, D, pos)
+
+
 @pytest.mark.parametrize("K", [1, 5, 25, 32, 33, 64, 65, 96])
 def test_canonical_helper(apgk_lib, K):
     rnd = random.Random(K)
