@@ -34,6 +34,56 @@
 
 namespace apgk {
 
+// Shared memory through 32-bit shared-window addresses and explicit ld/st/atom.shared: with generic
+// pointers into the dynamic shared array ptxas re-derived the array bases (S2UR SR_CgaCtaId, ULEA, ...)
+// for every key -- ~10 of ~30 instructions per key and phase in the scatter kernels' first SASS.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+  uint32_t r;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(addr), "r"(v) : "memory");
+  return r;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+  uint64_t r;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void sts_key(uint32_t addr, const Key<W>& k) {
+#pragma unroll
+  for (int i = 0; i < W; i++) sts_u64(addr + 8 * i, k.w[i]);
+}
+template <int W>
+__device__ __forceinline__ Key<W> lds_key(uint32_t addr) {
+  Key<W> k;
+#pragma unroll
+  for (int i = 0; i < W; i++) k.w[i] = lds_u64(addr + 8 * i);
+  return k;
+}
+
+template <typename T> struct SmemElem;
+template <int W> struct SmemElem<Key<W>> {
+  __device__ __forceinline__ static void st(uint32_t a, const Key<W>& k) { sts_key<W>(a, k); }
+  __device__ __forceinline__ static Key<W> ld(uint32_t a) { return lds_key<W>(a); }
+};
+template <> struct SmemElem<uint32_t> {
+  __device__ __forceinline__ static void st(uint32_t a, const uint32_t& k) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(k) : "memory");
+  }
+  __device__ __forceinline__ static uint32_t ld(uint32_t a) { return lds_u32(a); }
+};
+
 constexpr int DIGIT_BITS = 0;   // digit = key bits [pos, pos+len)
 constexpr int DIGIT_OWNER = 1;  // digit = owner rank of the canonical k-mer (multi-GPU shuffle)
 
@@ -48,8 +98,8 @@ struct DigitSpec {
 // (the generic pad/mode/lowmask code cost ~25 of 59 instructions per position in the first profile).
 template <int MODE>
 struct DigitFn {
-  int kind;          // W == 1: 0 = bits straddle/below word 1 (funnel shift), 1 = bits in the high word, 2 = left shift (tiny K)
-  int sh;            // shift amount for `kind`
+  int kind;          // W == 1: left shift applied after the right shift (tiny K: digit reaches below bit 0), else 0
+  int sh;            // W == 1: right shift of the one-word key
   uint32_t mask;
   int rsh;           // 32-bit elements: (e >> rsh) & mask
   int pos, len;      // W > 1: key_bits(k, pos, len)
@@ -59,13 +109,10 @@ struct DigitFn {
   __device__ __forceinline__ uint32_t operator()(const Key<W>& k) const {
     if constexpr (MODE == DIGIT_OWNER) return key_owner(k, n_ranks);
     else if constexpr (W == 1) {
-      // 32-bit formulation: a 64-bit shift by a register amount costs 4-5 instructions, this costs 2
-      const uint32_t lo = (uint32_t)k.w[0], hi = (uint32_t)(k.w[0] >> 32);
-      uint32_t d;
-      if (kind == 0) d = __funnelshift_r(lo, hi, sh);
-      else if (kind == 1) d = hi >> sh;
-      else d = lo << sh;
-      return d & mask;
+      // branch-free: low word of a 64-bit right shift (one SHF.R.U64 once the amount is known < 64),
+      // then the tiny-K left shift (0 otherwise) and the mask
+      const uint32_t t = (uint32_t)(k.w[0] >> (sh & 63));
+      return (t << (kind & 31)) & mask;
     } else return key_bits(k, pos, len);
   }
   __device__ __forceinline__ uint32_t operator()(uint32_t e) const { return (e >> rsh) & mask; }
@@ -74,9 +121,8 @@ template <int MODE>
 inline DigitFn<MODE> make_digit_fn(const DigitSpec& ds) {
   DigitFn<MODE> f;
   const int eff = ds.pos - ds.pad;  // position of the digit inside the real (unpadded) one-word key
-  if (eff >= 32) { f.kind = 1; f.sh = eff - 32; }
-  else if (eff >= 0) { f.kind = 0; f.sh = eff; }
-  else { f.kind = 2; f.sh = -eff; }
+  if (eff >= 0) { f.kind = 0; f.sh = eff; }
+  else { f.kind = -eff; f.sh = 0; }
   f.mask = lowmask32(ds.len);
   f.rsh = ds.pos;
   f.pos = ds.pos; f.len = ds.len; f.n_ranks = ds.n_ranks;
@@ -191,6 +237,7 @@ __global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> d
   __syncthreads();
   int s; uint32_t t0, t1;
   chunk_tiles(lp, blockIdx.x, s, t0, t1);
+  const uint32_t hist_a = smem_u32(hist);
   for (uint32_t t = t0; t < t1; t++) {
     const uint64_t p = ((uint64_t)t * NT + threadIdx.x) * POS_PER_THREAD;
     if (p < rs.total_bases) {
@@ -198,13 +245,13 @@ __global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> d
       if (valid) {
         if (MODE == DIGIT_BITS && top_bits > 0) {
           top_digits16(rs.bases32, p, rs.K, top_bits, [&](int j, uint32_t d) {
-            if ((valid >> j) & 1u) atomicAdd(&hist[d], 1u);
+            if ((valid >> j) & 1u) reds_add(hist_a + 4 * d, 1u);
           });
         } else {
           Window16<W> win;
           load_window16<W>(rs.bases32, p, rs.K, win);
           extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
-            if ((valid >> j) & 1u) atomicAdd(&hist[dg(c)], 1u);
+            if ((valid >> j) & 1u) reds_add(hist_a + 4 * dg(c), 1u);
           });
         }
       }
@@ -301,9 +348,11 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
   chunk_tiles(lp, blockIdx.x, s, t0, t1);
   chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, 0ull, bins, Gabs, cnt2);
   __syncthreads();
+  const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G);
   for (uint32_t t = t0; t < t1; t++) {
     uint32_t* cnt = cnt2 + ((t - t0) & 1u) * bins;
     uint32_t* cnt_next = cnt2 + (((t - t0) & 1u) ^ 1u) * bins;
+    const uint32_t cnt_a = smem_u32(cnt);
     // ---- phase 1: extract 16 windows into registers; each key takes its rank inside (tile, bin)
     Key<W> key[POS_PER_THREAD];
     uint32_t rk[POS_PER_THREAD / 2];  // two 16-bit ranks per register
@@ -329,7 +378,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
           if (FILTER && (d - dg.flo) >= dg.fwidth) {
             valid &= ~(1u << j);  // belongs to another round
           } else {
-            const uint32_t r = atomicAdd(&cnt[d], 1u);
+            const uint32_t r = atoms_add(cnt_a + 4 * d, 1u);
             rk[j >> 1] |= r << ((j & 1) * 16);
           }
         }
@@ -341,7 +390,10 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
     if (valid) {
 #pragma unroll
       for (int j = 0; j < POS_PER_THREAD; j++) {
-        if ((valid >> j) & 1u) stage[cnt[dg(key[j])] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu)] = key[j];
+        if ((valid >> j) & 1u) {
+          const uint32_t slot = lds_u32(cnt_a + 4 * dg(key[j])) + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+          sts_key<W>(stage_a + slot * (uint32_t)sizeof(Key<W>), key[j]);
+        }
       }
     }
     __syncthreads();
@@ -351,12 +403,12 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const uint32_t i = i0 + u * NT + threadIdx.x;
-        if (i < tile_n) kq[u] = stage[i];
+        if (i < tile_n) kq[u] = lds_key<W>(stage_a + i * (uint32_t)sizeof(Key<W>));
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const uint32_t i = i0 + u * NT + threadIdx.x;
-        if (i < tile_n) out[G[dg(kq[u])] + i] = kq[u];
+        if (i < tile_n) out[lds_u64(G_a + 8 * dg(kq[u])) + i] = kq[u];
       }
     }
     __syncthreads();  // stage and G are reused by the next tile
@@ -396,6 +448,7 @@ __global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, 
   uint64_t e1 = seg_lo + (uint64_t)(t1 - lp.seg_tile0[s]) * lp.tile_elems;
   if (e1 > seg_hi) e1 = seg_hi;
   constexpr int U = 4;
+  const uint32_t hist_a = smem_u32(hist);
   for (uint64_t base = e0; base < e1; base += (uint64_t)NT * U) {
     Elem r[U];
 #pragma unroll
@@ -406,7 +459,7 @@ __global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, 
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint64_t i = base + (uint64_t)u * NT + threadIdx.x;
-      if (i < e1) atomicAdd(&hist[dg(r[u])], 1u);
+      if (i < e1) reds_add(hist_a + 4 * dg(r[u]), 1u);
     }
   }
   __syncthreads();
@@ -429,9 +482,12 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
   chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, bstart64 ? 0ull : seg_lo, bins, Gabs, cnt2);
   __syncthreads();
   constexpr int ITEMS = TileItems<ElemIn>::N;  // lp.tile_elems == NT * ITEMS
+  constexpr uint32_t ES = (uint32_t)sizeof(ElemIn);
+  const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G);
   for (uint32_t t = t0; t < t1; t++) {
     uint32_t* cnt = cnt2 + ((t - t0) & 1u) * bins;
     uint32_t* cnt_next = cnt2 + (((t - t0) & 1u) ^ 1u) * bins;
+    const uint32_t cnt_a = smem_u32(cnt);
     const uint64_t e0 = seg_lo + (uint64_t)(t - lp.seg_tile0[s]) * lp.tile_elems;
     const uint64_t e1 = e0 + lp.tile_elems < seg_hi ? e0 + lp.tile_elems : seg_hi;
     ElemIn r[ITEMS];
@@ -455,19 +511,22 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
       for (int u = 0; u < ITEMS; u++) r[u] = p[u * NT];
 #pragma unroll
       for (int u = 0; u < ITEMS; u++) {
-        const uint32_t rr = atomicAdd(&cnt[dg(r[u])], 1u);
+        const uint32_t rr = atoms_add(cnt_a + 4 * dg(r[u]), 1u);
         rk[u >> 1] |= rr << ((u & 1) * 16);
       }
       __syncthreads();
       tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
 #pragma unroll
-      for (int u = 0; u < ITEMS; u++) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
+      for (int u = 0; u < ITEMS; u++) {
+        const uint32_t slot = lds_u32(cnt_a + 4 * dg(r[u])) + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu);
+        SmemElem<ElemIn>::st(stage_a + slot * ES, r[u]);
+      }
       __syncthreads();
 #pragma unroll
       for (int u = 0; u < ITEMS; u++) {
         const uint32_t i = u * NT + threadIdx.x;
-        const ElemIn e = stage[i];
-        out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
+        const ElemIn e = SmemElem<ElemIn>::ld(stage_a + i * ES);
+        out[lds_u64(G_a + 8 * dg(e)) + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
       }
     } else {
       uint32_t live = 0;  // bit u: item u exists and belongs to this round
@@ -483,7 +542,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
           if (FILTER && (d - dg.flo) >= dg.fwidth) {
             live &= ~(1u << u);
           } else {
-            const uint32_t rr = atomicAdd(&cnt[d], 1u);
+            const uint32_t rr = atoms_add(cnt_a + 4 * d, 1u);
             rk[u >> 1] |= rr << ((u & 1) * 16);
           }
         }
@@ -492,12 +551,15 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
       const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
 #pragma unroll
       for (int u = 0; u < ITEMS; u++) {
-        if ((live >> u) & 1u) stage[cnt[dg(r[u])] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu)] = r[u];
+        if ((live >> u) & 1u) {
+          const uint32_t slot = lds_u32(cnt_a + 4 * dg(r[u])) + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu);
+          SmemElem<ElemIn>::st(stage_a + slot * ES, r[u]);
+        }
       }
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
-        const ElemIn e = stage[i];
-        out[G[dg(e)] + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
+        const ElemIn e = SmemElem<ElemIn>::ld(stage_a + i * ES);
+        out[lds_u64(G_a + 8 * dg(e)) + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
       }
     }
     __syncthreads();  // stage and G are reused by the next tile
