@@ -72,15 +72,47 @@ __device__ __forceinline__ Key<W> lds_key(uint32_t addr) {
   return k;
 }
 
+// Predicated forms: a per-key `if` around an atomic or a store compiles to BSSY/BRA/BSYNC per key, and
+// at read ends nearly every warp has both kinds of lanes, so the branch never skips anything.
+__device__ __forceinline__ uint32_t atoms_add_if(uint32_t addr, uint32_t v, uint32_t pred) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.u32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+               : "=r"(r) : "r"(addr), "r"(v), "r"(pred) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_u64_if(uint32_t addr, uint64_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u64 [%0], %1;\n\t}" ::"r"(addr), "l"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void stg_u64_if(void* ptr, uint64_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u64 [%0], %1;\n\t}" ::"l"(ptr), "l"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void stg_u32_if(void* ptr, uint32_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"(pred) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void stg_if(Key<W>* ptr, const Key<W>& k, uint32_t pred) {
+#pragma unroll
+  for (int i = 0; i < W; i++) stg_u64_if(&ptr->w[i], k.w[i], pred);
+}
+__device__ __forceinline__ void stg_if(uint32_t* ptr, const uint32_t& k, uint32_t pred) { stg_u32_if(ptr, k, pred); }
+
 template <typename T> struct SmemElem;
 template <int W> struct SmemElem<Key<W>> {
   __device__ __forceinline__ static void st(uint32_t a, const Key<W>& k) { sts_key<W>(a, k); }
+  __device__ __forceinline__ static void st_if(uint32_t a, const Key<W>& k, uint32_t pred) {
+#pragma unroll
+    for (int i = 0; i < W; i++) sts_u64_if(a + 8 * i, k.w[i], pred);
+  }
   __device__ __forceinline__ static Key<W> ld(uint32_t a) { return lds_key<W>(a); }
 };
 template <> struct SmemElem<uint32_t> {
   __device__ __forceinline__ static void st(uint32_t a, const uint32_t& k) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(k) : "memory");
   }
+  __device__ __forceinline__ static void st_if(uint32_t a, const uint32_t& k, uint32_t pred) { sts_u32_if(a, k, pred); }
   __device__ __forceinline__ static uint32_t ld(uint32_t a) { return lds_u32(a); }
 };
 
@@ -336,6 +368,9 @@ __device__ __forceinline__ uint32_t tile_scan(int bins, unsigned long long* G, u
   return total;
 }
 
+// Software-pipelined over tiles like k_scatter_keys below: the extraction and ranking of tile t+1
+// (ALU + shared atomics) is interleaved, position by position, with the write-out of tile t
+// (LDS -> LDS -> STG), so the one resident CTA per SM overlaps its compute with its stores.
 template <int W, int NT, int MODE, bool FILTER>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp,
                                                       const uint32_t* __restrict__ chunkpref,
@@ -347,71 +382,66 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
   int s; uint32_t t0, t1;
   chunk_tiles(lp, blockIdx.x, s, t0, t1);
   chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, 0ull, bins, Gabs, cnt2);
-  __syncthreads();
-  const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G);
-  for (uint32_t t = t0; t < t1; t++) {
-    uint32_t* cnt = cnt2 + ((t - t0) & 1u) * bins;
-    uint32_t* cnt_next = cnt2 + (((t - t0) & 1u) ^ 1u) * bins;
-    const uint32_t cnt_a = smem_u32(cnt);
-    // ---- phase 1: extract 16 windows into registers; each key takes its rank inside (tile, bin)
-    Key<W> key[POS_PER_THREAD];
-    uint32_t rk[POS_PER_THREAD / 2];  // two 16-bit ranks per register
-    uint32_t valid = 0;
+  constexpr uint32_t ES = (uint32_t)sizeof(Key<W>);
+  const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G), cnt2_a = smem_u32(cnt2);
+  Key<W> key[POS_PER_THREAD];
+  uint32_t rk[POS_PER_THREAD / 2];  // two 16-bit ranks per register
+  uint32_t valid = 0;               // bit j: window j of the tile in key[] is a k-mer of this round
+  // tile t: 16 windows per thread -> key[], valid; each k-mer takes its rank inside (tile, bin) from one
+  // shared atomic.  between(j) runs after window j (the write-out of the previous tile hooks in here).
+  auto extract_rank = [&](uint32_t t, uint32_t cnt_a, auto&& between) {
     const uint64_t p = ((uint64_t)t * NT + threadIdx.x) * POS_PER_THREAD;
-    if (p < rs.total_bases) valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
+    const bool inside = p < rs.total_bases;
+    valid = inside ? window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases) : 0u;
 #pragma unroll
     for (int j = 0; j < POS_PER_THREAD / 2; j++) rk[j] = 0;
-    if (t + 1 < t1) {  // the next tile's bases / start bits: pull them into L1 while this tile is ranked and written
-      const uint64_t pn = p + (uint64_t)NT * POS_PER_THREAD;
-      if (pn < rs.total_bases) {
-        if ((threadIdx.x & 7) == 0) prefetch_l1(rs.bases32 + (pn >> 4));   // 8 threads share a 32-byte sector
-        if ((threadIdx.x & 15) == 0) prefetch_l1(rs.starts32 + (pn >> 5));
-      }
-    }
-    if (valid) {
-      Window16<W> win;
-      load_window16<W>(rs.bases32, p, rs.K, win);
-      extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
-        key[j] = c;
-        if ((valid >> j) & 1u) {
-          const uint32_t d = dg(c);
-          if (FILTER && (d - dg.flo) >= dg.fwidth) {
-            valid &= ~(1u << j);  // belongs to another round
-          } else {
-            const uint32_t r = atoms_add(cnt_a + 4 * d, 1u);
-            rk[j >> 1] |= r << ((j & 1) * 16);
-          }
-        }
-      });
-    }
-    __syncthreads();
+    Window16<W> win;
+    load_window16<W>(rs.bases32, inside ? p : 0ull, rs.K, win);
+    extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
+      key[j] = c;
+      const uint32_t d = dg(c);
+      if (FILTER) valid &= ~((uint32_t)((d - dg.flo) >= dg.fwidth) << j);  // belongs to another round
+      const uint32_t r = atoms_add_if(cnt_a + 4 * d, 1u, valid & (1u << j));
+      rk[j >> 1] |= r << ((j & 1) * 16);
+      between(j);
+    });
+  };
+  __syncthreads();  // chunk_begin
+  extract_rank(t0, cnt2_a, [](int) {});
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t cur = (t - t0) & 1u;
+    uint32_t* cnt = cnt2 + cur * bins;
+    uint32_t* cnt_next = cnt2 + (cur ^ 1u) * bins;
+    const uint32_t cnt_a = cnt2_a + cur * 4u * (uint32_t)bins, cnt_next_a = cnt2_a + (cur ^ 1u) * 4u * (uint32_t)bins;
+    __syncthreads();  // ranks of tile t complete; write-out of tile t-1 done with stage and G
     const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
-    // ---- phase 2: place the keys in bin order in the stage
-    if (valid) {
+    // ---- place the keys in bin order in the stage
 #pragma unroll
-      for (int j = 0; j < POS_PER_THREAD; j++) {
-        if ((valid >> j) & 1u) {
-          const uint32_t slot = lds_u32(cnt_a + 4 * dg(key[j])) + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
-          sts_key<W>(stage_a + slot * (uint32_t)sizeof(Key<W>), key[j]);
-        }
-      }
+    for (int j = 0; j < POS_PER_THREAD; j++) {
+      const uint32_t slot = lds_u32(cnt_a + 4 * dg(key[j])) + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+      SmemElem<Key<W>>::st_if(stage_a + slot * ES, key[j], valid & (1u << j));
     }
     __syncthreads();
-    // ---- coalesced runs out
-    for (uint32_t i0 = 0; i0 < tile_n; i0 += 4 * NT) {  // 4 independent LDS -> digit -> LDS -> STG chains in flight
-      Key<W> kq[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t i = i0 + u * NT + threadIdx.x;
-        if (i < tile_n) kq[u] = lds_key<W>(stage_a + i * (uint32_t)sizeof(Key<W>));
+    // ---- coalesced runs of tile t out, interleaved with the windows of tile t+1.
+    // Slots past tile_n hold stale keys: reading them and their (in-range) bins is harmless.
+    auto write_out = [&](int j) {
+      const uint32_t i = (uint32_t)j * NT + threadIdx.x;
+      const Key<W> kq = lds_key<W>(stage_a + i * ES);
+      stg_if(out + lds_u64(G_a + 8 * dg(kq)) + i, kq, (uint32_t)(i < tile_n));
+    };
+    if (t + 1 < t1) {
+      if (t + 2 < t1) {  // the bases / start bits of tile t+2 toward L1
+        const uint64_t pn = ((uint64_t)(t + 2) * NT + threadIdx.x) * POS_PER_THREAD;
+        if (pn < rs.total_bases) {
+          if ((threadIdx.x & 7) == 0) prefetch_l1(rs.bases32 + (pn >> 4));   // 8 threads share a 32-byte sector
+          if ((threadIdx.x & 15) == 0) prefetch_l1(rs.starts32 + (pn >> 5));
+        }
       }
+      extract_rank(t + 1, cnt_next_a, write_out);
+    } else {
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t i = i0 + u * NT + threadIdx.x;
-        if (i < tile_n) out[lds_u64(G_a + 8 * dg(kq[u])) + i] = kq[u];
-      }
+      for (int j = 0; j < POS_PER_THREAD; j++) write_out(j);
     }
-    __syncthreads();  // stage and G are reused by the next tile
   }
 }
 
@@ -467,6 +497,11 @@ __global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, 
   for (int i = threadIdx.x; i < bins; i += NT) row[i] = hist[i];
 }
 
+// Software-pipelined over tiles: the loads and the ranking atomics of tile t+1 are issued in the same
+// barrier-free block as the write-out of tile t (LDS -> LDS -> STG chains), so one resident CTA per SM
+// still has independent global loads, shared atomics and global stores in flight together.  The first
+// version ran the phases back to back and stalled on long_scoreboard / lg_throttle / barrier in turn
+// (profiles/r01_ncu_v10_summary.txt: 25% issue utilisation).
 template <typename ElemIn, typename ElemOut, int NT, int MODE, bool FILTER>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const ElemIn* __restrict__ src, LevelPlan lp, DigitFn<MODE> dg,
                                                      const uint32_t* __restrict__ chunkpref,
@@ -480,89 +515,64 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
   chunk_tiles(lp, blockIdx.x, s, t0, t1);
   const uint64_t seg_lo = lp.seg_start[s], seg_hi = lp.seg_start[s + 1];
   chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, bstart64 ? 0ull : seg_lo, bins, Gabs, cnt2);
-  __syncthreads();
   constexpr int ITEMS = TileItems<ElemIn>::N;  // lp.tile_elems == NT * ITEMS
   constexpr uint32_t ES = (uint32_t)sizeof(ElemIn);
-  const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G);
-  for (uint32_t t = t0; t < t1; t++) {
-    uint32_t* cnt = cnt2 + ((t - t0) & 1u) * bins;
-    uint32_t* cnt_next = cnt2 + (((t - t0) & 1u) ^ 1u) * bins;
-    const uint32_t cnt_a = smem_u32(cnt);
-    const uint64_t e0 = seg_lo + (uint64_t)(t - lp.seg_tile0[s]) * lp.tile_elems;
-    const uint64_t e1 = e0 + lp.tile_elems < seg_hi ? e0 + lp.tile_elems : seg_hi;
-    ElemIn r[ITEMS];
-    uint32_t rk[(ITEMS + 1) / 2];
+  const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G), cnt2_a = smem_u32(cnt2);
+  const uint64_t chunk_e0 = seg_lo + (uint64_t)(t0 - lp.seg_tile0[s]) * lp.tile_elems;
+  ElemIn r[ITEMS];
+  uint32_t rk[(ITEMS + 1) / 2];
+  uint32_t live = 0;  // bit u: item u of the tile in r[] exists and belongs to this round
+  // tile t's keys -> r[], live
+  auto load_tile = [&](uint32_t t) {
+    const uint64_t e0 = chunk_e0 + (uint64_t)(t - t0) * lp.tile_elems;
+    live = 0;
+#pragma unroll
+    for (int u = 0; u < ITEMS; u++) {
+      const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
+      if (i < seg_hi) { r[u] = src[i]; live |= 1u << u; }
+      else r[u] = ElemIn{};
+    }
+  };
+  // each live key of r[] takes its rank inside (tile, bin) from one shared atomic
+  auto rank_tile = [&](uint32_t cnt_a) {
 #pragma unroll
     for (int u = 0; u < (ITEMS + 1) / 2; u++) rk[u] = 0;
-    const bool full = (e1 - e0) == (uint64_t)lp.tile_elems;  // uniform; the common case needs no bounds checks
-    if (t + 1 < t1) {  // next tile's keys toward L2 while this tile is ranked, placed and written
-      constexpr int PER_LINE = 128 / (int)sizeof(ElemIn) > 0 ? 128 / (int)sizeof(ElemIn) : 1;
-      if ((threadIdx.x % PER_LINE) == 0) {
 #pragma unroll
-        for (int u = 0; u < ITEMS; u++) {
-          const uint64_t i = e1 + (uint64_t)u * NT + threadIdx.x;
-          if (i < seg_hi) prefetch_l2(src + i);
-        }
-      }
+    for (int u = 0; u < ITEMS; u++) {
+      const uint32_t d = dg(r[u]);
+      if (FILTER) live &= ~((uint32_t)((d - dg.flo) >= dg.fwidth) << u);
+      const uint32_t rr = atoms_add_if(cnt_a + 4 * d, 1u, live & (1u << u));
+      rk[u >> 1] |= rr << ((u & 1) * 16);
     }
-    if (full && !FILTER) {
-      const ElemIn* __restrict__ p = src + e0 + threadIdx.x;
+  };
+  __syncthreads();  // chunk_begin
+  load_tile(t0);
+  rank_tile(cnt2_a);
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t cur = (t - t0) & 1u;
+    uint32_t* cnt = cnt2 + cur * bins;
+    uint32_t* cnt_next = cnt2 + (cur ^ 1u) * bins;
+    const uint32_t cnt_a = cnt2_a + cur * 4u * (uint32_t)bins, cnt_next_a = cnt2_a + (cur ^ 1u) * 4u * (uint32_t)bins;
+    __syncthreads();  // ranks of tile t complete; write-out of tile t-1 done with stage and G
+    const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
+    // ---- place the keys in bin order in the stage
 #pragma unroll
-      for (int u = 0; u < ITEMS; u++) r[u] = p[u * NT];
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        const uint32_t rr = atoms_add(cnt_a + 4 * dg(r[u]), 1u);
-        rk[u >> 1] |= rr << ((u & 1) * 16);
-      }
-      __syncthreads();
-      tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        const uint32_t slot = lds_u32(cnt_a + 4 * dg(r[u])) + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu);
-        SmemElem<ElemIn>::st(stage_a + slot * ES, r[u]);
-      }
-      __syncthreads();
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        const uint32_t i = u * NT + threadIdx.x;
-        const ElemIn e = SmemElem<ElemIn>::ld(stage_a + i * ES);
-        out[lds_u64(G_a + 8 * dg(e)) + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
-      }
-    } else {
-      uint32_t live = 0;  // bit u: item u exists and belongs to this round
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-        if (i < e1) { r[u] = src[i]; live |= 1u << u; }
-      }
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        if ((live >> u) & 1u) {
-          const uint32_t d = dg(r[u]);
-          if (FILTER && (d - dg.flo) >= dg.fwidth) {
-            live &= ~(1u << u);
-          } else {
-            const uint32_t rr = atoms_add(cnt_a + 4 * d, 1u);
-            rk[u >> 1] |= rr << ((u & 1) * 16);
-          }
-        }
-      }
-      __syncthreads();
-      const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
-#pragma unroll
-      for (int u = 0; u < ITEMS; u++) {
-        if ((live >> u) & 1u) {
-          const uint32_t slot = lds_u32(cnt_a + 4 * dg(r[u])) + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu);
-          SmemElem<ElemIn>::st(stage_a + slot * ES, r[u]);
-        }
-      }
-      __syncthreads();
-      for (uint32_t i = threadIdx.x; i < tile_n; i += NT) {
-        const ElemIn e = SmemElem<ElemIn>::ld(stage_a + i * ES);
-        out[lds_u64(G_a + 8 * dg(e)) + i] = ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem);
-      }
+    for (int u = 0; u < ITEMS; u++) {
+      const uint32_t slot = lds_u32(cnt_a + 4 * dg(r[u])) + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu);
+      SmemElem<ElemIn>::st_if(stage_a + slot * ES, r[u], live & (1u << u));
     }
-    __syncthreads();  // stage and G are reused by the next tile
+    __syncthreads();
+    // ---- one block: loads of tile t+1 | coalesced runs of tile t out | ranks of tile t+1
+    const bool more = t + 1 < t1;
+    if (more) load_tile(t + 1);
+    // slots past tile_n hold stale keys: reading them and their (in-range) bins is harmless
+#pragma unroll
+    for (int u = 0; u < ITEMS; u++) {
+      const uint32_t i = u * NT + threadIdx.x;
+      const ElemIn e = SmemElem<ElemIn>::ld(stage_a + i * ES);
+      stg_if(out + lds_u64(G_a + 8 * dg(e)) + i, ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem), (uint32_t)(i < tile_n));
+    }
+    if (more) rank_tile(cnt_next_a);
   }
 }
 
