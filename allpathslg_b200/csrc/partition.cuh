@@ -92,12 +92,57 @@ __device__ __forceinline__ void stg_u64_if(void* ptr, uint64_t v, uint32_t pred)
 __device__ __forceinline__ void stg_u32_if(void* ptr, uint32_t v, uint32_t pred) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"(pred) : "memory");
 }
-template <int W>
-__device__ __forceinline__ void stg_if(Key<W>* ptr, const Key<W>& k, uint32_t pred) {
-#pragma unroll
-  for (int i = 0; i < W; i++) stg_u64_if(&ptr->w[i], k.w[i], pred);
+// L2 eviction policies for the partition passes: the key stream is read once (evict_first), the
+// partially written sectors at the ends of each bin's run should stay until the next tile completes them.
+#ifndef APGK_LD_HINT
+#define APGK_LD_HINT 1  // measured: level-1 scatter 24.6 -> 18.7 ms; store hints made no difference
+#endif
+#ifndef APGK_SK_EARLY
+#define APGK_SK_EARLY 1
+#endif
+#ifndef APGK_ST_HINT
+#define APGK_ST_HINT 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
-__device__ __forceinline__ void stg_if(uint32_t* ptr, const uint32_t& k, uint32_t pred) { stg_u32_if(ptr, k, pred); }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t ldg_u64_pol(const void* ptr, uint64_t pol) {
+  uint64_t r;
+  asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(ptr), "l"(pol) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_u64_if_pol(void* ptr, uint64_t v, uint32_t pred, uint64_t pol) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.L2::cache_hint.u64 [%0], %1, %3;\n\t}" ::"l"(ptr), "l"(v), "r"(pred), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_u32_if_pol(void* ptr, uint32_t v, uint32_t pred, uint64_t pol) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.L2::cache_hint.u32 [%0], %1, %3;\n\t}" ::"l"(ptr), "r"(v), "r"(pred), "l"(pol) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void stg_if(Key<W>* ptr, const Key<W>& k, uint32_t pred, uint64_t pol) {
+#pragma unroll
+  for (int i = 0; i < W; i++) {
+    if (APGK_ST_HINT) stg_u64_if_pol(&ptr->w[i], k.w[i], pred, pol);
+    else stg_u64_if(&ptr->w[i], k.w[i], pred);
+  }
+}
+__device__ __forceinline__ void stg_if(uint32_t* ptr, const uint32_t& k, uint32_t pred, uint64_t pol) {
+  if (APGK_ST_HINT) stg_u32_if_pol(ptr, k, pred, pol);
+  else stg_u32_if(ptr, k, pred);
+}
+__device__ __forceinline__ uint32_t ldg_stream(const uint32_t* ptr, uint64_t) { return *ptr; }
+template <int W>
+__device__ __forceinline__ Key<W> ldg_stream(const Key<W>* ptr, uint64_t pol) {
+  if constexpr (APGK_LD_HINT == 0) return *ptr;
+  else {
+    Key<W> k;
+#pragma unroll
+    for (int i = 0; i < W; i++) k.w[i] = ldg_u64_pol(&ptr->w[i], pol);
+    return k;
+  }
+}
 
 template <typename T> struct SmemElem;
 template <int W> struct SmemElem<Key<W>> {
@@ -384,6 +429,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
   chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, 0ull, bins, Gabs, cnt2);
   constexpr uint32_t ES = (uint32_t)sizeof(Key<W>);
   const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G), cnt2_a = smem_u32(cnt2);
+  const uint64_t pol_st = APGK_ST_HINT == 1 ? l2_policy_evict_last() : (APGK_ST_HINT == 2 ? l2_policy_evict_first() : 0ull);
   Key<W> key[POS_PER_THREAD];
   uint32_t rk[POS_PER_THREAD / 2];  // two 16-bit ranks per register
   uint32_t valid = 0;               // bit j: window j of the tile in key[] is a k-mer of this round
@@ -427,7 +473,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
     auto write_out = [&](int j) {
       const uint32_t i = (uint32_t)j * NT + threadIdx.x;
       const Key<W> kq = lds_key<W>(stage_a + i * ES);
-      stg_if(out + lds_u64(G_a + 8 * dg(kq)) + i, kq, (uint32_t)(i < tile_n));
+      stg_if(out + lds_u64(G_a + 8 * dg(kq)) + i, kq, (uint32_t)(i < tile_n), pol_st);
     };
     if (t + 1 < t1) {
       if (t + 2 < t1) {  // the bases / start bits of tile t+2 toward L1
@@ -519,6 +565,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
   constexpr uint32_t ES = (uint32_t)sizeof(ElemIn);
   const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G), cnt2_a = smem_u32(cnt2);
   const uint64_t chunk_e0 = seg_lo + (uint64_t)(t0 - lp.seg_tile0[s]) * lp.tile_elems;
+  const uint64_t pol_ld = APGK_LD_HINT ? l2_policy_evict_first() : 0ull;
+  const uint64_t pol_st = APGK_ST_HINT == 1 ? l2_policy_evict_last() : (APGK_ST_HINT == 2 ? l2_policy_evict_first() : 0ull);
   ElemIn r[ITEMS];
   uint32_t rk[(ITEMS + 1) / 2];
   uint32_t live = 0;  // bit u: item u of the tile in r[] exists and belongs to this round
@@ -529,7 +577,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
 #pragma unroll
     for (int u = 0; u < ITEMS; u++) {
       const uint64_t i = e0 + (uint64_t)u * NT + threadIdx.x;
-      if (i < seg_hi) { r[u] = src[i]; live |= 1u << u; }
+      if (i < seg_hi) { r[u] = ldg_stream(src + i, pol_ld); live |= 1u << u; }
       else r[u] = ElemIn{};
     }
   };
@@ -564,14 +612,24 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
     __syncthreads();
     // ---- one block: loads of tile t+1 | coalesced runs of tile t out | ranks of tile t+1
     const bool more = t + 1 < t1;
+#if APGK_SK_EARLY
     if (more) load_tile(t + 1);
+#else
+    if (more) {  // one 128-byte line of tile t+1 per thread toward L2
+      const uint64_t i = chunk_e0 + (uint64_t)(t + 1 - t0) * lp.tile_elems + (uint64_t)threadIdx.x * (128 / ES);
+      if (i < seg_hi && threadIdx.x * (128 / ES) < lp.tile_elems) prefetch_l2(src + i);
+    }
+#endif
     // slots past tile_n hold stale keys: reading them and their (in-range) bins is harmless
 #pragma unroll
     for (int u = 0; u < ITEMS; u++) {
       const uint32_t i = u * NT + threadIdx.x;
       const ElemIn e = SmemElem<ElemIn>::ld(stage_a + i * ES);
-      stg_if(out + lds_u64(G_a + 8 * dg(e)) + i, ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem), (uint32_t)(i < tile_n));
+      stg_if(out + lds_u64(G_a + 8 * dg(e)) + i, ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem), (uint32_t)(i < tile_n), pol_st);
     }
+#if !APGK_SK_EARLY
+    if (more) load_tile(t + 1);
+#endif
     if (more) rank_tile(cnt_next_a);
   }
 }
