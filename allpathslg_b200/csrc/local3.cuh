@@ -7,6 +7,11 @@
 // inside the row.  One CAS + one ADD per key instance groups identical keys.  Rows
 // are in ascending key order by construction, so only the <= 16 entries of a row have
 // to be ranked against each other: there is no separate sort.
+// (Tried and measured no faster, profiles/r01_sweeps.txt "local3 variants": four straight-line first
+// probes per thread with the occupancy bitmap rebuilt by one thread per row instead of an atomicOr per
+// fresh slot; a two-choice start slot that keeps most warps out of the probing loop; an L2 prefetch of
+// the next bucket.  Issue slots and the L1 data pipe both sit at ~60%: the kernel is bound by the
+// barrier-separated phases of small buckets, not by instruction count.)
 // (A fully monotone slot hash was tried first: sequencing-error variants of a genomic
 // k-mer differ in their low bits, land on the same home slot and build clusters right
 // where the 45x-covered k-mer lives -- ncu showed 6.5 warp instructions per key in
@@ -34,6 +39,9 @@
 #pragma once
 #include "local2.cuh"
 
+#ifndef L3_PREFETCH
+#define L3_PREFETCH 1
+#endif
 namespace apgk {
 
 constexpr int L3_ROW = 16;      // slots per row (a row is half a bitmap word)
@@ -63,7 +71,7 @@ struct Local3Smem {
 };
 
 template <int NT, int W>
-__global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src, BucketTable bt, int rem_bits, EmitCtx<W> ec,
+__global__ void __launch_bounds__(NT, 1536 / NT) k_local3(const uint32_t* __restrict__ src, BucketTable bt, int rem_bits, EmitCtx<W> ec,
                                                uint32_t* __restrict__ nd_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Local3Smem sm;
@@ -74,13 +82,22 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src,
   for (int i = tid; i < SPEC_SMEM; i += NT) sm.spec[i] = 0;
   const int up = 32 - rem_bits;                       // remainder left-aligned in 32 bits
   const uint32_t m_cap = (uint32_t)LM + (uint32_t)LM / 4 + 1;  // homes of a full-size pass
+  // The next bucket's size / offset are loaded one bucket ahead and its keys are pulled toward L2 while
+  // the current bucket is processed: a CTA otherwise sits through two dependent DRAM latencies per
+  // bucket (bsize/bofs, then the keys) and three CTAs per SM do not cover them.
+  unsigned long long n_nx = 0, o_nx = 0;
+  if (blockIdx.x < bt.nb) { n_nx = bt.bsize[blockIdx.x]; o_nx = bt.bofs[blockIdx.x]; }
   for (uint32_t b = blockIdx.x; b < bt.nb; b += gridDim.x) {
-    const unsigned long long n64 = bt.bsize[b];
+    const unsigned long long n64 = n_nx;
+    const unsigned long long o = o_nx;
+    {
+      const uint32_t bn = b + gridDim.x;
+      if (bn < bt.nb) { n_nx = bt.bsize[bn]; o_nx = bt.bofs[bn]; }
+    }
     if (n64 == 0) {
       if (tid == 0) nd_out[b] = 0;
       continue;
     }
-    const unsigned long long o = bt.bofs[b];
     const uint32_t* s = src + o;
     // a pass over a small bucket only needs a small table
     const uint32_t m_want = n64 < (unsigned long long)LM ? (uint32_t)n64 + ((uint32_t)n64 >> 2) + 1 : m_cap;
@@ -152,6 +169,12 @@ __global__ void __launch_bounds__(NT) k_local3(const uint32_t* __restrict__ src,
         if (n64 > (unsigned long long)LM && __any_sync(0xffffffffu, vmisc[0] != 0)) break;  // failed pass of a big bucket
       }
       __syncthreads();
+#if L3_PREFETCH
+      if (L3_PREFETCH == 1 || run_nd == 0) {  // next bucket's keys toward L2 (32 keys per 128-byte line)
+        const unsigned long long i = (unsigned long long)tid * 32;
+        if (b + gridDim.x < bt.nb && i < n_nx && tid < 1024) prefetch_l2(src + o_nx + i);
+      }
+#endif
       // ---- 3. dense list of occupied slots, in slot order
       uint32_t nd_total;
       {

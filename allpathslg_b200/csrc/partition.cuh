@@ -144,6 +144,22 @@ __device__ __forceinline__ Key<W> ldg_stream(const Key<W>* ptr, uint64_t pol) {
   }
 }
 
+__device__ __forceinline__ void reds_add_if(uint32_t addr, uint32_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t r;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(r) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return r;
+}
+// returns `val` (as if the slot already held it) when pred == 0
+__device__ __forceinline__ uint32_t atoms_cas_if(uint32_t addr, uint32_t cmp, uint32_t val, uint32_t pred) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\tmov.u32 %0, %3;\n\t@p atom.shared.cas.b32 %0, [%1], %2, %3;\n\t}"
+               : "=r"(r) : "r"(addr), "r"(cmp), "r"(val), "r"(pred) : "memory");
+  return r;
+}
+
 template <typename T> struct SmemElem;
 template <int W> struct SmemElem<Key<W>> {
   __device__ __forceinline__ static void st(uint32_t a, const Key<W>& k) { sts_key<W>(a, k); }
