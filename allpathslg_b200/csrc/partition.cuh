@@ -478,18 +478,38 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
     __syncthreads();  // ranks of tile t complete; write-out of tile t-1 done with stage and G
     const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
     // ---- place the keys in bin order in the stage
+    // (the shared-memory asm statements keep their program order: batch the loads by hand so that
+    // eight LDS are in flight instead of one LDS -> STS chain at a time)
 #pragma unroll
-    for (int j = 0; j < POS_PER_THREAD; j++) {
-      const uint32_t slot = lds_u32(cnt_a + 4 * dg(key[j])) + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
-      SmemElem<Key<W>>::st_if(stage_a + slot * ES, key[j], valid & (1u << j));
+    for (int j0 = 0; j0 < POS_PER_THREAD; j0 += 8) {
+      uint32_t first[8];
+#pragma unroll
+      for (int j = j0; j < j0 + 8; j++) first[j - j0] = lds_u32(cnt_a + 4 * dg(key[j]));
+#pragma unroll
+      for (int j = j0; j < j0 + 8; j++) {
+        const uint32_t slot = first[j - j0] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+        SmemElem<Key<W>>::st_if(stage_a + slot * ES, key[j], valid & (1u << j));
+      }
     }
     __syncthreads();
     // ---- coalesced runs of tile t out, interleaved with the windows of tile t+1.
     // Slots past tile_n hold stale keys: reading them and their (in-range) bins is harmless.
-    auto write_out = [&](int j) {
-      const uint32_t i = (uint32_t)j * NT + threadIdx.x;
-      const Key<W> kq = lds_key<W>(stage_a + i * ES);
-      stg_if(out + lds_u64(G_a + 8 * dg(kq)) + i, kq, (uint32_t)(i < tile_n), pol_st);
+    Key<W> kq[4];
+    unsigned long long gq[4];
+    auto write_out = [&](int j) {  // items j-3 .. j every fourth call: 4 LDS, 4 LDS, 4 STG
+      if ((j & 3) == 1) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) kq[u] = lds_key<W>(stage_a + ((uint32_t)(j - 1 + u) * NT + threadIdx.x) * ES);
+      } else if ((j & 3) == 2) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) gq[u] = lds_u64(G_a + 8 * dg(kq[u]));
+      } else if ((j & 3) == 3) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t i = (uint32_t)(j - 3 + u) * NT + threadIdx.x;
+          stg_if(out + gq[u] + i, kq[u], (uint32_t)(i < tile_n), pol_st);
+        }
+      }
     };
     if (t + 1 < t1) {
       if (t + 2 < t1) {  // the bases / start bits of tile t+2 toward L1
@@ -620,10 +640,19 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
     __syncthreads();  // ranks of tile t complete; write-out of tile t-1 done with stage and G
     const uint32_t tile_n = tile_scan<NT>(bins, G, Gabs, cnt, cnt_next, scratch);
     // ---- place the keys in bin order in the stage
+    {
+      constexpr int PB = ITEMS >= 8 ? 8 : ITEMS;  // loads in flight per batch (asm statements keep program order)
 #pragma unroll
-    for (int u = 0; u < ITEMS; u++) {
-      const uint32_t slot = lds_u32(cnt_a + 4 * dg(r[u])) + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu);
-      SmemElem<ElemIn>::st_if(stage_a + slot * ES, r[u], live & (1u << u));
+      for (int u0 = 0; u0 < ITEMS; u0 += PB) {
+        uint32_t first[PB];
+#pragma unroll
+        for (int u = u0; u < u0 + PB && u < ITEMS; u++) first[u - u0] = lds_u32(cnt_a + 4 * dg(r[u]));
+#pragma unroll
+        for (int u = u0; u < u0 + PB && u < ITEMS; u++) {
+          const uint32_t slot = first[u - u0] + ((rk[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu);
+          SmemElem<ElemIn>::st_if(stage_a + slot * ES, r[u], live & (1u << u));
+        }
+      }
     }
     __syncthreads();
     // ---- one block: loads of tile t+1 | coalesced runs of tile t out | ranks of tile t+1
@@ -637,11 +666,22 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
     }
 #endif
     // slots past tile_n hold stale keys: reading them and their (in-range) bins is harmless
+    {
+      constexpr int WB = ITEMS >= 4 ? 4 : ITEMS;
 #pragma unroll
-    for (int u = 0; u < ITEMS; u++) {
-      const uint32_t i = u * NT + threadIdx.x;
-      const ElemIn e = SmemElem<ElemIn>::ld(stage_a + i * ES);
-      stg_if(out + lds_u64(G_a + 8 * dg(e)) + i, ElemCvt<ElemOut, ElemIn>::cvt(e, out_pad, out_rem), (uint32_t)(i < tile_n), pol_st);
+      for (int u0 = 0; u0 < ITEMS; u0 += WB) {
+        ElemIn e[WB];
+        unsigned long long g[WB];
+#pragma unroll
+        for (int u = u0; u < u0 + WB && u < ITEMS; u++) e[u - u0] = SmemElem<ElemIn>::ld(stage_a + ((uint32_t)u * NT + threadIdx.x) * ES);
+#pragma unroll
+        for (int u = u0; u < u0 + WB && u < ITEMS; u++) g[u - u0] = lds_u64(G_a + 8 * dg(e[u - u0]));
+#pragma unroll
+        for (int u = u0; u < u0 + WB && u < ITEMS; u++) {
+          const uint32_t i = (uint32_t)u * NT + threadIdx.x;
+          stg_if(out + g[u - u0] + i, ElemCvt<ElemOut, ElemIn>::cvt(e[u - u0], out_pad, out_rem), (uint32_t)(i < tile_n), pol_st);
+        }
+      }
     }
 #if !APGK_SK_EARLY
     if (more) load_tile(t + 1);
