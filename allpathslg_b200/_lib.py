@@ -54,6 +54,12 @@ SYMBOLS = {
     "apgk_key_buffer": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "apgk_owner_of": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, _vp]),
     "apgk_finish_keys_device": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "apgk_window_upper": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "apgk_choose_prefix_bits": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_int32)]),
+    "apgk_partition": (C.c_int, [_vp, C.c_int32]),
+    "apgk_partition_info": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint32),
+                                      C.POINTER(C.c_uint64)]),
+    "apgk_count_pieces": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_uint64, C.c_uint64]),
     "apgk_spectrum_device": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
     "apgk_spectrum_reload": (C.c_int, [_vp]),
     "apgk_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),

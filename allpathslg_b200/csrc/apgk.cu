@@ -83,6 +83,10 @@ struct apgk_ctx {
   uint32_t n_deferred = 0, local_max = 0, n_rounds = 0;
   std::vector<uint64_t> spec_host, sparse_f, sparse_n;
   bool spec_loaded = false;
+  // ---- partition-only state (sharded counting: apgk_partition -> exchange -> apgk_count_pieces)
+  bool part_ready = false;
+  uint64_t part_n = 0;       // elements in B, grouped by the nb1 buckets (sizes in segtot)
+  DevBuf piece_off, piece_tmp;
   // ---- owner partition state
   uint32_t owner_ranks = 0;
   uint32_t owner_tiles = 0;
@@ -300,24 +304,34 @@ void invalidate_results(apgk_ctx* c) {
   c->finished = false; c->have_table = false; c->spec_loaded = false;
   c->n_instances = c->n_distinct = 0;
   c->owner_ranks = 0;
+  c->part_ready = false; c->part_n = 0;
 }
 
 // ---------------------------------------------------------------- the pipeline
+enum RunMode { RUN_FULL = 0, RUN_PARTITION = 1 };
 template <int W, typename ElemB>
-int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys);
+int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode);
+template <int W, typename ElemB>
+int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N_all, uint64_t& n_prev);
 
+// upper bound of the k-mer instances a run over the read store will see
+uint64_t window_upper(const apgk_ctx* c) {
+  // reads shorter than K aside, a read of L bases yields L-K+1 windows
+  const uint64_t lost = c->n_reads * (uint64_t)(c->cfg.K - 1);
+  return c->total_bases > lost ? c->total_bases - lost : 1;
+}
+
+// Geometry of a run over `upper` instances (forced_P > 0 overrides the choice: ranks of a sharded run
+// must agree on it).  Returns true when level 1 stores 32-bit remainders.
 template <int W>
-int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
-  invalidate_results(c);
-  for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
-  uint64_t upper = dev_keys ? n_keys : c->total_bases;
-  if (!dev_keys) {  // reads shorter than K aside, a read of L bases yields L-K+1 windows
-    const uint64_t lost = c->n_reads * (uint64_t)(c->cfg.K - 1);
-    upper = upper > lost ? upper - lost : 1;
-  }
+bool select_geometry(apgk_ctx* c, uint64_t upper, int forced_P) {
   // decide element type of the level-1 buffer first (it fixes LOCAL_MAX, which fixes P)
   int lm_u32 = LM_U32;
   if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) lm_u32 = atoi(e); }
+  if (forced_P > 0) {
+    make_geom(c, std::max(2, std::min(24, forced_P)));
+    return W == 1 && c->geom.REM <= 32;
+  }
   // try the 32-bit-remainder geometry first: one-word keys whose remainder below the prefix fits 31 bits
   int P = choose_prefix_bits(c, upper, lm_u32, true);
   make_geom(c, P);
@@ -329,22 +343,31 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     P = choose_prefix_bits(c, upper, Geo<W>::LM_KEY, false);
     make_geom(c, P);
   }
+  return u32;
+}
+
+template <int W>
+int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode = RUN_FULL, int forced_P = 0) {
+  invalidate_results(c);
+  for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
+  select_geometry<W>(c, dev_keys ? n_keys : window_upper(c), forced_P);
   stage_begin(c, ST_TOTAL);
   int rc;
   if constexpr (W == 1) {
-    if (c->geom.REM <= 32) rc = run_levels<W, uint32_t>(c, dev_keys, n_keys);
-    else rc = run_levels<W, Key<W>>(c, dev_keys, n_keys);
+    if (c->geom.REM <= 32) rc = run_levels<W, uint32_t>(c, dev_keys, n_keys, mode);
+    else rc = run_levels<W, Key<W>>(c, dev_keys, n_keys, mode);
   } else {
-    rc = run_levels<W, Key<W>>(c, dev_keys, n_keys);
+    rc = run_levels<W, Key<W>>(c, dev_keys, n_keys, mode);
   }
   if (rc) return rc;
   stage_end(c, ST_TOTAL);
   c->n_deferred = 0;
-  if (c->deferred.p && c->n_instances)
+  if (mode == RUN_FULL && c->deferred.p && c->n_instances)
     CU(cudaMemcpyAsync(&c->n_deferred, c->deferred.p, 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   for (int s = 0; s < APGK_N_STAGES; s++) stage_flush(c, s);
-  c->finished = true;
+  if (mode == RUN_FULL) c->finished = true;
+  else c->part_ready = true;
   return APGK_OK;
 }
 
@@ -373,7 +396,7 @@ int ensure_preserve(apgk_ctx* c, DevBuf& b, size_t bytes, size_t keep_bytes) {
 }
 
 template <int W, typename ElemB>
-int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
+int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode) {
   const KeyGeom g = c->geom;
   const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
   int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : Geo<W>::LM_KEY;
@@ -405,6 +428,10 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   if (hp0.lp.n_tiles == 0) {  // nothing to count
     c->n_instances = 0;
     c->have_table = want_table != 0;
+    if (mode == RUN_PARTITION) {
+      CU(c->segtot.ensure((size_t)c->nb1 * 8));
+      CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
+    }
     return APGK_OK;
   }
   {  // the level-0 plan must outlive the level-1 uploads of every round: it gets its own device copy
@@ -450,6 +477,10 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
   c->n_instances = N;
   if (N == 0) {
     c->have_table = want_table != 0;
+    if (mode == RUN_PARTITION) {
+      CU(c->segtot.ensure((size_t)c->nb1 * 8));
+      CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
+    }
     return APGK_OK;
   }
 
@@ -475,6 +506,8 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     rounds.push_back({lo, bins0});
   }
   c->n_rounds = (uint32_t)rounds.size();
+  if (mode == RUN_PARTITION && rounds.size() > 1)
+    FAIL(APGK_E_RANGE, "apgk_partition: %zu k-mer-space rounds would be needed; the sharded exchange takes one", rounds.size());
 
   CU(c->spec_ovf.ensure(((size_t)N / SPEC_DENSE + 16) * 8));
   CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
@@ -545,20 +578,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     stage_end(c, ST_HIST1);
     stage_begin(c, ST_SCAN1);
     { int rc = column_scan(c, hp1, 1, c->bofs.as<unsigned long long>()); if (rc) return rc; }
-    // bucket classification (oversize list)
-    const uint32_t big_cap = (uint32_t)(Nr / local_max + 16);
-    CU(c->big_list.ensure((size_t)big_cap * 4));
-    k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
-                                                           use_l3 ? 0xFFFFFFFFu : (uint32_t)local_max,
-                                                           c->big_list.as<uint32_t>(), big_cap,
-                                                           c->stats.as<unsigned long long>());
-    LAUNCHED();
     stage_end(c, ST_SCAN1);
-    unsigned long long stats[2] = {0, 0};
-    CU(cudaMemcpyAsync(stats, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    const uint64_t n_big = stats[0];
-    c->n_big += n_big;
     CU(c->B.ensure(std::max<size_t>(Nr, 1) * sizeof(ElemB) + 16));
     stage_begin(c, ST_SCATTER1);
     {
@@ -571,7 +591,42 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
     }
     stage_end(c, ST_SCATTER1);
 
-    // ---- per-bucket sort + count
+    if (mode == RUN_PARTITION) { c->part_n = Nr; return APGK_OK; }
+    { int rc = count_buckets<W, ElemB>(c, Nr, N, n_prev); if (rc) return rc; }
+  }
+  c->n_distinct = n_prev;
+  c->have_table = want_table != 0;
+  return APGK_OK;
+}
+
+// ---------------------------------------------------------------- per-bucket sort + count, table append
+// Input: c->B holds Nr elements grouped by the nb1 buckets (offsets c->bofs, sizes c->segtot).  Appends the
+// distinct k-mers of these buckets to the result table at n_prev (buckets ascend in k-mer order).
+template <int W, typename ElemB>
+int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
+  const KeyGeom g = c->geom;
+  const int local_max = (int)c->local_max;
+  int l3_nt = L3_NT;
+  if (std::is_same<ElemB, uint32_t>::value) {
+    if (const char* e = getenv("APGK_L3_NT")) { if (atoi(e) == 256 || atoi(e) == 512) l3_nt = atoi(e); }
+  }
+  const bool use_l3 = std::is_same<ElemB, uint32_t>::value && g.REM >= 1 && g.REM <= 31;
+  const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
+  // bucket classification (oversize list)
+  const uint32_t big_cap = (uint32_t)(Nr / local_max + 16);
+  CU(c->big_list.ensure((size_t)big_cap * 4));
+  CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
+  k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
+                                                         use_l3 ? 0xFFFFFFFFu : (uint32_t)local_max,
+                                                         c->big_list.as<uint32_t>(), big_cap,
+                                                         c->stats.as<unsigned long long>());
+  LAUNCHED();
+  unsigned long long stats[2] = {0, 0};
+  CU(cudaMemcpyAsync(stats, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const uint64_t n_big = stats[0];
+  c->n_big += n_big;
+  {
     EmitCtx<W> ec;
     ec.want_table = want_table; ec.rem_bits = g.REM; ec.pad = g.pad;
     ec.tmp_keys = c->A.as<Key<W>>();
@@ -683,9 +738,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys) {
       n_prev += total;
     }
     stage_end(c, ST_TABLE);
-  }
-  c->n_distinct = n_prev;
-  c->have_table = want_table != 0;
+    }
   return APGK_OK;
 }
 
@@ -768,6 +821,102 @@ int read_freqs_impl(apgk_ctx* c, uint64_t first, uint64_t n, uint32_t* out) {
   r.release();
   CU(e);
   return APGK_OK;
+}
+
+// ---------------------------------------------------------------- sharded counting, receiver side
+// exclusive scan of a u32 array into u64[n+1] (total -> *total_out if not null)
+int scan_u32(apgk_ctx* c, const uint32_t* in, uint64_t n, unsigned long long* out, unsigned long long* total_out) {
+  const uint32_t nblocks = (uint32_t)((n + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
+  CU(c->blocksum.ensure(((size_t)nblocks + 1) * 8));
+  k_scan_blocksum<<<nblocks, SCAN_NT, 0, c->stream>>>(in, n, c->blocksum.as<unsigned long long>());
+  LAUNCHED();
+  k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks);
+  LAUNCHED();
+  k_scan_apply<<<nblocks, SCAN_NT, 0, c->stream>>>(in, n, c->blocksum.as<unsigned long long>(), out);
+  LAUNCHED();
+  if (total_out) {
+    CU(cudaMemcpyAsync(total_out, c->blocksum.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return APGK_OK;
+}
+
+template <int W, typename ElemB>
+int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
+                       const uint64_t* seg_off_host, uint32_t lo, uint32_t hi) {
+  const uint32_t nb = c->nb1;
+  for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
+  stage_begin(c, ST_TOTAL);
+  stage_begin(c, ST_OWNER);
+  CU(c->segtot.ensure((size_t)nb * 8));
+  CU(c->nd.ensure(((size_t)nb + 1) * 4));
+  CU(c->bofs.ensure(((size_t)nb + 1) * 8));
+  CU(c->out_off_local.ensure(((size_t)nb + 1) * 8));
+  CU(c->stats.ensure(64));
+  CU(c->misc.ensure(64));
+  CU(c->bstart64.ensure(std::max<size_t>(((size_t)(1u << c->geom.D0) + 1) * 8, (size_t)n_src * 8)));
+  CU(cudaMemsetAsync(c->misc.p, 0, 64, c->stream));
+  // merged bucket sizes and offsets
+  k_merge_sizes<<<(nb + 255) / 256, 256, 0, c->stream>>>(d_sizes_all, n_src, nb, lo, hi, c->segtot.as<unsigned long long>(),
+                                                       c->nd.as<uint32_t>(), c->misc.as<unsigned int>());
+  LAUNCHED();
+  unsigned long long Nr = 0;
+  { int rc = scan_u32(c, c->nd.as<uint32_t>(), nb, c->bofs.as<unsigned long long>(), &Nr); if (rc) return rc; }
+  unsigned int ovf = 0;
+  CU(cudaMemcpyAsync(&ovf, c->misc.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (ovf) FAIL(APGK_E_RANGE, "a merged bucket holds 2^32 or more k-mers");
+  // offset of every piece inside its source's segment
+  CU(c->piece_off.ensure((size_t)n_src * ((size_t)nb + 1) * 8));
+  CU(c->piece_tmp.ensure((size_t)nb * 4));
+  for (uint32_t s = 0; s < n_src; s++) {
+    k_mask_sizes<<<(nb + 255) / 256, 256, 0, c->stream>>>(d_sizes_all + (size_t)s * nb, nb, lo, hi, c->piece_tmp.as<uint32_t>());
+    LAUNCHED();
+    int rc = scan_u32(c, c->piece_tmp.as<uint32_t>(), nb, c->piece_off.as<unsigned long long>() + (size_t)s * (nb + 1), nullptr);
+    if (rc) return rc;
+  }
+  CU(cudaMemcpyAsync(c->bstart64.p, seg_off_host, (size_t)n_src * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // seg_off_host may die; also orders the copies before the gather
+  CU(c->B.ensure(std::max<size_t>(Nr, 1) * sizeof(ElemB) + 16));
+  CU(c->A.ensure(std::max<size_t>(Nr, 1) * sizeof(Key<W>)));
+  if (Nr && hi > lo) {
+    const uint32_t grid = std::min<uint32_t>(hi - lo, (uint32_t)c->n_sm * 16);
+    k_gather_pieces<ElemB><<<grid, 128, 0, c->stream>>>((const ElemB*)d_recv, c->bstart64.as<unsigned long long>(),
+                                                        c->piece_off.as<unsigned long long>(), d_sizes_all,
+                                                        c->bofs.as<unsigned long long>(), n_src, nb, lo, hi, c->B.as<ElemB>());
+    LAUNCHED();
+  }
+  stage_end(c, ST_OWNER);
+  c->n_instances = Nr;
+  c->n_big = 0;
+  uint64_t n_prev = 0;
+  CU(c->spec_ovf.ensure(((size_t)Nr / SPEC_DENSE + 16) * 8));
+  CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
+  CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
+  CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)nb + 1) * 8, c->stream));
+  if (Nr) { int rc = count_buckets<W, ElemB>(c, Nr, Nr, n_prev); if (rc) return rc; }
+  c->n_distinct = n_prev;
+  c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
+  stage_end(c, ST_TOTAL);
+  c->n_deferred = 0;
+  if (c->deferred.p && Nr) CU(cudaMemcpyAsync(&c->n_deferred, c->deferred.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < APGK_N_STAGES; s++) stage_flush(c, s);
+  c->part_ready = false;
+  c->spec_loaded = false;
+  c->finished = true;
+  return APGK_OK;
+}
+
+template <int W>
+int count_pieces_impl(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
+                      const uint64_t* seg_off_host, uint64_t lo, uint64_t hi) {
+  if (!c->part_ready) FAIL(APGK_E_STATE, "apgk_count_pieces needs a preceding apgk_partition on this context");
+  if (n_src == 0 || n_src > 1024 || lo > hi || hi > c->nb1) FAIL(APGK_E_ARG, "apgk_count_pieces: bad source count or bucket range");
+  if constexpr (W == 1) {
+    if (c->elem_bytes == 4) return count_pieces_typed<W, uint32_t>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi);
+  }
+  return count_pieces_typed<W, Key<W>>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi);
 }
 
 // ---------------------------------------------------------------- owner partition (multi-GPU shuffle, sender side)
@@ -1016,6 +1165,59 @@ int apgk_finish_keys_device(apgk_ctx* c, const uint64_t* d_keys, uint64_t n) {
     case 1: return finish_impl<1>(c, (const Key<1>*)d_keys, n);
     case 2: return finish_impl<2>(c, (const Key<2>*)d_keys, n);
     case 3: return finish_impl<3>(c, (const Key<3>*)d_keys, n);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_window_upper(const apgk_ctx* c, uint64_t* upper) {
+  if (!c || !upper) return APGK_E_ARG;
+  *upper = window_upper(c);
+  return APGK_OK;
+}
+
+int apgk_choose_prefix_bits(apgk_ctx* c, uint64_t upper, int32_t* prefix_bits) {
+  if (!c || !prefix_bits) return APGK_E_ARG;
+  switch (c->W) {
+    case 1: select_geometry<1>(c, upper, 0); break;
+    case 2: select_geometry<2>(c, upper, 0); break;
+    case 3: select_geometry<3>(c, upper, 0); break;
+    default: return APGK_E_ARG;
+  }
+  *prefix_bits = c->geom.D0 + c->geom.D1;
+  return APGK_OK;
+}
+
+int apgk_partition(apgk_ctx* c, int32_t prefix_bits) {
+  if (!c || prefix_bits < 0 || prefix_bits > 24) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return finish_impl<1>(c, nullptr, 0, RUN_PARTITION, prefix_bits);
+    case 2: return finish_impl<2>(c, nullptr, 0, RUN_PARTITION, prefix_bits);
+    case 3: return finish_impl<3>(c, nullptr, 0, RUN_PARTITION, prefix_bits);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_partition_info(apgk_ctx* c, const uint64_t** d_bucket_sizes, uint64_t* n_buckets, void** d_elems,
+                        uint32_t* elem_bytes, uint64_t* n_elems) {
+  if (!c) return APGK_E_ARG;
+  if (!c->part_ready) FAIL(APGK_E_STATE, "apgk_partition has not run");
+  if (d_bucket_sizes) *d_bucket_sizes = c->segtot.as<uint64_t>();
+  if (n_buckets) *n_buckets = c->nb1;
+  if (d_elems) *d_elems = c->part_n ? c->B.p : nullptr;
+  if (elem_bytes) *elem_bytes = c->elem_bytes;
+  if (n_elems) *n_elems = c->part_n;
+  return APGK_OK;
+}
+
+int apgk_count_pieces(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
+                      const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi) {
+  if (!c || !d_sizes_all || !seg_off) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return count_pieces_impl<1>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi);
+    case 2: return count_pieces_impl<2>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi);
+    case 3: return count_pieces_impl<3>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi);
   }
   return APGK_E_ARG;
 }

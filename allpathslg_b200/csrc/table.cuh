@@ -73,6 +73,43 @@ __global__ void k_classify(const unsigned long long* __restrict__ bsize, uint32_
   }
 }
 
+// ---------------------------------------------------------------- sharded counting: pieces -> buckets
+// After the exchange a rank holds, for every bucket b it owns (lo <= b < hi), one piece from each source
+// rank s (sizes_all[s][b] elements), laid out source-major.  These kernels merge the sizes and gather the
+// pieces into one bucket-major array, so the per-bucket kernels run unchanged on the shard.
+__global__ void k_merge_sizes(const uint32_t* __restrict__ sizes_all, uint32_t n_src, uint32_t nb, uint32_t lo, uint32_t hi,
+                              unsigned long long* __restrict__ bsize, uint32_t* __restrict__ bsize32,
+                              unsigned int* __restrict__ overflow) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  unsigned long long t = 0;
+  if (b >= lo && b < hi)
+    for (uint32_t s = 0; s < n_src; s++) t += sizes_all[(size_t)s * nb + b];
+  if (t >= (1ull << 32)) { atomicExch(overflow, 1u); t = 0; }
+  bsize[b] = t;
+  bsize32[b] = (uint32_t)t;
+}
+__global__ void k_mask_sizes(const uint32_t* __restrict__ sizes, uint32_t nb, uint32_t lo, uint32_t hi, uint32_t* __restrict__ out) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb) out[b] = (b >= lo && b < hi) ? sizes[b] : 0u;
+}
+// one CTA per owned bucket (grid-stride): copy its n_src pieces back to back to bofs[b]
+template <typename Elem>
+__global__ void k_gather_pieces(const Elem* __restrict__ recv, const unsigned long long* __restrict__ seg_off,
+                                const unsigned long long* __restrict__ piece_off /* [n_src][nb+1] */,
+                                const uint32_t* __restrict__ sizes_all, const unsigned long long* __restrict__ bofs,
+                                uint32_t n_src, uint32_t nb, uint32_t lo, uint32_t hi, Elem* __restrict__ out) {
+  for (uint32_t b = lo + blockIdx.x; b < hi; b += gridDim.x) {
+    unsigned long long dst = bofs[b];
+    for (uint32_t s = 0; s < n_src; s++) {
+      const uint32_t n = sizes_all[(size_t)s * nb + b];
+      const Elem* src = recv + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[dst + i] = src[i];
+      dst += n;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- compaction: temp records -> final table
 // One warp per bucket.  Temp keys / counts live at element offset bofs[b] of the temp buffers.
 template <int W>

@@ -1,18 +1,140 @@
-"""Multi-GPU k-mer spectrum: one process per GPU, hash-sharded by canonical k-mer.
+"""Multi-GPU k-mer spectrum: one process per GPU, sharded by canonical k-mer.
 
-Each rank extracts the canonical k-mers of ITS reads and groups them by owner
-rank (owner = hash(k-mer) % world, `apgk_owner_plan` / `apgk_owner_scatter`),
-the groups are exchanged with one NCCL all-to-all over NVLink
-(`torch.distributed.all_to_all_single`), each rank sorts and counts the shard it
-owns (`apgk_finish_keys_device`), and the per-rank spectra -- disjoint sets of
-k-mers, so plain integer sums -- are all-reduced.  Identical k-mers always land
-on the same rank, so counts are final without a merge.
+Partition-first form (`sharded_count`, the default).  Every rank runs levels 0 and 1 of the
+single-GPU pipeline on ITS reads (`apgk_partition`): the canonical k-mers end up grouped by their
+leading P bits, as 32-bit remainders when they fit.  The ranks all-gather the bucket histogram,
+cut the bucket space into `world` contiguous ranges of (nearly) equal instance counts
+(`balanced_splitters`), exchange whole ranges with one NCCL all-to-all over NVLink
+(`torch.distributed.all_to_all_single`), and each rank sorts + counts the ranges it owns
+(`apgk_count_pieces`).  The per-rank spectra -- disjoint sets of k-mers, so plain integer sums --
+are all-reduced.  A k-mer's owner depends on the canonical k-mer alone, so counts are final
+without a merge.
 
-torch is used for device buffers, streams and the collective only.
+Hash form (`sharded_count_hash`, the first implementation, kept as the fallback when a rank's
+k-mers need more than one k-mer-space round): owner = hash(k-mer) % world
+(`apgk_owner_plan` / `apgk_owner_scatter`), exchange of full k-mers, then the whole pipeline again
+on the received keys (`apgk_finish_keys_device`).  It extracts and partitions every k-mer twice
+and sends 8 bytes per instance where the partition-first form sends 4.
+
+torch is used for device buffers, streams and the collectives only.
 """
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+def balanced_splitters(bucket_totals, world):
+    """Cut buckets [0, nb) into `world` contiguous ranges with (nearly) equal instance counts.
+    bucket_totals: 1-D integer torch tensor or numpy array (instances per bucket, summed over ranks).
+    -> list of world+1 bucket indices, bounds[0] = 0, bounds[world] = nb, non-decreasing.
+    Deterministic in its input, so every rank derives the same ownership."""
+    t = torch.as_tensor(np.asarray(bucket_totals.cpu() if isinstance(bucket_totals, torch.Tensor) else bucket_totals)
+                        .astype(np.int64))
+    nb = int(t.numel())
+    cum = torch.cumsum(t, 0)
+    total = int(cum[-1]) if nb else 0
+    bounds = [0]
+    for r in range(1, world):
+        target = (total * r) // world
+        b = int(torch.searchsorted(cum, torch.tensor([target], dtype=torch.int64), right=True)[0]) if nb else 0
+        bounds.append(max(bounds[-1], min(b, nb)))
+    bounds.append(nb)
+    return bounds
+
+
+def sharded_count(kc, rank, world, group=None, timings=None):
+    """Run the sharded pipeline on this rank's KmerCounter `kc` (reads already in its store).
+
+    Returns (spectrum uint64 array summed over all ranks, n_instances_global, n_distinct_global).
+    The rank's own shard table stays queryable in `kc` (counts of the k-mers it owns)."""
+    from .kmers import ApgkError
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+    e0.record()
+    # ---- same geometry on every rank
+    up = torch.tensor([kc.window_upper()], dtype=torch.int64, device=dev)
+    dist.all_reduce(up, op=dist.ReduceOp.MAX, group=group)
+    P = kc.choose_prefix_bits(int(up.item()))
+    # ---- local partition (levels 0 + 1)
+    failed = 0
+    try:
+        kc.partition(P)
+    except ApgkError as e:
+        if e.code != -5:  # APGK_E_RANGE: more than one k-mer-space round needed here
+            raise
+        failed = 1
+    flag = torch.tensor([failed], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()):
+        if timings is not None:
+            timings["path"] = "hash"
+        return sharded_count_hash(kc, rank, world, group, timings)
+    sizes_ptr, nb, elems_ptr, eb, n_elems = kc.partition_info()
+    sizes = _wrap(sizes_ptr, nb, "<i8", dev)
+    all_sizes = torch.empty((world, nb), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes.contiguous(), group=group)
+    if int(all_sizes.max().item()) >= 2 ** 31:
+        raise RuntimeError("a bucket piece holds 2^31 or more k-mers")
+    bounds = balanced_splitters(all_sizes.sum(0), world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    # per-destination send counts (my pieces) and per-source receive counts (their pieces of my range)
+    cum = torch.zeros((world, nb + 1), dtype=torch.int64, device=dev)
+    torch.cumsum(all_sizes, 1, out=cum[:, 1:])
+    bt = torch.tensor(bounds, dtype=torch.int64, device=dev)
+    at_bounds = cum[:, bt].cpu().numpy()                      # [world, world+1]
+    send_counts = (at_bounds[rank, 1:] - at_bounds[rank, :-1]).astype(np.int64)
+    recv_counts = (at_bounds[:, rank + 1] - at_bounds[:, rank]).astype(np.int64)
+    n_recv = int(recv_counts.sum())
+    words = 1 if eb == 4 else eb // 8
+    tstr, tdt = ("<i4", torch.int32) if eb == 4 else ("<i8", torch.int64)
+    send = _wrap(elems_ptr, max(n_elems, 1) * words, tstr, dev) if elems_ptr else torch.empty(1, dtype=tdt, device=dev)
+    need = max(n_recv, 1) * eb
+    buf = getattr(kc, "_recv_buf", None)
+    if buf is None or buf.numel() * 8 < need:
+        kc._recv_buf = None
+        del buf
+        torch.cuda.empty_cache()
+        buf = torch.empty(int(need * 1.02) // 8 + 1024, dtype=torch.int64, device=dev)
+        kc._recv_buf = buf
+    recv = buf.view(tdt)
+    e1.record()
+    dist.all_to_all_single(recv[: n_recv * words], send[: n_elems * words],
+                           output_split_sizes=[int(c) * words for c in recv_counts],
+                           input_split_sizes=[int(c) * words for c in send_counts], group=group)
+    e2.record()
+    sizes_u32 = all_sizes.to(torch.int32).contiguous()
+    torch.cuda.current_stream().synchronize()
+    del send
+    seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
+    kc.count_pieces(recv.data_ptr(), world, sizes_u32.data_ptr(), seg_off, lo, hi)
+    e3.record()
+    out = _reduce_results(kc, dev, group)
+    if timings is not None:
+        torch.cuda.current_stream().synchronize()
+        timings["path"] = "partition-first"
+        timings["partition_ms"] = e0.elapsed_time(e1)
+        timings["all_to_all_ms"] = e1.elapsed_time(e2)
+        timings["count_ms"] = e2.elapsed_time(e3)
+        timings["sent_elems"] = int(n_elems)
+        timings["recv_elems"] = n_recv
+        timings["elem_bytes"] = int(eb)
+        timings["bucket_range"] = (int(lo), int(hi))
+    return out
+
+
+def _reduce_results(kc, dev, group):
+    """sum the dense spectra in place on the device, reload on the host side of the library; totals"""
+    ptr, n = kc.spectrum_device()
+    spec = _wrap(ptr, n, "<i8", dev)
+    dist.all_reduce(spec, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.current_stream().synchronize()
+    kc.spectrum_reload()
+    ni, nd = kc.totals()
+    tot = torch.tensor([ni, nd], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return kc.spectrum(), int(tot[0].item()), int(tot[1].item())
 
 
 def exchange_plan(send_counts, world, group=None, device=None):
@@ -24,11 +146,8 @@ def exchange_plan(send_counts, world, group=None, device=None):
     return t_recv.cpu().numpy()
 
 
-def sharded_count(kc, rank, world, group=None, timings=None):
-    """Run the sharded pipeline on this rank's KmerCounter `kc` (reads already in its store).
-
-    Returns (spectrum uint64 array summed over all ranks, n_instances_global, n_distinct_global).
-    The rank's own shard table stays queryable in `kc` (counts of the k-mers it owns)."""
+def sharded_count_hash(kc, rank, world, group=None, timings=None):
+    """Hash-owner form of the sharded pipeline (see the module docstring); same contract as sharded_count."""
     dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     W = kc.W
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -77,12 +196,16 @@ def sharded_count(kc, rank, world, group=None, timings=None):
 class _CudaArray:
     """Minimal __cuda_array_interface__ holder so torch can view library-owned device memory."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr, n, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _wrap(ptr, n, typestr, dev):
+    return torch.as_tensor(_CudaArray(ptr, n, typestr), device=dev)
 
 
 def _wrap_u64(ptr, n, dev):
-    return torch.as_tensor(_CudaArray(ptr, n), device=dev)
+    return _wrap(ptr, n, "<i8", dev)
 
 
 # ---------------------------------------------------------------------------
@@ -107,3 +230,39 @@ def host_shuffle(kmers, K, rank, world, group=None):
     dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * W for c in recv_counts],
                            input_split_sizes=[int(c) * W for c in send_counts], group=group)
     return recv.numpy().astype(np.uint64).reshape(-1, W)
+
+
+def host_partition_shuffle(kmers, K, prefix_bits, rank, world, group=None):
+    """Host mirror of the partition-first exchange (gloo or nccl): kmers uint64[n, W] canonical k-mer
+    instances held by this rank.  Buckets = leading prefix_bits of the 2K-bit k-mer; bucket ranges are
+    cut by `balanced_splitters` from the all-gathered histogram; returns (the instances this rank owns,
+    (bucket_lo, bucket_hi))."""
+    from .kmers import words_per_kmer
+
+    W = words_per_kmer(K)
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64).reshape(-1, W)
+    top = 2 * K - 64 * (W - 1)  # bits in word 0
+    if prefix_bits > 2 * K:
+        raise ValueError("prefix longer than the k-mer")
+    if prefix_bits <= top:
+        bucket = (kmers[:, 0] >> np.uint64(top - prefix_bits)).astype(np.int64) if len(kmers) else np.zeros(0, np.int64)
+    else:  # the prefix reaches into word 1
+        r = prefix_bits - top
+        bucket = ((kmers[:, 0] << np.uint64(r)) | (kmers[:, 1] >> np.uint64(64 - r))).astype(np.int64)
+    nb = 1 << prefix_bits
+    sizes = torch.from_numpy(np.bincount(bucket, minlength=nb).astype(np.int64))
+    all_sizes = [torch.empty(nb, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = torch.stack(all_sizes)
+    bounds = balanced_splitters(all_sizes.sum(0), world)
+    order = np.argsort(bucket, kind="stable")
+    cum = np.concatenate([[0], np.cumsum(all_sizes.numpy(), axis=1)[rank]])
+    send_counts = np.array([cum[bounds[r + 1]] - cum[bounds[r]] for r in range(world)], dtype=np.int64)
+    send = torch.from_numpy(kmers[order].astype(np.int64).reshape(-1))
+    t_recv_counts = torch.empty(world, dtype=torch.int64)
+    dist.all_to_all_single(t_recv_counts, torch.from_numpy(send_counts), group=group)
+    recv_counts = t_recv_counts.numpy()
+    recv = torch.empty(int(recv_counts.sum()) * W, dtype=torch.int64)
+    dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * W for c in recv_counts],
+                           input_split_sizes=[int(c) * W for c in send_counts], group=group)
+    return recv.numpy().astype(np.uint64).reshape(-1, W), (bounds[rank], bounds[rank + 1])

@@ -184,6 +184,33 @@ class KmerCounter:
         self._ck(self._L.apgk_key_buffer(self._h, n_keys, C.byref(p)))
         return p.value
 
+    # -- multi-GPU, partition-first form
+    def window_upper(self):
+        u = C.c_uint64()
+        self._ck(self._L.apgk_window_upper(self._h, C.byref(u)))
+        return u.value
+
+    def choose_prefix_bits(self, upper):
+        p = C.c_int32()
+        self._ck(self._L.apgk_choose_prefix_bits(self._h, upper, C.byref(p)))
+        return p.value
+
+    def partition(self, prefix_bits=0):
+        """levels 0+1 only; raises ApgkError (code APGK_E_RANGE) if one k-mer-space round is not enough"""
+        self._ck(self._L.apgk_partition(self._h, prefix_bits))
+
+    def partition_info(self):
+        """-> (d_bucket_sizes ptr (uint64[n_buckets]), n_buckets, d_elems ptr, elem_bytes, n_elems)"""
+        a, b = C.c_void_p(), C.c_void_p()
+        nb, ne = C.c_uint64(), C.c_uint64()
+        eb = C.c_uint32()
+        self._ck(self._L.apgk_partition_info(self._h, C.byref(a), C.byref(nb), C.byref(b), C.byref(eb), C.byref(ne)))
+        return a.value, nb.value, b.value, eb.value, ne.value
+
+    def count_pieces(self, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi):
+        so = np.ascontiguousarray(seg_off, dtype=np.uint64)
+        self._ck(self._L.apgk_count_pieces(self._h, d_recv, n_src, d_sizes_all, so.ctypes.data, bucket_lo, bucket_hi))
+
     def spectrum_device(self):
         p = C.c_void_p()
         n = C.c_uint64()

@@ -143,6 +143,32 @@ int apgk_finish_keys_device(apgk_ctx* ctx, const uint64_t* d_keys, uint64_t n);
 int apgk_spectrum_device(apgk_ctx* ctx, uint64_t** d_spec, uint64_t* len);
 int apgk_spectrum_reload(apgk_ctx* ctx);
 
+/* ---- multi-GPU, partition-first form (the one allpathslg_b200.dist.sharded_count uses): every rank
+ * partitions ITS reads by the leading prefix_bits of the canonical k-mer (levels 0 and 1 of the
+ * single-GPU pipeline, nothing else), the ranks agree on balanced bucket ranges from the summed
+ * bucket histogram, exchange whole bucket ranges of level-1 elements (32-bit remainders when they
+ * fit) and each rank sorts + counts the ranges it owns.  A k-mer's owner is a function of the
+ * canonical k-mer alone, so counts are final without a merge; compared with the hash form above
+ * the k-mers are extracted and partitioned once, not twice, and half the bytes cross NVLink. */
+/* Upper bound of the k-mer instances in the read store (what the geometry choice is based on). */
+int apgk_window_upper(const apgk_ctx* ctx, uint64_t* upper);
+/* Prefix bits a run over `upper` instances would pick.  Ranks call it with the maximum over ranks
+ * and pass the result to apgk_partition so that all of them use the same geometry. */
+int apgk_choose_prefix_bits(apgk_ctx* ctx, uint64_t upper, int32_t* prefix_bits);
+/* Levels 0+1 over the read store with 2^prefix_bits buckets (0 = choose).  APGK_E_RANGE when the
+ * k-mers would need more than one k-mer-space round on this device. */
+int apgk_partition(apgk_ctx* ctx, int32_t prefix_bits);
+/* Result of apgk_partition, all DEVICE pointers owned by the library: bucket sizes
+ * (uint64[n_buckets]), the elements grouped by bucket (elem_bytes each: 4, or 8 * W). */
+int apgk_partition_info(apgk_ctx* ctx, const uint64_t** d_bucket_sizes, uint64_t* n_buckets, void** d_elems,
+                        uint32_t* elem_bytes, uint64_t* n_elems);
+/* Receiver side.  d_recv (DEVICE) holds n_src segments, segment s starting at element seg_off[s]
+ * (HOST array) and containing source s's pieces of buckets [bucket_lo, bucket_hi) in bucket order;
+ * d_sizes_all (DEVICE, uint32[n_src][n_buckets]) are the piece sizes.  Sorts + counts the shard:
+ * afterwards the context answers totals / spectrum / counts / lookups for the k-mers it owns. */
+int apgk_count_pieces(apgk_ctx* ctx, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
+                      const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi);
+
 /* ---- instrumentation */
 #define APGK_N_STAGES 12
 /* Device milliseconds of the last finish, by stage; names via apgk_stage_name(i). */

@@ -21,12 +21,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, K, out_dir):
+def _worker(rank, world, port, K, out_dir, mode="hash"):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
 
     from allpathslg_b200 import _lib
-    from allpathslg_b200.dist import host_shuffle
+    from allpathslg_b200.dist import host_partition_shuffle, host_shuffle
     from oracle import oracle_a as A
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -43,7 +43,11 @@ def _worker(rank, world, port, K, out_dir):
     va = np.zeros(total, dtype=np.uint8)
     assert L.apgk_debug_host_extract(packed.ctypes.data, off.ctypes.data, n_per, K, km.ctypes.data, va.ctypes.data) == 0
     inst = km.reshape(-1, W)[va.astype(bool)]
-    mine = host_shuffle(inst, K, rank, world)
+    rng = (0, 0)
+    if mode == "hash":
+        mine = host_shuffle(inst, K, rank, world)
+    else:
+        mine, rng = host_partition_shuffle(inst, K, 12, rank, world)
     # sort + count the shard this rank owns
     if len(mine):
         order = np.lexsort(tuple(mine[:, j] for j in range(W - 1, -1, -1)))
@@ -56,7 +60,7 @@ def _worker(rank, world, port, K, out_dir):
     else:
         counts = np.zeros(0, dtype=np.int64)
         kmers = np.zeros((0, W), dtype=np.uint64)
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), kmers=kmers, counts=counts)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), kmers=kmers, counts=counts, rng=np.array(rng))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,3 +86,52 @@ def test_hash_sharded_count_gloo(oracle, tmp_path, world, K):
         spec += np.bincount(pt["counts"], minlength=len(spec)).astype(np.uint64)
     assert (spec == oracle.spectrum(ec)).all()
     assert sum(int(pt["counts"].sum()) for pt in parts) == en
+
+
+@pytest.mark.parametrize("world,K", [(2, 25), (3, 40), (2, 96)])
+def test_partition_first_sharded_count_gloo(oracle, tmp_path, world, K):
+    """Host mirror of dist.sharded_count's exchange: bucket ranges of the 12-bit prefix, cut by
+    balanced_splitters from the all-gathered histogram, routed with all_to_all over gloo."""
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, K, str(tmp_path), "partition"), nprocs=world, join=True)
+    sp = oracle.synth_params(40_000, 100)
+    packed, off = oracle.synth_reads(sp, 0, 3000 * world)
+    ek, ec, en = oracle.count(packed, off, K)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    W = ek.shape[1]
+    top = 2 * K - 64 * (W - 1)
+    bucket = (ek[:, 0] >> np.uint64(top - 12)).astype(np.int64)
+    lo_prev = 0
+    for r, pt in enumerate(parts):
+        lo, hi = int(pt["rng"][0]), int(pt["rng"][1])
+        assert lo == lo_prev and hi >= lo
+        lo_prev = hi
+        sel = (bucket >= lo) & (bucket < hi)
+        assert (pt["kmers"] == ek[sel]).all()
+        assert (pt["counts"].astype(np.uint64) == ec[sel]).all()
+    assert lo_prev == 1 << 12
+    per = [int(pt["counts"].sum()) for pt in parts]
+    assert sum(per) == en and max(per) < 1.2 * en / world  # balanced shards
+    # union in rank order is the sorted table; summed spectra equal the single-process spectrum
+    allk = np.concatenate([pt["kmers"] for pt in parts])
+    assert (allk == ek).all()
+    spec = np.zeros(int(ec.max()) + 1, dtype=np.uint64)
+    for pt in parts:
+        spec += np.bincount(pt["counts"], minlength=len(spec)).astype(np.uint64)
+    assert (spec == oracle.spectrum(ec)).all()
+
+
+def test_balanced_splitters():
+    from allpathslg_b200.dist import balanced_splitters
+
+    assert balanced_splitters(np.array([5, 5]), 2) == [0, 1, 2]
+    assert balanced_splitters(np.array([10, 0, 0, 10]), 2) == [0, 3, 4]
+    assert balanced_splitters(np.zeros(8, dtype=np.int64), 3) == [0, 8, 8, 8]
+    assert balanced_splitters(np.array([7]), 4) == [0, 0, 0, 0, 1] or balanced_splitters(np.array([7]), 4)[-1] == 1
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 1000, size=4096)
+    for world in (1, 2, 3, 8):
+        b = balanced_splitters(t, world)
+        assert b[0] == 0 and b[-1] == 4096 and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        per = [int(t[b[r]:b[r + 1]].sum()) for r in range(world)]
+        assert sum(per) == int(t.sum()) and max(per) - min(per) <= 2 * 1000

@@ -400,6 +400,96 @@ def test_owner_partition_and_key_ingest(oracle, K, world):
     kc.close()
 
 
+@pytest.mark.parametrize("K,world,n_reads", [(25, 2, 30_000), (25, 5, 30_000), (20, 3, 20_000), (48, 3, 12_000), (96, 2, 8_000)])
+def test_partition_first_shards_emulated_ranks(oracle, K, world, n_reads):
+    """The partition-first multi-GPU path emulated on one GPU: every "rank" partitions its share of the
+    reads (apgk_partition), the exchange of bucket ranges is done here with host copies exactly as
+    dist.sharded_count does it with all_to_all, every rank counts its range (apgk_count_pieces).
+    The union of the shard tables and the summed spectra must equal the oracle on all the reads;
+    every shard table must also answer lookups for its own k-mers (and 0 for the others)."""
+    import torch
+
+    from allpathslg_b200 import KmerCounter
+    from allpathslg_b200.dist import balanced_splitters
+
+    L = 100
+    sp = oracle.synth_params(200_000, L)
+    p, o = oracle.synth_reads(sp, 0, n_reads)
+    ek, ec, en = oracle.count(p, o, K)
+    W = ek.shape[1]
+    share = [(n_reads * r) // world for r in range(world + 1)]
+    if world == 5:
+        share[3] = share[2]  # one rank without reads
+    kcs = []
+    for r in range(world):
+        kc = KmerCounter(K)
+        n = share[r + 1] - share[r]
+        if n:
+            pr, _ = oracle.synth_reads(sp, share[r], n)
+            kc.add_reads_uniform(pr, n, L)
+        kcs.append(kc)
+    P = kcs[0].choose_prefix_bits(max(kc.window_upper() for kc in kcs))
+    sizes, elems, eb = [], [], None
+    for kc in kcs:
+        kc.partition(P)
+        sp_, nb, ep, eb_, ne = kc.partition_info()
+        eb = eb_ if eb is None else eb
+        assert eb_ == eb and nb == 1 << P
+        sz = torch.empty(nb, dtype=torch.int64, device="cuda")
+        sz.copy_(torch.as_tensor(_CudaView(sp_, nb, "<i8"), device="cuda"))
+        sizes.append(sz.cpu().numpy())
+        dt = "<i4" if eb == 4 else "<i8"
+        words = 1 if eb == 4 else eb // 8
+        e = torch.as_tensor(_CudaView(ep, max(ne, 1) * words, dt), device="cuda")[: ne * words].cpu().numpy() if ne else \
+            np.zeros(0, dtype=np.int32 if eb == 4 else np.int64)
+        elems.append(e)
+        assert int(sizes[-1].sum()) == ne
+    assert sum(int(s.sum()) for s in sizes) == en
+    all_sizes = np.stack(sizes)
+    bounds = balanced_splitters(all_sizes.sum(0), world)
+    assert bounds[0] == 0 and bounds[-1] == 1 << P and all(a <= b for a, b in zip(bounds, bounds[1:]))
+    words = 1 if eb == 4 else eb // 8
+    cum = np.concatenate([np.zeros((world, 1), np.int64), np.cumsum(all_sizes, axis=1)], axis=1)
+    d_sizes = torch.from_numpy(all_sizes.astype(np.int32)).cuda().contiguous()
+    total_spec = np.zeros(1, dtype=np.uint64)
+    got_k, got_c = [], []
+    per_rank = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        parts = [elems[s][cum[s, lo] * words: cum[s, hi] * words] for s in range(world)]
+        seg_off = np.concatenate([[0], np.cumsum([len(x) // words for x in parts])[:-1]]).astype(np.uint64)
+        recv = torch.from_numpy(np.concatenate(parts) if sum(len(x) for x in parts) else np.zeros(1, parts[0].dtype)).cuda()
+        kcs[r].count_pieces(recv.data_ptr(), world, d_sizes.data_ptr(), seg_off, lo, hi)
+        gk, gc = kcs[r].counts()
+        got_k.append(gk); got_c.append(gc)
+        per_rank.append(kcs[r].totals()[0])
+        s = kcs[r].spectrum()
+        if len(s) > len(total_spec):
+            total_spec = np.concatenate([total_spec, np.zeros(len(s) - len(total_spec), np.uint64)])
+        total_spec[: len(s)] += s
+    gk = np.concatenate(got_k); gc = np.concatenate(got_c)
+    assert len(gk) == len(ek) and (gk == ek).all() and (gc.astype(np.uint64) == ec).all()  # ranges ascend: union is sorted
+    es = oracle.spectrum(ec)
+    assert len(total_spec) == len(es) and (total_spec == es).all()
+    assert sum(per_rank) == en
+    if world > 1 and en > 10 * world:
+        assert max(per_rank) < 1.25 * en / world + (en >> P) * 64  # balanced up to bucket granularity
+    # shard tables answer lookups for their own k-mers only
+    pick = ek[:: max(1, len(ek) // 500)]
+    exp = ec[:: max(1, len(ek) // 500)]
+    tot = np.zeros(len(pick), dtype=np.uint64)
+    for r in range(world):
+        tot += kcs[r].lookup(pick, canonicalise=False).astype(np.uint64)
+    assert (tot == exp).all()
+    for kc in kcs:
+        kc.close()
+
+
+class _CudaView:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
 # ------------------------------------------------------------------ reference-named host API
 def test_reference_named_entry_points(oracle, tmp_path):
     from allpathslg_b200 import KmerFreqTable, KmerParcelsBuilder, KmerSpectrum, SortKmers
