@@ -843,25 +843,31 @@ int scan_u32(apgk_ctx* c, const uint32_t* in, uint64_t n, unsigned long long* ou
 
 template <int W, typename ElemB>
 int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
-                       const uint64_t* seg_off_host, uint32_t lo, uint32_t hi) {
+                       const uint64_t* seg_off_host, uint32_t lo, uint32_t hi, int d2) {
   const uint32_t nb = c->nb1;
+  // split bits: every merged bucket is cut into 2^d2 sub-buckets by the leading remainder bits
+  d2 = std::max(0, std::min(d2, 5));
+  d2 = std::min(d2, std::max(0, c->geom.REM - 1));
+  while (d2 > 0 && c->geom.D0 + c->geom.D1 + d2 > 27) d2--;
+  const uint32_t nbf = nb << d2;
   for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
   stage_begin(c, ST_TOTAL);
   stage_begin(c, ST_OWNER);
-  CU(c->segtot.ensure((size_t)nb * 8));
-  CU(c->nd.ensure(((size_t)nb + 1) * 4));
-  CU(c->bofs.ensure(((size_t)nb + 1) * 8));
-  CU(c->out_off_local.ensure(((size_t)nb + 1) * 8));
+  CU(c->segtot.ensure((size_t)nbf * 8));
+  CU(c->nd.ensure(((size_t)nbf + 1) * 4));
+  CU(c->bofs.ensure(((size_t)nbf + 1) * 8));
+  CU(c->out_off_local.ensure(((size_t)nbf + 1) * 8));
+  CU(c->out_off.ensure(((size_t)nbf + 1) * 8));
   CU(c->stats.ensure(64));
   CU(c->misc.ensure(64));
   CU(c->bstart64.ensure(std::max<size_t>(((size_t)(1u << c->geom.D0) + 1) * 8, (size_t)n_src * 8)));
   CU(cudaMemsetAsync(c->misc.p, 0, 64, c->stream));
-  // merged bucket sizes and offsets
-  k_merge_sizes<<<(nb + 255) / 256, 256, 0, c->stream>>>(d_sizes_all, n_src, nb, lo, hi, c->segtot.as<unsigned long long>(),
-                                                       c->nd.as<uint32_t>(), c->misc.as<unsigned int>());
+  // merged (coarse) bucket sizes -> nd, their offsets -> out_off_local (both are free until the counting starts)
+  k_merge_sizes<<<(nb + 255) / 256, 256, 0, c->stream>>>(d_sizes_all, n_src, nb, lo, hi, c->nd.as<uint32_t>(),
+                                                       c->misc.as<unsigned int>());
   LAUNCHED();
   unsigned long long Nr = 0;
-  { int rc = scan_u32(c, c->nd.as<uint32_t>(), nb, c->bofs.as<unsigned long long>(), &Nr); if (rc) return rc; }
+  { int rc = scan_u32(c, c->nd.as<uint32_t>(), nb, c->out_off_local.as<unsigned long long>(), &Nr); if (rc) return rc; }
   unsigned int ovf = 0;
   CU(cudaMemcpyAsync(&ovf, c->misc.p, 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -876,24 +882,31 @@ int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const ui
     if (rc) return rc;
   }
   CU(cudaMemcpyAsync(c->bstart64.p, seg_off_host, (size_t)n_src * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));  // seg_off_host may die; also orders the copies before the gather
+  CU(cudaStreamSynchronize(c->stream));  // seg_off_host may die
   CU(c->B.ensure(std::max<size_t>(Nr, 1) * sizeof(ElemB) + 16));
   CU(c->A.ensure(std::max<size_t>(Nr, 1) * sizeof(Key<W>)));
+  CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)nbf * 8, c->stream));
+  CU(cudaMemsetAsync(c->bofs.p, 0, ((size_t)nbf + 1) * 8, c->stream));
   if (Nr && hi > lo) {
-    const uint32_t grid = std::min<uint32_t>(hi - lo, (uint32_t)c->n_sm * 16);
-    k_gather_pieces<ElemB><<<grid, 128, 0, c->stream>>>((const ElemB*)d_recv, c->bstart64.as<unsigned long long>(),
-                                                        c->piece_off.as<unsigned long long>(), d_sizes_all,
-                                                        c->bofs.as<unsigned long long>(), n_src, nb, lo, hi, c->B.as<ElemB>());
+    const uint32_t grid = std::min<uint32_t>(hi - lo, (uint32_t)c->n_sm * 8);
+    // digit = the d2 bits just below the prefix: remainder bits [REM - d2, REM)
+    k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(
+        (const ElemB*)d_recv, c->bstart64.as<unsigned long long>(), c->piece_off.as<unsigned long long>(), d_sizes_all,
+        c->out_off_local.as<unsigned long long>(), n_src, nb, lo, hi, d2, c->geom.REM - d2, c->B.as<ElemB>(),
+        c->segtot.as<unsigned long long>(), c->bofs.as<unsigned long long>());
     LAUNCHED();
   }
   stage_end(c, ST_OWNER);
+  // from here on the context describes the finer geometry: P + d2 prefix bits
+  c->geom.D1 += d2; c->geom.REM -= d2;
+  c->nb1 = nbf;
   c->n_instances = Nr;
   c->n_big = 0;
   uint64_t n_prev = 0;
   CU(c->spec_ovf.ensure(((size_t)Nr / SPEC_DENSE + 16) * 8));
   CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
   CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
-  CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)nb + 1) * 8, c->stream));
+  CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)nbf + 1) * 8, c->stream));
   if (Nr) { int rc = count_buckets<W, ElemB>(c, Nr, Nr, n_prev); if (rc) return rc; }
   c->n_distinct = n_prev;
   c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
@@ -910,13 +923,13 @@ int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const ui
 
 template <int W>
 int count_pieces_impl(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
-                      const uint64_t* seg_off_host, uint64_t lo, uint64_t hi) {
+                      const uint64_t* seg_off_host, uint64_t lo, uint64_t hi, int d2) {
   if (!c->part_ready) FAIL(APGK_E_STATE, "apgk_count_pieces needs a preceding apgk_partition on this context");
   if (n_src == 0 || n_src > 1024 || lo > hi || hi > c->nb1) FAIL(APGK_E_ARG, "apgk_count_pieces: bad source count or bucket range");
   if constexpr (W == 1) {
-    if (c->elem_bytes == 4) return count_pieces_typed<W, uint32_t>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi);
+    if (c->elem_bytes == 4) return count_pieces_typed<W, uint32_t>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi, d2);
   }
-  return count_pieces_typed<W, Key<W>>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi);
+  return count_pieces_typed<W, Key<W>>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi, d2);
 }
 
 // ---------------------------------------------------------------- owner partition (multi-GPU shuffle, sender side)
@@ -1211,13 +1224,13 @@ int apgk_partition_info(apgk_ctx* c, const uint64_t** d_bucket_sizes, uint64_t* 
 }
 
 int apgk_count_pieces(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
-                      const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi) {
+                      const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi, int32_t split_bits) {
   if (!c || !d_sizes_all || !seg_off) return APGK_E_ARG;
   CU(cudaSetDevice(c->device));
   switch (c->W) {
-    case 1: return count_pieces_impl<1>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi);
-    case 2: return count_pieces_impl<2>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi);
-    case 3: return count_pieces_impl<3>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi);
+    case 1: return count_pieces_impl<1>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits);
+    case 2: return count_pieces_impl<2>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits);
+    case 3: return count_pieces_impl<3>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits);
   }
   return APGK_E_ARG;
 }

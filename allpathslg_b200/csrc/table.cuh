@@ -78,35 +78,95 @@ __global__ void k_classify(const unsigned long long* __restrict__ bsize, uint32_
 // rank s (sizes_all[s][b] elements), laid out source-major.  These kernels merge the sizes and gather the
 // pieces into one bucket-major array, so the per-bucket kernels run unchanged on the shard.
 __global__ void k_merge_sizes(const uint32_t* __restrict__ sizes_all, uint32_t n_src, uint32_t nb, uint32_t lo, uint32_t hi,
-                              unsigned long long* __restrict__ bsize, uint32_t* __restrict__ bsize32,
-                              unsigned int* __restrict__ overflow) {
+                              uint32_t* __restrict__ bsize32, unsigned int* __restrict__ overflow) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   unsigned long long t = 0;
   if (b >= lo && b < hi)
     for (uint32_t s = 0; s < n_src; s++) t += sizes_all[(size_t)s * nb + b];
   if (t >= (1ull << 32)) { atomicExch(overflow, 1u); t = 0; }
-  bsize[b] = t;
   bsize32[b] = (uint32_t)t;
 }
 __global__ void k_mask_sizes(const uint32_t* __restrict__ sizes, uint32_t nb, uint32_t lo, uint32_t hi, uint32_t* __restrict__ out) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nb) out[b] = (b >= lo && b < hi) ? sizes[b] : 0u;
 }
-// one CTA per owned bucket (grid-stride): copy its n_src pieces back to back to bofs[b]
-template <typename Elem>
-__global__ void k_gather_pieces(const Elem* __restrict__ recv, const unsigned long long* __restrict__ seg_off,
-                                const unsigned long long* __restrict__ piece_off /* [n_src][nb+1] */,
-                                const uint32_t* __restrict__ sizes_all, const unsigned long long* __restrict__ bofs,
-                                uint32_t n_src, uint32_t nb, uint32_t lo, uint32_t hi, Elem* __restrict__ out) {
+
+// split digit of a level-1 element: bits [pos, pos+len) of the remainder (32-bit elements) or of the key
+__device__ __forceinline__ uint32_t split_digit(uint32_t e, int pos, uint32_t mask) { return (e >> pos) & mask; }
+template <int W>
+__device__ __forceinline__ uint32_t split_digit(const Key<W>& e, int pos, uint32_t mask) { return mask ? key_bits(e, pos, __popc(mask)) : 0u; }
+__device__ __forceinline__ uint32_t split_strip(uint32_t e, int pos) { return e & lowmask32(pos); }  // keep the bits below the digit
+template <int W>
+__device__ __forceinline__ Key<W> split_strip(const Key<W>& e, int) { return e; }
+
+// One CTA per owned bucket (grid-stride).  A merged bucket holds n_src times the instances the sender's
+// geometry aimed at, so the gather also SPLITS it by the next d2 remainder bits into 2^d2 sub-buckets
+// (two passes over the pieces, the second served by L2): count, then place with warp-aggregated
+// cursors.  Order inside a sub-bucket is arbitrary -- the counting kernels do not depend on it.
+// Writes the fine bucket table (sizes, offsets) for buckets (b << d2) | j.
+template <typename Elem, int NT>
+__global__ void __launch_bounds__(NT) k_gather_split(const Elem* __restrict__ recv, const unsigned long long* __restrict__ seg_off,
+                                                     const unsigned long long* __restrict__ piece_off /* [n_src][nb+1] */,
+                                                     const uint32_t* __restrict__ sizes_all,
+                                                     const unsigned long long* __restrict__ bofs_coarse, uint32_t n_src, uint32_t nb,
+                                                     uint32_t lo, uint32_t hi, int d2, int digit_pos, Elem* __restrict__ out,
+                                                     unsigned long long* __restrict__ bsize_fine,
+                                                     unsigned long long* __restrict__ bofs_fine) {
+  __shared__ uint32_t hist[32];
+  __shared__ unsigned long long cursor[32];
+  const uint32_t nbins = 1u << d2, mask = nbins - 1u;
+  const int lane = threadIdx.x & 31;
   for (uint32_t b = lo + blockIdx.x; b < hi; b += gridDim.x) {
-    unsigned long long dst = bofs[b];
+    if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+    __syncthreads();
+    if (d2 > 0) {
+      for (uint32_t s = 0; s < n_src; s++) {
+        const uint32_t n = sizes_all[(size_t)s * nb + b];
+        const Elem* src = recv + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
+        for (uint32_t i = threadIdx.x; i < n; i += NT) atomicAdd(&hist[split_digit(src[i], digit_pos, mask)], 1u);
+      }
+    } else if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (uint32_t s = 0; s < n_src; s++) t += sizes_all[(size_t)s * nb + b];
+      hist[0] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long run = bofs_coarse[b];
+      for (uint32_t j = 0; j < nbins; j++) {
+        const size_t f = ((size_t)b << d2) | j;
+        bsize_fine[f] = hist[j];
+        bofs_fine[f] = run;
+        cursor[j] = run;
+        run += hist[j];
+      }
+    }
+    __syncthreads();
     for (uint32_t s = 0; s < n_src; s++) {
       const uint32_t n = sizes_all[(size_t)s * nb + b];
       const Elem* src = recv + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
-      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[dst + i] = src[i];
-      dst += n;
+      for (uint32_t i0 = 0; i0 < n; i0 += NT) {   // uniform trip count: the ballots below need whole warps
+        const uint32_t i = i0 + threadIdx.x;
+        const bool ok = i < n;
+        Elem e{};
+        uint32_t d = 0;
+        if (ok) { e = src[i]; d = split_digit(e, digit_pos, mask); }
+        unsigned long long pos = 0;
+        for (uint32_t j = 0; j < nbins; j++) {
+          const uint32_t m = __ballot_sync(0xffffffffu, ok && d == j);
+          if (m) {
+            const int leader = __ffs((int)m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[j], (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ok && d == j) pos = base + __popc(m & ((1u << lane) - 1u));
+          }
+        }
+        if (ok) out[pos] = split_strip(e, digit_pos);
+      }
     }
+    __syncthreads();
   }
 }
 

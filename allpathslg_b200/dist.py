@@ -186,6 +186,7 @@ def sharded_count_hash(kc, rank, world, group=None, timings=None):
     tot = torch.tensor([ni, nd], dtype=torch.int64, device=dev)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
     if timings is not None:
+        timings.setdefault("path", "hash")
         timings["owner_ms"] = e0.elapsed_time(e1)
         timings["all_to_all_ms"] = e1.elapsed_time(e2)
         timings["sent_kmers"] = n_send

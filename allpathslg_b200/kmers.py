@@ -207,9 +207,12 @@ class KmerCounter:
         self._ck(self._L.apgk_partition_info(self._h, C.byref(a), C.byref(nb), C.byref(b), C.byref(eb), C.byref(ne)))
         return a.value, nb.value, b.value, eb.value, ne.value
 
-    def count_pieces(self, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi):
+    def count_pieces(self, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits=None):
         so = np.ascontiguousarray(seg_off, dtype=np.uint64)
-        self._ck(self._L.apgk_count_pieces(self._h, d_recv, n_src, d_sizes_all, so.ctypes.data, bucket_lo, bucket_hi))
+        if split_bits is None:
+            split_bits = max(0, (n_src - 1).bit_length())
+        self._ck(self._L.apgk_count_pieces(self._h, d_recv, n_src, d_sizes_all, so.ctypes.data, bucket_lo, bucket_hi,
+                                           split_bits))
 
     def spectrum_device(self):
         p = C.c_void_p()

@@ -216,6 +216,7 @@ def run_ours(args):
     kc.reset_counters()
     stage_acc = {}
     shard_acc = {}
+    shard_info = {}
     barrier()
     t0 = time.perf_counter()
     n_inst_total = 0
@@ -224,7 +225,10 @@ def run_ours(args):
         for k_, v in kc.stage_ms().items():
             stage_acc[k_] = stage_acc.get(k_, 0.0) + v
         for k_, v in (tm or {}).items():
-            shard_acc[k_] = shard_acc.get(k_, 0.0) + v
+            if isinstance(v, (int, float)) and not isinstance(v, bool):
+                shard_acc[k_] = shard_acc.get(k_, 0.0) + v
+            else:
+                shard_info[k_] = v
     barrier()
     dt = time.perf_counter() - t0
     launches = kc.kernel_launches()
@@ -324,7 +328,7 @@ def run_ours(args):
         "cpu_baseline": {"value": round(cb_inst / cb_dt / 1e9, 4), "unit": "Gk-mers/s", "cores": cores, "kind": "port",
                          "sample": "first %d reads (%d k-mer instances) of the workload, oracle port "
                                    "(not the reference's code: parity unpinned)" % (CPU_SAMPLE_READS, cb_inst)},
-        "geometry": geo, "shard_ms": {k_: round(v / args.steps, 2) for k_, v in shard_acc.items()} if shard_acc else None,
+        "geometry": geo, "shard_ms": dict({k_: round(v / args.steps, 2) for k_, v in shard_acc.items()}, **{k_: (list(v) if isinstance(v, tuple) else v) for k_, v in shard_info.items()}) if shard_acc else None,
         "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }

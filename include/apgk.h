@@ -164,10 +164,12 @@ int apgk_partition_info(apgk_ctx* ctx, const uint64_t** d_bucket_sizes, uint64_t
                         uint32_t* elem_bytes, uint64_t* n_elems);
 /* Receiver side.  d_recv (DEVICE) holds n_src segments, segment s starting at element seg_off[s]
  * (HOST array) and containing source s's pieces of buckets [bucket_lo, bucket_hi) in bucket order;
- * d_sizes_all (DEVICE, uint32[n_src][n_buckets]) are the piece sizes.  Sorts + counts the shard:
+ * d_sizes_all (DEVICE, uint32[n_src][n_buckets]) are the piece sizes.  A merged bucket holds the
+ * instances of all the sources, so each is first cut into 2^split_bits sub-buckets by its next
+ * remainder bits (pass ceil(log2(n_src)); clamped by the library).  Sorts + counts the shard:
  * afterwards the context answers totals / spectrum / counts / lookups for the k-mers it owns. */
 int apgk_count_pieces(apgk_ctx* ctx, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
-                      const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi);
+                      const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi, int32_t split_bits);
 
 /* ---- instrumentation */
 #define APGK_N_STAGES 12

@@ -20,16 +20,26 @@ for (K, G, L, n_per) in [(25, 2_000_000, 100, 400_000), (64, 500_000, 250, 40_00
     packed, off = A.synth_reads(A.synth_params(G, L), 0, n_per * world)
     ek, ec, en = A.count(packed, off, K)
     es = A.spectrum(ec)
-    own = owner_of(K, ek, world)
     gk, gc = kc.counts()
-    sel = own == rank
+    if tm["path"] == "hash":
+        sel = owner_of(K, ek, world) == rank
+    else:  # partition-first: this rank owns a range of the P-bit prefix buckets
+        g = kc.geometry()
+        P = g["D0"] + g["D1"]
+        W = ek.shape[1]
+        top = 2 * K - 64 * (W - 1)
+        assert P <= top
+        bucket = (ek[:, 0] >> np.uint64(top - P)).astype(np.int64)
+        lo, hi = tm["bucket_range"]
+        sel = (bucket >= lo) & (bucket < hi)
     good = (ni == en and nd == len(ek) and len(spec) == len(es) and (spec == es).all()
             and len(gk) == int(sel.sum()) and (gk == ek[sel]).all() and (gc.astype(np.uint64) == ec[sel]).all())
     t = torch.tensor([1 if good else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("K=%d world=%d instances=%d distinct=%d all-ranks-ok=%s  (rank0 sent %d recv %d, a2a %.2f ms)" %
-              (K, world, ni, nd, bool(t.item()), tm["sent_kmers"], tm["recv_kmers"], tm["all_to_all_ms"]), flush=True)
+        print("K=%d world=%d instances=%d distinct=%d all-ranks-ok=%s  (%s; rank0 sent %d recv %d, a2a %.2f ms)" %
+              (K, world, ni, nd, bool(t.item()), tm["path"], tm.get("sent_elems", tm.get("sent_kmers", 0)),
+               tm.get("recv_elems", tm.get("recv_kmers", 0)), tm["all_to_all_ms"]), flush=True)
     ok = ok and bool(t.item())
     kc.close()
 dist.barrier()
