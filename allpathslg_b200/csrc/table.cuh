@@ -113,18 +113,34 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* __restrict__ re
                                                      uint32_t lo, uint32_t hi, int d2, int digit_pos, Elem* __restrict__ out,
                                                      unsigned long long* __restrict__ bsize_fine,
                                                      unsigned long long* __restrict__ bofs_fine) {
-  __shared__ uint32_t hist[32];
-  __shared__ unsigned long long cursor[32];
+  constexpr int U = 4;                 // elements per thread and step
+  constexpr int MAXB = 32;             // 2^d2 <= 32
+  __shared__ uint32_t hist[MAXB];
+  __shared__ uint32_t cursor[MAXB];    // next free slot of each sub-bucket, relative to the bucket start
   const uint32_t nbins = 1u << d2, mask = nbins - 1u;
   const int lane = threadIdx.x & 31;
   for (uint32_t b = lo + blockIdx.x; b < hi; b += gridDim.x) {
-    if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+    if (threadIdx.x < MAXB) hist[threadIdx.x] = 0;
     __syncthreads();
+    // ---- pass 1: sub-digit histogram (per-warp ballots, one shared atomic per warp, bin and step)
     if (d2 > 0) {
       for (uint32_t s = 0; s < n_src; s++) {
         const uint32_t n = sizes_all[(size_t)s * nb + b];
         const Elem* src = recv + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
-        for (uint32_t i = threadIdx.x; i < n; i += NT) atomicAdd(&hist[split_digit(src[i], digit_pos, mask)], 1u);
+        for (uint32_t i0 = 0; i0 < n; i0 += NT * U) {
+          uint32_t d[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * NT + threadIdx.x;
+            d[u] = i < n ? split_digit(src[i], digit_pos, mask) : 0xFFFFFFFFu;
+          }
+          for (uint32_t j = 0; j < nbins; j++) {
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) cnt += __popc(__ballot_sync(0xffffffffu, d[u] == j));
+            if (lane == 0 && cnt) atomicAdd(&hist[j], cnt);
+          }
+        }
       }
     } else if (threadIdx.x == 0) {
       uint32_t t = 0;
@@ -132,38 +148,47 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* __restrict__ re
       hist[0] = t;
     }
     __syncthreads();
+    const unsigned long long base_b = bofs_coarse[b];
     if (threadIdx.x == 0) {
-      unsigned long long run = bofs_coarse[b];
+      uint32_t run = 0;
       for (uint32_t j = 0; j < nbins; j++) {
         const size_t f = ((size_t)b << d2) | j;
         bsize_fine[f] = hist[j];
-        bofs_fine[f] = run;
+        bofs_fine[f] = base_b + run;
         cursor[j] = run;
         run += hist[j];
       }
     }
     __syncthreads();
+    // ---- pass 2 (the pieces come from L2 now): place with warp-aggregated cursors
     for (uint32_t s = 0; s < n_src; s++) {
       const uint32_t n = sizes_all[(size_t)s * nb + b];
       const Elem* src = recv + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
-      for (uint32_t i0 = 0; i0 < n; i0 += NT) {   // uniform trip count: the ballots below need whole warps
-        const uint32_t i = i0 + threadIdx.x;
-        const bool ok = i < n;
-        Elem e{};
-        uint32_t d = 0;
-        if (ok) { e = src[i]; d = split_digit(e, digit_pos, mask); }
-        unsigned long long pos = 0;
+      for (uint32_t i0 = 0; i0 < n; i0 += NT * U) {   // uniform trip count: the ballots need whole warps
+        Elem e[U];
+        uint32_t d[U], pos[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t i = i0 + u * NT + threadIdx.x;
+          d[u] = 0xFFFFFFFFu; pos[u] = 0; e[u] = Elem{};
+          if (i < n) { e[u] = src[i]; d[u] = split_digit(e[u], digit_pos, mask); }
+        }
         for (uint32_t j = 0; j < nbins; j++) {
-          const uint32_t m = __ballot_sync(0xffffffffu, ok && d == j);
-          if (m) {
-            const int leader = __ffs((int)m) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(&cursor[j], (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (ok && d == j) pos = base + __popc(m & ((1u << lane) - 1u));
+          uint32_t m[U], tot = 0;
+#pragma unroll
+          for (int u = 0; u < U; u++) { m[u] = __ballot_sync(0xffffffffu, d[u] == j); tot += __popc(m[u]); }
+          uint32_t base = 0;
+          if (lane == 0 && tot) base = atomicAdd(&cursor[j], tot);
+          base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            if (d[u] == j) pos[u] = base + __popc(m[u] & ((1u << lane) - 1u));
+            base += __popc(m[u]);
           }
         }
-        if (ok) out[pos] = split_strip(e, digit_pos);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (d[u] != 0xFFFFFFFFu) out[base_b + pos[u]] = split_strip(e[u], digit_pos);
       }
     }
     __syncthreads();

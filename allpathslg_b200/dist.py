@@ -23,23 +23,31 @@ import torch
 import torch.distributed as dist
 
 
+def _splitters_tensor(bucket_totals, world):
+    """bounds as an int64 tensor [world+1] on the device of bucket_totals (no host round trip)."""
+    t = bucket_totals.to(torch.int64)
+    nb = int(t.numel())
+    dev = t.device
+    if nb == 0:
+        return torch.zeros(world + 1, dtype=torch.int64, device=dev)
+    cum = torch.cumsum(t, 0)
+    total = cum[-1]
+    r = torch.arange(1, world, dtype=torch.int64, device=dev)
+    targets = torch.div(total * r, world, rounding_mode="floor")
+    inner = torch.searchsorted(cum, targets, right=True).clamp(max=nb)
+    return torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), inner,
+                      torch.full((1,), nb, dtype=torch.int64, device=dev)])
+
+
 def balanced_splitters(bucket_totals, world):
     """Cut buckets [0, nb) into `world` contiguous ranges with (nearly) equal instance counts.
     bucket_totals: 1-D integer torch tensor or numpy array (instances per bucket, summed over ranks).
-    -> list of world+1 bucket indices, bounds[0] = 0, bounds[world] = nb, non-decreasing.
+    -> list of world+1 bucket indices, bounds[0] = 0, bounds[world] = nb, non-decreasing: range r ends
+    after the first bucket whose cumulative count exceeds total * (r+1) / world.
     Deterministic in its input, so every rank derives the same ownership."""
-    t = torch.as_tensor(np.asarray(bucket_totals.cpu() if isinstance(bucket_totals, torch.Tensor) else bucket_totals)
-                        .astype(np.int64))
-    nb = int(t.numel())
-    cum = torch.cumsum(t, 0)
-    total = int(cum[-1]) if nb else 0
-    bounds = [0]
-    for r in range(1, world):
-        target = (total * r) // world
-        b = int(torch.searchsorted(cum, torch.tensor([target], dtype=torch.int64), right=True)[0]) if nb else 0
-        bounds.append(max(bounds[-1], min(b, nb)))
-    bounds.append(nb)
-    return bounds
+    if not isinstance(bucket_totals, torch.Tensor):
+        bucket_totals = torch.from_numpy(np.ascontiguousarray(np.asarray(bucket_totals)).astype(np.int64))
+    return [int(x) for x in _splitters_tensor(bucket_totals, world).cpu()]
 
 
 def sharded_count(kc, rank, world, group=None, timings=None):
@@ -65,25 +73,34 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         if e.code != -5:  # APGK_E_RANGE: more than one k-mer-space round needed here
             raise
         failed = 1
-    flag = torch.tensor([failed], dtype=torch.int64, device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-    if int(flag.item()):
+    sizes = None
+    if not failed:
+        sizes_ptr, nb, elems_ptr, eb, n_elems = kc.partition_info()
+        sizes = _wrap(sizes_ptr, nb, "<i8", dev)
+    # one all-gather carries the bucket histogram and the "could not partition" flag
+    nb_all = 1 << P
+    mine = torch.empty(nb_all + 1, dtype=torch.int64, device=dev)
+    mine[:nb_all] = sizes if sizes is not None else 0
+    mine[nb_all] = failed
+    gathered = torch.empty((world, nb_all + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    all_sizes = gathered[:, :nb_all]
+    bounds_t = _splitters_tensor(all_sizes.sum(0), world)
+    cum = torch.zeros((world, nb_all + 1), dtype=torch.int64, device=dev)
+    torch.cumsum(all_sizes, 1, out=cum[:, 1:])
+    # everything the host needs in one transfer: flags, largest piece, bounds, cumulative counts at the bounds
+    small = torch.cat([gathered[:, nb_all].max().reshape(1), all_sizes.max().reshape(1), bounds_t,
+                       cum[:, bounds_t].reshape(-1)]).cpu().numpy()
+    if int(small[0]):
         if timings is not None:
             timings["path"] = "hash"
         return sharded_count_hash(kc, rank, world, group, timings)
-    sizes_ptr, nb, elems_ptr, eb, n_elems = kc.partition_info()
-    sizes = _wrap(sizes_ptr, nb, "<i8", dev)
-    all_sizes = torch.empty((world, nb), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_sizes, sizes.contiguous(), group=group)
-    if int(all_sizes.max().item()) >= 2 ** 31:
+    if int(small[1]) >= 2 ** 31:
         raise RuntimeError("a bucket piece holds 2^31 or more k-mers")
-    bounds = balanced_splitters(all_sizes.sum(0), world)
+    bounds = [int(x) for x in small[2: 3 + world]]
+    at_bounds = small[3 + world:].reshape(world, world + 1)
     lo, hi = bounds[rank], bounds[rank + 1]
     # per-destination send counts (my pieces) and per-source receive counts (their pieces of my range)
-    cum = torch.zeros((world, nb + 1), dtype=torch.int64, device=dev)
-    torch.cumsum(all_sizes, 1, out=cum[:, 1:])
-    bt = torch.tensor(bounds, dtype=torch.int64, device=dev)
-    at_bounds = cum[:, bt].cpu().numpy()                      # [world, world+1]
     send_counts = (at_bounds[rank, 1:] - at_bounds[rank, :-1]).astype(np.int64)
     recv_counts = (at_bounds[:, rank + 1] - at_bounds[:, rank]).astype(np.int64)
     n_recv = int(recv_counts.sum())
@@ -99,12 +116,12 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         buf = torch.empty(int(need * 1.02) // 8 + 1024, dtype=torch.int64, device=dev)
         kc._recv_buf = buf
     recv = buf.view(tdt)
+    sizes_u32 = all_sizes.to(torch.int32).contiguous()
     e1.record()
     dist.all_to_all_single(recv[: n_recv * words], send[: n_elems * words],
                            output_split_sizes=[int(c) * words for c in recv_counts],
                            input_split_sizes=[int(c) * words for c in send_counts], group=group)
     e2.record()
-    sizes_u32 = all_sizes.to(torch.int32).contiguous()
     torch.cuda.current_stream().synchronize()
     del send
     seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
@@ -121,20 +138,22 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         timings["recv_elems"] = n_recv
         timings["elem_bytes"] = int(eb)
         timings["bucket_range"] = (int(lo), int(hi))
+        timings["prefix_bits"] = int(P)
     return out
 
 
 def _reduce_results(kc, dev, group):
-    """sum the dense spectra in place on the device, reload on the host side of the library; totals"""
+    """sum the dense spectra (and the totals, in the same all-reduce) on the device; the library then
+    reloads its host copy of the spectrum"""
     ptr, n = kc.spectrum_device()
     spec = _wrap(ptr, n, "<i8", dev)
-    dist.all_reduce(spec, op=dist.ReduceOp.SUM, group=group)
-    torch.cuda.current_stream().synchronize()
-    kc.spectrum_reload()
     ni, nd = kc.totals()
-    tot = torch.tensor([ni, nd], dtype=torch.int64, device=dev)
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    return kc.spectrum(), int(tot[0].item()), int(tot[1].item())
+    both = torch.cat([spec, torch.tensor([ni, nd], dtype=torch.int64, device=dev)])
+    dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
+    spec.copy_(both[:n])
+    tot = both[n:].cpu()
+    kc.spectrum_reload()
+    return kc.spectrum(), int(tot[0]), int(tot[1])
 
 
 def exchange_plan(send_counts, world, group=None, device=None):

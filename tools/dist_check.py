@@ -24,8 +24,7 @@ for (K, G, L, n_per) in [(25, 2_000_000, 100, 400_000), (64, 500_000, 250, 40_00
     if tm["path"] == "hash":
         sel = owner_of(K, ek, world) == rank
     else:  # partition-first: this rank owns a range of the P-bit prefix buckets
-        g = kc.geometry()
-        P = g["D0"] + g["D1"]
+        P = tm["prefix_bits"]  # the exchange's bucket space (the shard's own table is indexed finer)
         W = ek.shape[1]
         top = 2 * K - 64 * (W - 1)
         assert P <= top
