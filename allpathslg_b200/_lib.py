@@ -60,6 +60,11 @@ SYMBOLS = {
     "apgk_partition_info": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint32),
                                       C.POINTER(C.c_uint64)]),
     "apgk_count_pieces": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int32]),
+    "apgk_count_pieces_peer": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int32, _vp]),
+    "apgk_partition_subsizes": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_vp)]),
+    "apgk_partition_export": (C.c_int, [_vp, _vp]),
+    "apgk_peer_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "apgk_peer_close": (C.c_int, [_vp, _vp]),
     "apgk_spectrum_device": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
     "apgk_spectrum_reload": (C.c_int, [_vp]),
     "apgk_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),

@@ -86,7 +86,8 @@ struct apgk_ctx {
   // ---- partition-only state (sharded counting: apgk_partition -> exchange -> apgk_count_pieces)
   bool part_ready = false;
   uint64_t part_n = 0;       // elements in B, grouped by the nb1 buckets (sizes in segtot)
-  DevBuf piece_off, piece_tmp;
+  DevBuf piece_off, piece_tmp, piece_ptrs, C2, sub_sizes;
+  void* count_src = nullptr;  // elements count_buckets reads (B, or C2 on the peer-memory path)
   // ---- owner partition state
   uint32_t owner_ranks = 0;
   uint32_t owner_tiles = 0;
@@ -592,6 +593,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
     stage_end(c, ST_SCATTER1);
 
     if (mode == RUN_PARTITION) { c->part_n = Nr; return APGK_OK; }
+    c->count_src = c->B.p;
     { int rc = count_buckets<W, ElemB>(c, Nr, N, n_prev); if (rc) return rc; }
   }
   c->n_distinct = n_prev;
@@ -651,7 +653,7 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
           int occ3 = 1;
           CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kern3, nt, sm3));
           const uint32_t grid3 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ3, 1)));
-          kern3<<<grid3, nt, sm3, c->stream>>>(c->B.as<uint32_t>(), bt, g.REM, ec, c->nd.as<uint32_t>());
+          kern3<<<grid3, nt, sm3, c->stream>>>((const uint32_t*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>());
           return APGK_OK;
         };
         int rc3 = l3_nt == 256 ? launch3(k_local3<256, W>, 256) : launch3(k_local3<512, W>, 512);
@@ -666,7 +668,7 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       int occ2 = 1;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, L2_NT, sm2));
       const uint32_t grid2 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ2, 1)));
-      kern2<<<grid2, L2_NT, sm2, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
+      kern2<<<grid2, L2_NT, sm2, c->stream>>>((const ElemB*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>(),
                                               c->deferred.as<uint32_t>(), c->nb1);
       LAUNCHED();
       // ... which the barrier-heavy general kernel then walks (normally empty)
@@ -676,7 +678,7 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       int occ = 1;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
       const uint32_t grid = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ, 1)));
-      kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(),
+      kern<<<grid, LOCAL_NT, sm, c->stream>>>((const ElemB*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>(),
                                               c->deferred.as<uint32_t>(), c->nb1);
       LAUNCHED();
     }
@@ -701,7 +703,7 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       bp.scratch = c->scratch.p;
       bp.stacks = c->stacks.as<unsigned long long>();
       stage_begin(c, ST_BIG);
-      kern<<<grid, LOCAL_NT, sm, c->stream>>>(c->B.as<ElemB>(), bt, g.REM, ec, c->nd.as<uint32_t>(), bp);
+      kern<<<grid, LOCAL_NT, sm, c->stream>>>((ElemB*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>(), bp);
       LAUNCHED();
       stage_end(c, ST_BIG);
     }
@@ -841,14 +843,35 @@ int scan_u32(apgk_ctx* c, const uint32_t* in, uint64_t n, unsigned long long* ou
   return APGK_OK;
 }
 
-template <int W, typename ElemB>
-int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
-                       const uint64_t* seg_off_host, uint32_t lo, uint32_t hi, int d2) {
-  const uint32_t nb = c->nb1;
-  // split bits: every merged bucket is cut into 2^d2 sub-buckets by the leading remainder bits
+// split bits actually used for a request (same on every rank: it depends on the geometry only)
+int effective_split_bits(const apgk_ctx* c, int d2) {
   d2 = std::max(0, std::min(d2, 5));
   d2 = std::min(d2, std::max(0, c->geom.REM - 1));
   while (d2 > 0 && c->geom.D0 + c->geom.D1 + d2 > 27) d2--;
+  return d2;
+}
+
+template <int W, typename ElemB>
+int sub_sizes_typed(apgk_ctx* c, int d2) {
+  const uint32_t nb = c->nb1;
+  CU(c->sub_sizes.ensure(((size_t)nb << d2) * 4 + 16));
+  if (!c->part_n) { CU(cudaMemsetAsync(c->sub_sizes.p, 0, ((size_t)nb << d2) * 4, c->stream)); }
+  else {
+    k_sub_hist<ElemB, 256><<<c->n_sm * 8, 256, 0, c->stream>>>(c->B.as<ElemB>(), c->bofs.as<unsigned long long>(),
+                                                               c->segtot.as<unsigned long long>(), nb, d2, c->geom.REM - d2,
+                                                               c->sub_sizes.as<uint32_t>());
+    LAUNCHED();
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return APGK_OK;
+}
+
+template <int W, typename ElemB>
+int count_pieces_typed(apgk_ctx* c, const void* const* bases_host, bool peer, uint32_t n_src, const uint32_t* d_sizes_all,
+                       const uint64_t* seg_off_host, uint32_t lo, uint32_t hi, int d2, const uint32_t* d_sub) {
+  const uint32_t nb = c->nb1;
+  // split bits: every merged bucket is cut into 2^d2 sub-buckets by the leading remainder bits
+  d2 = effective_split_bits(c, d2);
   const uint32_t nbf = nb << d2;
   for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
   stage_begin(c, ST_TOTAL);
@@ -881,9 +904,14 @@ int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const ui
     int rc = scan_u32(c, c->piece_tmp.as<uint32_t>(), nb, c->piece_off.as<unsigned long long>() + (size_t)s * (nb + 1), nullptr);
     if (rc) return rc;
   }
+  CU(c->piece_ptrs.ensure((size_t)n_src * 8));
+  CU(cudaMemcpyAsync(c->piece_ptrs.p, bases_host, (size_t)n_src * 8, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->bstart64.p, seg_off_host, (size_t)n_src * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));  // seg_off_host may die
-  CU(c->B.ensure(std::max<size_t>(Nr, 1) * sizeof(ElemB) + 16));
+  CU(cudaStreamSynchronize(c->stream));  // the host arrays may die
+  // the gathered shard: over the dead send buffer B after an all-to-all; a second buffer when the peers
+  // (and this rank itself) are still reading B
+  DevBuf& dst = peer ? c->C2 : c->B;
+  CU(dst.ensure(std::max<size_t>(Nr, 1) * sizeof(ElemB) + 16));
   CU(c->A.ensure(std::max<size_t>(Nr, 1) * sizeof(Key<W>)));
   CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)nbf * 8, c->stream));
   CU(cudaMemsetAsync(c->bofs.p, 0, ((size_t)nbf + 1) * 8, c->stream));
@@ -891,9 +919,9 @@ int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const ui
     const uint32_t grid = std::min<uint32_t>(hi - lo, (uint32_t)c->n_sm * 8);
     // digit = the d2 bits just below the prefix: remainder bits [REM - d2, REM)
     k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(
-        (const ElemB*)d_recv, c->bstart64.as<unsigned long long>(), c->piece_off.as<unsigned long long>(), d_sizes_all,
-        c->out_off_local.as<unsigned long long>(), n_src, nb, lo, hi, d2, c->geom.REM - d2, c->B.as<ElemB>(),
-        c->segtot.as<unsigned long long>(), c->bofs.as<unsigned long long>());
+        (const ElemB* const*)c->piece_ptrs.p, c->bstart64.as<unsigned long long>(), c->piece_off.as<unsigned long long>(), d_sizes_all,
+        c->out_off_local.as<unsigned long long>(), n_src, nb, lo, hi, d2, c->geom.REM - d2, (ElemB*)dst.p,
+        c->segtot.as<unsigned long long>(), c->bofs.as<unsigned long long>(), d_sub);
     LAUNCHED();
   }
   stage_end(c, ST_OWNER);
@@ -907,6 +935,7 @@ int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const ui
   CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
   CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
   CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)nbf + 1) * 8, c->stream));
+  c->count_src = dst.p;
   if (Nr) { int rc = count_buckets<W, ElemB>(c, Nr, Nr, n_prev); if (rc) return rc; }
   c->n_distinct = n_prev;
   c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
@@ -922,14 +951,14 @@ int count_pieces_typed(apgk_ctx* c, const void* d_recv, uint32_t n_src, const ui
 }
 
 template <int W>
-int count_pieces_impl(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
-                      const uint64_t* seg_off_host, uint64_t lo, uint64_t hi, int d2) {
+int count_pieces_impl(apgk_ctx* c, const void* const* bases_host, bool peer, uint32_t n_src, const uint32_t* d_sizes_all,
+                      const uint64_t* seg_off_host, uint64_t lo, uint64_t hi, int d2, const uint32_t* d_sub) {
   if (!c->part_ready) FAIL(APGK_E_STATE, "apgk_count_pieces needs a preceding apgk_partition on this context");
   if (n_src == 0 || n_src > 1024 || lo > hi || hi > c->nb1) FAIL(APGK_E_ARG, "apgk_count_pieces: bad source count or bucket range");
   if constexpr (W == 1) {
-    if (c->elem_bytes == 4) return count_pieces_typed<W, uint32_t>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi, d2);
+    if (c->elem_bytes == 4) return count_pieces_typed<W, uint32_t>(c, bases_host, peer, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi, d2, d_sub);
   }
-  return count_pieces_typed<W, Key<W>>(c, d_recv, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi, d2);
+  return count_pieces_typed<W, Key<W>>(c, bases_host, peer, n_src, d_sizes_all, seg_off_host, (uint32_t)lo, (uint32_t)hi, d2, d_sub);
 }
 
 // ---------------------------------------------------------------- owner partition (multi-GPU shuffle, sender side)
@@ -1223,14 +1252,75 @@ int apgk_partition_info(apgk_ctx* c, const uint64_t** d_bucket_sizes, uint64_t* 
   return APGK_OK;
 }
 
+int apgk_partition_subsizes(apgk_ctx* c, int32_t split_bits, int32_t* effective_bits, const uint32_t** d_sub_sizes) {
+  if (!c || !effective_bits || !d_sub_sizes) return APGK_E_ARG;
+  if (!c->part_ready) FAIL(APGK_E_STATE, "apgk_partition has not run");
+  CU(cudaSetDevice(c->device));
+  const int d2 = effective_split_bits(c, split_bits);
+  *effective_bits = d2;
+  int rc = APGK_E_ARG;
+  switch (c->W) {
+    case 1: rc = c->elem_bytes == 4 ? sub_sizes_typed<1, uint32_t>(c, d2) : sub_sizes_typed<1, Key<1>>(c, d2); break;
+    case 2: rc = sub_sizes_typed<2, Key<2>>(c, d2); break;
+    case 3: rc = sub_sizes_typed<3, Key<3>>(c, d2); break;
+  }
+  *d_sub_sizes = c->sub_sizes.as<uint32_t>();
+  return rc;
+}
+
 int apgk_count_pieces(apgk_ctx* c, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
                       const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi, int32_t split_bits) {
-  if (!c || !d_sizes_all || !seg_off) return APGK_E_ARG;
+  if (!c || !d_sizes_all || !seg_off || n_src == 0 || n_src > 1024) return APGK_E_ARG;
   CU(cudaSetDevice(c->device));
+  std::vector<const void*> bases(n_src, d_recv);
   switch (c->W) {
-    case 1: return count_pieces_impl<1>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits);
-    case 2: return count_pieces_impl<2>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits);
-    case 3: return count_pieces_impl<3>(c, d_recv, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits);
+    case 1: return count_pieces_impl<1>(c, bases.data(), false, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits, nullptr);
+    case 2: return count_pieces_impl<2>(c, bases.data(), false, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits, nullptr);
+    case 3: return count_pieces_impl<3>(c, bases.data(), false, n_src, d_sizes_all, seg_off, bucket_lo, bucket_hi, split_bits, nullptr);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_partition_export(apgk_ctx* c, uint8_t handle_out[64]) {
+  if (!c || !handle_out) return APGK_E_ARG;
+  if (!c->part_ready) FAIL(APGK_E_STATE, "apgk_partition has not run");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaSetDevice(c->device));
+  CU(c->B.ensure(16));  // an empty partition still exports a valid buffer
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->B.p));
+  memcpy(handle_out, &h, 64);
+  return APGK_OK;
+}
+
+int apgk_peer_open(apgk_ctx* c, const uint8_t handle[64], void** d_ptr) {
+  if (!c || !handle || !d_ptr) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return APGK_OK;
+}
+
+int apgk_peer_close(apgk_ctx* c, void* d_ptr) {
+  if (!c || !d_ptr) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return APGK_OK;
+}
+
+int apgk_count_pieces_peer(apgk_ctx* c, const void* const* d_src_base, uint32_t n_src, const uint32_t* d_sizes_all,
+                           const uint64_t* src_off, uint64_t bucket_lo, uint64_t bucket_hi, int32_t split_bits,
+                           const uint32_t* d_sub_sizes) {
+  if (!c || !d_src_base || !d_sizes_all || !src_off || n_src == 0 || n_src > 1024) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  std::vector<const void*> bases(d_src_base, d_src_base + n_src);
+  for (uint32_t s = 0; s < n_src; s++)
+    if (!bases[s]) bases[s] = c->B.p;  // NULL = this rank's own partition buffer
+  switch (c->W) {
+    case 1: return count_pieces_impl<1>(c, bases.data(), true, n_src, d_sizes_all, src_off, bucket_lo, bucket_hi, split_bits, d_sub_sizes);
+    case 2: return count_pieces_impl<2>(c, bases.data(), true, n_src, d_sizes_all, src_off, bucket_lo, bucket_hi, split_bits, d_sub_sizes);
+    case 3: return count_pieces_impl<3>(c, bases.data(), true, n_src, d_sizes_all, src_off, bucket_lo, bucket_hi, split_bits, d_sub_sizes);
   }
   return APGK_E_ARG;
 }

@@ -100,19 +100,56 @@ __device__ __forceinline__ uint32_t split_strip(uint32_t e, int pos) { return e 
 template <int W>
 __device__ __forceinline__ Key<W> split_strip(const Key<W>& e, int) { return e; }
 
-// One CTA per owned bucket (grid-stride).  A merged bucket holds n_src times the instances the sender's
+// Sender side: sizes of the 2^d2 sub-buckets of every bucket of this rank's partition buffer
+// (sub[(b << d2) | j]), so that the receivers can place the pieces in ONE pass over NVLink.
+// One WARP per bucket (no barriers, eight buckets in flight per CTA); lane j accumulates bin j.
+template <typename Elem, int NT>
+__global__ void __launch_bounds__(NT) k_sub_hist(const Elem* __restrict__ elems, const unsigned long long* __restrict__ bofs,
+                                                 const unsigned long long* __restrict__ bsize, uint32_t nb, int d2, int digit_pos,
+                                                 uint32_t* __restrict__ sub) {
+  constexpr int U = 8;
+  const uint32_t nbins = 1u << d2, mask = nbins - 1u;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * NT + threadIdx.x) >> 5, nwarps = (gridDim.x * NT) >> 5;
+  for (uint32_t b = warp; b < nb; b += nwarps) {
+    const uint32_t n = (uint32_t)bsize[b];
+    const Elem* src = elems + bofs[b];
+    uint32_t mine = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32 * U) {
+      uint32_t d[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t i = i0 + u * 32 + lane;
+        d[u] = i < n ? split_digit(src[i], digit_pos, mask) : 0xFFFFFFFFu;
+      }
+      for (uint32_t j = 0; j < nbins; j++) {
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) cnt += __popc(__ballot_sync(0xffffffffu, d[u] == j));
+        if (lane == j) mine += cnt;
+      }
+    }
+    if (lane < nbins) sub[((size_t)b << d2) | lane] = mine;
+  }
+}
+
+// One CTA per owned bucket (grid-stride).  Source s's pieces start at src_base[s] + seg_off[s]: either
+// segments of one receive buffer (after an NCCL all-to-all) or the senders' own partition buffers mapped
+// over NVLink peer memory -- then this kernel IS the exchange, the loads cross NVLink and no receive
+// buffer exists.  A merged bucket holds n_src times the instances the sender's
 // geometry aimed at, so the gather also SPLITS it by the next d2 remainder bits into 2^d2 sub-buckets
 // (two passes over the pieces, the second served by L2): count, then place with warp-aggregated
 // cursors.  Order inside a sub-bucket is arbitrary -- the counting kernels do not depend on it.
 // Writes the fine bucket table (sizes, offsets) for buckets (b << d2) | j.
 template <typename Elem, int NT>
-__global__ void __launch_bounds__(NT) k_gather_split(const Elem* __restrict__ recv, const unsigned long long* __restrict__ seg_off,
+__global__ void __launch_bounds__(NT) k_gather_split(const Elem* const* __restrict__ src_base, const unsigned long long* __restrict__ seg_off,
                                                      const unsigned long long* __restrict__ piece_off /* [n_src][nb+1] */,
                                                      const uint32_t* __restrict__ sizes_all,
                                                      const unsigned long long* __restrict__ bofs_coarse, uint32_t n_src, uint32_t nb,
                                                      uint32_t lo, uint32_t hi, int d2, int digit_pos, Elem* __restrict__ out,
                                                      unsigned long long* __restrict__ bsize_fine,
-                                                     unsigned long long* __restrict__ bofs_fine) {
+                                                     unsigned long long* __restrict__ bofs_fine,
+                                                     const uint32_t* __restrict__ sub_sizes /* [n_src][(hi-lo) << d2] or null */) {
   constexpr int U = 4;                 // elements per thread and step
   constexpr int MAXB = 32;             // 2^d2 <= 32
   __shared__ uint32_t hist[MAXB];
@@ -122,11 +159,19 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* __restrict__ re
   for (uint32_t b = lo + blockIdx.x; b < hi; b += gridDim.x) {
     if (threadIdx.x < MAXB) hist[threadIdx.x] = 0;
     __syncthreads();
-    // ---- pass 1: sub-digit histogram (per-warp ballots, one shared atomic per warp, bin and step)
-    if (d2 > 0) {
+    // ---- pass 1: sub-digit histogram -- from the senders' own counts when they came along (then the
+    // pieces cross NVLink once), else by reading the pieces (per-warp ballots)
+    if (d2 > 0 && sub_sizes) {
+      const size_t row = (size_t)(hi - lo) << d2;
+      for (uint32_t q = threadIdx.x; q < n_src * nbins; q += NT) {
+        const uint32_t s = q / nbins, j = q % nbins;
+        const uint32_t v = sub_sizes[(size_t)s * row + (((size_t)(b - lo)) << d2) + j];
+        if (v) atomicAdd(&hist[j], v);
+      }
+    } else if (d2 > 0) {
       for (uint32_t s = 0; s < n_src; s++) {
         const uint32_t n = sizes_all[(size_t)s * nb + b];
-        const Elem* src = recv + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
+        const Elem* src = src_base[s] + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
         for (uint32_t i0 = 0; i0 < n; i0 += NT * U) {
           uint32_t d[U];
 #pragma unroll
@@ -163,7 +208,7 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* __restrict__ re
     // ---- pass 2 (the pieces come from L2 now): place with warp-aggregated cursors
     for (uint32_t s = 0; s < n_src; s++) {
       const uint32_t n = sizes_all[(size_t)s * nb + b];
-      const Elem* src = recv + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
+      const Elem* src = src_base[s] + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
       for (uint32_t i0 = 0; i0 < n; i0 += NT * U) {   // uniform trip count: the ballots need whole warps
         Elem e[U];
         uint32_t d[U], pos[U];

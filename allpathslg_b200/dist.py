@@ -18,6 +18,8 @@ and sends 8 bytes per instance where the partition-first form sends 4.
 
 torch is used for device buffers, streams and the collectives only.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -74,23 +76,29 @@ def sharded_count(kc, rank, world, group=None, timings=None):
             raise
         failed = 1
     sizes = None
+    want_peer = world > 1 and os.environ.get("APGK_SHARD_EXCHANGE", "peer") == "peer"
+    handle = np.zeros(64, dtype=np.uint8)
     if not failed:
         sizes_ptr, nb, elems_ptr, eb, n_elems = kc.partition_info()
         sizes = _wrap(sizes_ptr, nb, "<i8", dev)
-    # one all-gather carries the bucket histogram and the "could not partition" flag
+        if want_peer:
+            handle = kc.partition_export()
+            d2, sub_ptr = kc.partition_subsizes(max(0, (world - 1).bit_length()))
+    # one all-gather carries the bucket histogram, the "could not partition" flag and the IPC handle
     nb_all = 1 << P
-    mine = torch.empty(nb_all + 1, dtype=torch.int64, device=dev)
+    mine = torch.empty(nb_all + 9, dtype=torch.int64, device=dev)
     mine[:nb_all] = sizes if sizes is not None else 0
     mine[nb_all] = failed
-    gathered = torch.empty((world, nb_all + 1), dtype=torch.int64, device=dev)
+    mine[nb_all + 1:] = torch.from_numpy(handle.view(np.int64).copy()).to(dev)
+    gathered = torch.empty((world, nb_all + 9), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(gathered, mine, group=group)
     all_sizes = gathered[:, :nb_all]
     bounds_t = _splitters_tensor(all_sizes.sum(0), world)
     cum = torch.zeros((world, nb_all + 1), dtype=torch.int64, device=dev)
     torch.cumsum(all_sizes, 1, out=cum[:, 1:])
-    # everything the host needs in one transfer: flags, largest piece, bounds, cumulative counts at the bounds
+    # everything the host needs in one transfer: flags, largest piece, bounds, cumulative counts at the bounds, handles
     small = torch.cat([gathered[:, nb_all].max().reshape(1), all_sizes.max().reshape(1), bounds_t,
-                       cum[:, bounds_t].reshape(-1)]).cpu().numpy()
+                       cum[:, bounds_t].reshape(-1), gathered[:, nb_all + 1:].reshape(-1)]).cpu().numpy()
     if int(small[0]):
         if timings is not None:
             timings["path"] = "hash"
@@ -98,39 +106,65 @@ def sharded_count(kc, rank, world, group=None, timings=None):
     if int(small[1]) >= 2 ** 31:
         raise RuntimeError("a bucket piece holds 2^31 or more k-mers")
     bounds = [int(x) for x in small[2: 3 + world]]
-    at_bounds = small[3 + world:].reshape(world, world + 1)
+    at_bounds = small[3 + world: 3 + world + world * (world + 1)].reshape(world, world + 1)
+    handles = small[3 + world + world * (world + 1):].reshape(world, 8)
     lo, hi = bounds[rank], bounds[rank + 1]
-    # per-destination send counts (my pieces) and per-source receive counts (their pieces of my range)
-    send_counts = (at_bounds[rank, 1:] - at_bounds[rank, :-1]).astype(np.int64)
-    recv_counts = (at_bounds[:, rank + 1] - at_bounds[:, rank]).astype(np.int64)
-    n_recv = int(recv_counts.sum())
-    words = 1 if eb == 4 else eb // 8
-    tstr, tdt = ("<i4", torch.int32) if eb == 4 else ("<i8", torch.int64)
-    send = _wrap(elems_ptr, max(n_elems, 1) * words, tstr, dev) if elems_ptr else torch.empty(1, dtype=tdt, device=dev)
-    need = max(n_recv, 1) * eb
-    buf = getattr(kc, "_recv_buf", None)
-    if buf is None or buf.numel() * 8 < need:
-        kc._recv_buf = None
-        del buf
-        torch.cuda.empty_cache()
-        buf = torch.empty(int(need * 1.02) // 8 + 1024, dtype=torch.int64, device=dev)
-        kc._recv_buf = buf
-    recv = buf.view(tdt)
     sizes_u32 = all_sizes.to(torch.int32).contiguous()
-    e1.record()
-    dist.all_to_all_single(recv[: n_recv * words], send[: n_elems * words],
-                           output_split_sizes=[int(c) * words for c in recv_counts],
-                           input_split_sizes=[int(c) * words for c in send_counts], group=group)
-    e2.record()
-    torch.cuda.current_stream().synchronize()
-    del send
-    seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
-    kc.count_pieces(recv.data_ptr(), world, sizes_u32.data_ptr(), seg_off, lo, hi)
-    e3.record()
+    # ---- exchange fused into the gather: map the peers' partition buffers (CUDA IPC over NVLink)
+    peer_ptrs = None
+    if want_peer:
+        peer_ptrs = _open_peers(kc, rank, world, handles)
+        ok = torch.tensor([1 if peer_ptrs is not None else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # every rank or none
+        if not int(ok.item()):
+            peer_ptrs = None
+    if peer_ptrs is not None:
+        e1.record()
+        e2.record()
+        torch.cuda.current_stream().synchronize()
+        n_recv = int((at_bounds[:, rank + 1] - at_bounds[:, rank]).sum())
+        # the senders' sub-bucket counts of my range (so that the pieces cross NVLink once)
+        sub = _wrap(sub_ptr, nb_all << d2, "<i4", dev)
+        sub_recv = torch.empty(world * ((hi - lo) << d2) + 1, dtype=torch.int32, device=dev)
+        dist.all_to_all_single(sub_recv[: world * ((hi - lo) << d2)], sub,
+                               output_split_sizes=[(hi - lo) << d2] * world,
+                               input_split_sizes=[(bounds[r + 1] - bounds[r]) << d2 for r in range(world)], group=group)
+        torch.cuda.current_stream().synchronize()
+        kc.count_pieces_peer(peer_ptrs, sizes_u32.data_ptr(), at_bounds[:, rank].astype(np.uint64), lo, hi,
+                             split_bits=d2, d_sub_sizes=sub_recv.data_ptr())
+        e3.record()
+    else:
+        # ---- NCCL all-to-all into a receive buffer, then gather
+        # per-destination send counts (my pieces) and per-source receive counts (their pieces of my range)
+        send_counts = (at_bounds[rank, 1:] - at_bounds[rank, :-1]).astype(np.int64)
+        recv_counts = (at_bounds[:, rank + 1] - at_bounds[:, rank]).astype(np.int64)
+        n_recv = int(recv_counts.sum())
+        words = 1 if eb == 4 else eb // 8
+        tstr, tdt = ("<i4", torch.int32) if eb == 4 else ("<i8", torch.int64)
+        send = _wrap(elems_ptr, max(n_elems, 1) * words, tstr, dev) if elems_ptr else torch.empty(1, dtype=tdt, device=dev)
+        need = max(n_recv, 1) * eb
+        buf = getattr(kc, "_recv_buf", None)
+        if buf is None or buf.numel() * 8 < need:
+            kc._recv_buf = None
+            del buf
+            torch.cuda.empty_cache()
+            buf = torch.empty(int(need * 1.02) // 8 + 1024, dtype=torch.int64, device=dev)
+            kc._recv_buf = buf
+        recv = buf.view(tdt)
+        e1.record()
+        dist.all_to_all_single(recv[: n_recv * words], send[: n_elems * words],
+                               output_split_sizes=[int(c) * words for c in recv_counts],
+                               input_split_sizes=[int(c) * words for c in send_counts], group=group)
+        e2.record()
+        torch.cuda.current_stream().synchronize()
+        del send
+        seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
+        kc.count_pieces(recv.data_ptr(), world, sizes_u32.data_ptr(), seg_off, lo, hi)
+        e3.record()
     out = _reduce_results(kc, dev, group)
     if timings is not None:
         torch.cuda.current_stream().synchronize()
-        timings["path"] = "partition-first"
+        timings["path"] = "partition-first" + ("/peer" if peer_ptrs is not None else "/nccl")
         timings["partition_ms"] = e0.elapsed_time(e1)
         timings["all_to_all_ms"] = e1.elapsed_time(e2)
         timings["count_ms"] = e2.elapsed_time(e3)
@@ -140,6 +174,34 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         timings["bucket_range"] = (int(lo), int(hi))
         timings["prefix_bits"] = int(P)
     return out
+
+
+def _open_peers(kc, rank, world, handles):
+    """Device pointers of every rank's partition buffer (None for this rank's own), mapping the peers'
+    IPC handles once and again only when a peer reallocated.  None if a handle cannot be mapped."""
+    from .kmers import ApgkError
+
+    cache = getattr(kc, "_peer_map", None)
+    if cache is None:
+        cache = kc._peer_map = {}
+    ptrs = []
+    for s in range(world):
+        if s == rank:
+            ptrs.append(None)
+            continue
+        key = handles[s].tobytes()
+        ent = cache.get(s)
+        if ent is None or ent[0] != key:
+            try:
+                if ent is not None:
+                    kc.peer_close(ent[1])
+                    del cache[s]
+                ptr = kc.peer_open(np.frombuffer(key, dtype=np.uint8))
+            except ApgkError:
+                return None
+            cache[s] = (key, ptr)
+        ptrs.append(cache[s][1])
+    return ptrs
 
 
 def _reduce_results(kc, dev, group):

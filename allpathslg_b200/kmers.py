@@ -214,6 +214,37 @@ class KmerCounter:
         self._ck(self._L.apgk_count_pieces(self._h, d_recv, n_src, d_sizes_all, so.ctypes.data, bucket_lo, bucket_hi,
                                            split_bits))
 
+    def partition_subsizes(self, split_bits):
+        """-> (effective split bits, device pointer of uint32[n_buckets << bits] sub-bucket sizes)"""
+        eff = C.c_int32()
+        p = C.c_void_p()
+        self._ck(self._L.apgk_partition_subsizes(self._h, split_bits, C.byref(eff), C.byref(p)))
+        return eff.value, p.value
+
+    def count_pieces_peer(self, src_ptrs, d_sizes_all, src_off, bucket_lo, bucket_hi, split_bits=None, d_sub_sizes=None):
+        """src_ptrs: one device pointer per source rank (0 / None = this context's own partition buffer)"""
+        n_src = len(src_ptrs)
+        bases = (C.c_void_p * n_src)(*[C.c_void_p(int(p) if p else 0) for p in src_ptrs])
+        so = np.ascontiguousarray(src_off, dtype=np.uint64)
+        if split_bits is None:
+            split_bits = max(0, (n_src - 1).bit_length())
+        self._ck(self._L.apgk_count_pieces_peer(self._h, bases, n_src, d_sizes_all, so.ctypes.data, bucket_lo, bucket_hi,
+                                                split_bits, d_sub_sizes))
+
+    def partition_export(self):
+        h = np.zeros(64, dtype=np.uint8)
+        self._ck(self._L.apgk_partition_export(self._h, h.ctypes.data))
+        return h
+
+    def peer_open(self, handle):
+        h = np.ascontiguousarray(handle, dtype=np.uint8)
+        p = C.c_void_p()
+        self._ck(self._L.apgk_peer_open(self._h, h.ctypes.data, C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr):
+        self._ck(self._L.apgk_peer_close(self._h, ptr))
+
     def spectrum_device(self):
         p = C.c_void_p()
         n = C.c_uint64()

@@ -171,6 +171,27 @@ int apgk_partition_info(apgk_ctx* ctx, const uint64_t** d_bucket_sizes, uint64_t
 int apgk_count_pieces(apgk_ctx* ctx, const void* d_recv, uint32_t n_src, const uint32_t* d_sizes_all,
                       const uint64_t* seg_off, uint64_t bucket_lo, uint64_t bucket_hi, int32_t split_bits);
 
+/* Same, with the exchange fused into the gather: d_src_base[s] (HOST array of DEVICE pointers) is
+ * source s's partition buffer -- its own for s == this rank (NULL selects it), a peer's buffer mapped
+ * with apgk_peer_open otherwise -- and src_off[s] the element offset of bucket_lo's piece in it.  The
+ * gather kernel then reads the pieces straight over NVLink peer memory: no all-to-all, no receive
+ * buffer, the transfer overlaps the splitting.  The peers must not touch their partition buffers
+ * until every rank has returned from this call (the spectrum all-reduce that follows is that barrier).
+ * d_sub_sizes (DEVICE, uint32[n_src][(bucket_hi - bucket_lo) << bits], may be NULL) are the senders'
+ * own sub-bucket counts (apgk_partition_subsizes) for this range: with them the pieces cross NVLink
+ * once instead of twice. */
+int apgk_count_pieces_peer(apgk_ctx* ctx, const void* const* d_src_base, uint32_t n_src, const uint32_t* d_sizes_all,
+                           const uint64_t* src_off, uint64_t bucket_lo, uint64_t bucket_hi, int32_t split_bits,
+                           const uint32_t* d_sub_sizes);
+/* Sender side of that: sizes of the 2^bits sub-buckets of every bucket of this context's partition
+ * (DEVICE, uint32[n_buckets << bits], library-owned); *effective_bits is the clamped split_bits. */
+int apgk_partition_subsizes(apgk_ctx* ctx, int32_t split_bits, int32_t* effective_bits, const uint32_t** d_sub_sizes);
+/* CUDA IPC plumbing for the peer form: export this context's partition buffer (64-byte handle, valid
+ * until the buffer is reallocated by a larger run), map a peer's handle, unmap it. */
+int apgk_partition_export(apgk_ctx* ctx, uint8_t handle_out[64]);
+int apgk_peer_open(apgk_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+int apgk_peer_close(apgk_ctx* ctx, void* d_ptr);
+
 /* ---- instrumentation */
 #define APGK_N_STAGES 12
 /* Device milliseconds of the last finish, by stage; names via apgk_stage_name(i). */

@@ -400,8 +400,9 @@ def test_owner_partition_and_key_ingest(oracle, K, world):
     kc.close()
 
 
+@pytest.mark.parametrize("exchange", ["recv", "peer"])
 @pytest.mark.parametrize("K,world,n_reads", [(25, 2, 30_000), (25, 5, 30_000), (20, 3, 20_000), (48, 3, 12_000), (96, 2, 8_000)])
-def test_partition_first_shards_emulated_ranks(oracle, K, world, n_reads):
+def test_partition_first_shards_emulated_ranks(oracle, K, world, n_reads, exchange):
     """The partition-first multi-GPU path emulated on one GPU: every "rank" partitions its share of the
     reads (apgk_partition), the exchange of bucket ranges is done here with host copies exactly as
     dist.sharded_count does it with all_to_all, every rank counts its range (apgk_count_pieces).
@@ -429,10 +430,13 @@ def test_partition_first_shards_emulated_ranks(oracle, K, world, n_reads):
             kc.add_reads_uniform(pr, n, L)
         kcs.append(kc)
     P = kcs[0].choose_prefix_bits(max(kc.window_upper() for kc in kcs))
-    sizes, elems, eb = [], [], None
+    sizes, elems, eb, eptrs, subs = [], [], None, [], []
     for kc in kcs:
         kc.partition(P)
         sp_, nb, ep, eb_, ne = kc.partition_info()
+        eptrs.append(ep)
+        d2, subp = kc.partition_subsizes(max(0, (world - 1).bit_length()))
+        subs.append(torch.as_tensor(_CudaView(subp, nb << d2, "<i4"), device="cuda").clone())
         eb = eb_ if eb is None else eb
         assert eb_ == eb and nb == 1 << P
         sz = torch.empty(nb, dtype=torch.int64, device="cuda")
@@ -459,7 +463,17 @@ def test_partition_first_shards_emulated_ranks(oracle, K, world, n_reads):
         parts = [elems[s][cum[s, lo] * words: cum[s, hi] * words] for s in range(world)]
         seg_off = np.concatenate([[0], np.cumsum([len(x) // words for x in parts])[:-1]]).astype(np.uint64)
         recv = torch.from_numpy(np.concatenate(parts) if sum(len(x) for x in parts) else np.zeros(1, parts[0].dtype)).cuda()
-        kcs[r].count_pieces(recv.data_ptr(), world, d_sizes.data_ptr(), seg_off, lo, hi)
+        if exchange == "recv":
+            kcs[r].count_pieces(recv.data_ptr(), world, d_sizes.data_ptr(), seg_off, lo, hi)
+        else:  # the gather reads every source's own partition buffer (here: the other contexts' buffers)
+            ptrs = [None if s == r else (eptrs[s] or 0) for s in range(world)]
+            if any(p == 0 for p in ptrs if p is not None):
+                ptrs = [None if s == r else (eptrs[s] or recv.data_ptr()) for s in range(world)]  # empty source: any valid pointer
+            sub_recv = torch.cat([subs[s][lo << d2: hi << d2] for s in range(world)] + [torch.zeros(1, dtype=torch.int32, device="cuda")])
+            for s in range(world):  # the senders' sub-bucket counts add up to their bucket sizes
+                assert int(subs[s].sum()) == int(all_sizes[s].sum())
+            kcs[r].count_pieces_peer(ptrs, d_sizes.data_ptr(), cum[:, lo].astype(np.uint64), lo, hi, split_bits=d2,
+                                     d_sub_sizes=sub_recv.data_ptr() if (r % 2 == 0) else None)  # with and without
         gk, gc = kcs[r].counts()
         got_k.append(gk); got_c.append(gc)
         per_rank.append(kcs[r].totals()[0])
