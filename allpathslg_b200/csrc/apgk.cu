@@ -916,7 +916,7 @@ int count_pieces_typed(apgk_ctx* c, const void* const* bases_host, bool peer, ui
   CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)nbf * 8, c->stream));
   CU(cudaMemsetAsync(c->bofs.p, 0, ((size_t)nbf + 1) * 8, c->stream));
   if (Nr && hi > lo) {
-    const uint32_t grid = std::min<uint32_t>(hi - lo, (uint32_t)c->n_sm * 8);
+    const uint32_t grid = std::min<uint32_t>((hi - lo + 7) / 8, (uint32_t)c->n_sm * 8);  // one warp per bucket
     // digit = the d2 bits just below the prefix: remainder bits [REM - d2, REM)
     k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(
         (const ElemB* const*)c->piece_ptrs.p, c->bstart64.as<unsigned long long>(), c->piece_off.as<unsigned long long>(), d_sizes_all,

@@ -150,93 +150,86 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* const* __restri
                                                      unsigned long long* __restrict__ bsize_fine,
                                                      unsigned long long* __restrict__ bofs_fine,
                                                      const uint32_t* __restrict__ sub_sizes /* [n_src][(hi-lo) << d2] or null */) {
-  constexpr int U = 4;                 // elements per thread and step
-  constexpr int MAXB = 32;             // 2^d2 <= 32
-  __shared__ uint32_t hist[MAXB];
-  __shared__ uint32_t cursor[MAXB];    // next free slot of each sub-bucket, relative to the bucket start
+  // One WARP per owned bucket: lane j keeps the count and then the write cursor of sub-bucket j in a
+  // register, positions come from ballots -- no shared memory, no barriers, no atomics, and the eight
+  // warps of a CTA keep eight buckets' loads (local HBM or NVLink) in flight.
+  constexpr int U = 4;                 // elements per lane and step
   const uint32_t nbins = 1u << d2, mask = nbins - 1u;
-  const int lane = threadIdx.x & 31;
-  for (uint32_t b = lo + blockIdx.x; b < hi; b += gridDim.x) {
-    if (threadIdx.x < MAXB) hist[threadIdx.x] = 0;
-    __syncthreads();
-    // ---- pass 1: sub-digit histogram -- from the senders' own counts when they came along (then the
-    // pieces cross NVLink once), else by reading the pieces (per-warp ballots)
-    if (d2 > 0 && sub_sizes) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * NT + threadIdx.x) >> 5, nwarps = (gridDim.x * NT) >> 5;
+  for (uint32_t b = lo + warp; b < hi; b += nwarps) {
+    // ---- sub-bucket sizes: from the senders' own counts when they came along (then the pieces are
+    // read once), else by a first pass over the pieces
+    uint32_t mine = 0;                 // lane j: size of sub-bucket j
+    if (d2 == 0) {
+      for (uint32_t s = 0; s < n_src; s++) mine += sizes_all[(size_t)s * nb + b];  // only lane 0's copy is used
+    } else if (sub_sizes) {
       const size_t row = (size_t)(hi - lo) << d2;
-      for (uint32_t q = threadIdx.x; q < n_src * nbins; q += NT) {
-        const uint32_t s = q / nbins, j = q % nbins;
-        const uint32_t v = sub_sizes[(size_t)s * row + (((size_t)(b - lo)) << d2) + j];
-        if (v) atomicAdd(&hist[j], v);
-      }
-    } else if (d2 > 0) {
+      if (lane < nbins)
+        for (uint32_t s = 0; s < n_src; s++) mine += sub_sizes[(size_t)s * row + (((size_t)(b - lo)) << d2) + lane];
+    } else {
       for (uint32_t s = 0; s < n_src; s++) {
         const uint32_t n = sizes_all[(size_t)s * nb + b];
         const Elem* src = src_base[s] + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
-        for (uint32_t i0 = 0; i0 < n; i0 += NT * U) {
+        for (uint32_t i0 = 0; i0 < n; i0 += 32 * U) {
           uint32_t d[U];
 #pragma unroll
           for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + u * NT + threadIdx.x;
+            const uint32_t i = i0 + u * 32 + lane;
             d[u] = i < n ? split_digit(src[i], digit_pos, mask) : 0xFFFFFFFFu;
           }
           for (uint32_t j = 0; j < nbins; j++) {
             uint32_t cnt = 0;
 #pragma unroll
             for (int u = 0; u < U; u++) cnt += __popc(__ballot_sync(0xffffffffu, d[u] == j));
-            if (lane == 0 && cnt) atomicAdd(&hist[j], cnt);
+            if (lane == j) mine += cnt;
           }
         }
       }
-    } else if (threadIdx.x == 0) {
-      uint32_t t = 0;
-      for (uint32_t s = 0; s < n_src; s++) t += sizes_all[(size_t)s * nb + b];
-      hist[0] = t;
     }
-    __syncthreads();
+    if (lane >= nbins) mine = 0;
+    // exclusive scan over the lanes -> start of every sub-bucket, relative to the bucket
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += v;
+    }
+    uint32_t cur = incl - mine;        // lane j: next free slot of sub-bucket j
     const unsigned long long base_b = bofs_coarse[b];
-    if (threadIdx.x == 0) {
-      uint32_t run = 0;
-      for (uint32_t j = 0; j < nbins; j++) {
-        const size_t f = ((size_t)b << d2) | j;
-        bsize_fine[f] = hist[j];
-        bofs_fine[f] = base_b + run;
-        cursor[j] = run;
-        run += hist[j];
-      }
+    if (lane < nbins) {
+      const size_t f = ((size_t)b << d2) | lane;
+      bsize_fine[f] = mine;
+      bofs_fine[f] = base_b + cur;
     }
-    __syncthreads();
-    // ---- pass 2 (the pieces come from L2 now): place with warp-aggregated cursors
+    // ---- place
     for (uint32_t s = 0; s < n_src; s++) {
       const uint32_t n = sizes_all[(size_t)s * nb + b];
       const Elem* src = src_base[s] + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
-      for (uint32_t i0 = 0; i0 < n; i0 += NT * U) {   // uniform trip count: the ballots need whole warps
+      for (uint32_t i0 = 0; i0 < n; i0 += 32 * U) {
         Elem e[U];
         uint32_t d[U], pos[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const uint32_t i = i0 + u * NT + threadIdx.x;
+          const uint32_t i = i0 + u * 32 + lane;
           d[u] = 0xFFFFFFFFu; pos[u] = 0; e[u] = Elem{};
           if (i < n) { e[u] = src[i]; d[u] = split_digit(e[u], digit_pos, mask); }
         }
         for (uint32_t j = 0; j < nbins; j++) {
-          uint32_t m[U], tot = 0;
-#pragma unroll
-          for (int u = 0; u < U; u++) { m[u] = __ballot_sync(0xffffffffu, d[u] == j); tot += __popc(m[u]); }
-          uint32_t base = 0;
-          if (lane == 0 && tot) base = atomicAdd(&cursor[j], tot);
-          base = __shfl_sync(0xffffffffu, base, 0);
+          uint32_t base = __shfl_sync(0xffffffffu, cur, j), tot = 0;
 #pragma unroll
           for (int u = 0; u < U; u++) {
-            if (d[u] == j) pos[u] = base + __popc(m[u] & ((1u << lane) - 1u));
-            base += __popc(m[u]);
+            const uint32_t m = __ballot_sync(0xffffffffu, d[u] == j);
+            if (d[u] == j) pos[u] = base + tot + __popc(m & ((1u << lane) - 1u));
+            tot += __popc(m);
           }
+          if (lane == j) cur += tot;
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
           if (d[u] != 0xFFFFFFFFu) out[base_b + pos[u]] = split_strip(e[u], digit_pos);
       }
     }
-    __syncthreads();
   }
 }
 

@@ -19,6 +19,7 @@ and sends 8 bytes per instance where the partition-first form sends 4.
 torch is used for device buffers, streams and the collectives only.
 """
 import os
+import time
 
 import numpy as np
 import torch
@@ -63,11 +64,20 @@ def sharded_count(kc, rank, world, group=None, timings=None):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     e0, e1, e2, e3 = ev(), ev(), ev(), ev()
     e0.record()
+    wall = {}
+    t_last = [time.perf_counter()]
+
+    def lap(name):  # host wall clock of the synchronous phases (diagnostics in `timings`)
+        now = time.perf_counter()
+        wall[name] = wall.get(name, 0.0) + 1e3 * (now - t_last[0])
+        t_last[0] = now
+
     # ---- same geometry on every rank
     up = torch.tensor([kc.window_upper()], dtype=torch.int64, device=dev)
     dist.all_reduce(up, op=dist.ReduceOp.MAX, group=group)
     P = kc.choose_prefix_bits(int(up.item()))
     # ---- local partition (levels 0 + 1)
+    lap("w_geometry")
     failed = 0
     try:
         kc.partition(P)
@@ -75,6 +85,7 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         if e.code != -5:  # APGK_E_RANGE: more than one k-mer-space round needed here
             raise
         failed = 1
+    lap("w_partition")
     sizes = None
     want_peer = world > 1 and os.environ.get("APGK_SHARD_EXCHANGE", "peer") == "peer"
     handle = np.zeros(64, dtype=np.uint8)
@@ -84,6 +95,7 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         if want_peer:
             handle = kc.partition_export()
             d2, sub_ptr = kc.partition_subsizes(max(0, (world - 1).bit_length()))
+    lap("w_subsizes")
     # one all-gather carries the bucket histogram, the "could not partition" flag and the IPC handle
     nb_all = 1 << P
     mine = torch.empty(nb_all + 9, dtype=torch.int64, device=dev)
@@ -99,6 +111,7 @@ def sharded_count(kc, rank, world, group=None, timings=None):
     # everything the host needs in one transfer: flags, largest piece, bounds, cumulative counts at the bounds, handles
     small = torch.cat([gathered[:, nb_all].max().reshape(1), all_sizes.max().reshape(1), bounds_t,
                        cum[:, bounds_t].reshape(-1), gathered[:, nb_all + 1:].reshape(-1)]).cpu().numpy()
+    lap("w_plan")
     if int(small[0]):
         if timings is not None:
             timings["path"] = "hash"
@@ -130,8 +143,10 @@ def sharded_count(kc, rank, world, group=None, timings=None):
                                output_split_sizes=[(hi - lo) << d2] * world,
                                input_split_sizes=[(bounds[r + 1] - bounds[r]) << d2 for r in range(world)], group=group)
         torch.cuda.current_stream().synchronize()
+        lap("w_peer_setup")
         kc.count_pieces_peer(peer_ptrs, sizes_u32.data_ptr(), at_bounds[:, rank].astype(np.uint64), lo, hi,
                              split_bits=d2, d_sub_sizes=sub_recv.data_ptr())
+        lap("w_count")
         e3.record()
     else:
         # ---- NCCL all-to-all into a receive buffer, then gather
@@ -159,11 +174,17 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         torch.cuda.current_stream().synchronize()
         del send
         seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
+        lap("w_all_to_all")
         kc.count_pieces(recv.data_ptr(), world, sizes_u32.data_ptr(), seg_off, lo, hi)
+        lap("w_count")
         e3.record()
+    gather_ms = kc.stage_ms().get("owner", 0.0)
     out = _reduce_results(kc, dev, group)
+    lap("w_reduce")
     if timings is not None:
         torch.cuda.current_stream().synchronize()
+        timings.update(wall)
+        timings["gather_split_ms"] = gather_ms
         timings["path"] = "partition-first" + ("/peer" if peer_ptrs is not None else "/nccl")
         timings["partition_ms"] = e0.elapsed_time(e1)
         timings["all_to_all_ms"] = e1.elapsed_time(e2)
