@@ -202,18 +202,41 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* const* __restri
       bsize_fine[f] = mine;
       bofs_fine[f] = base_b + cur;
     }
-    // ---- place
+    // ---- place.  32-bit elements are fetched 16 bytes per lane (512 bytes per warp instruction: NVLink
+    // and HBM both like long requests); a scalar step first brings the piece to 16-byte alignment.
     for (uint32_t s = 0; s < n_src; s++) {
       const uint32_t n = sizes_all[(size_t)s * nb + b];
       const Elem* src = src_base[s] + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
-      for (uint32_t i0 = 0; i0 < n; i0 += 32 * U) {
+      uint32_t head = 0;
+      if constexpr (sizeof(Elem) == 4) {
+        head = (uint32_t)((16u - ((uint32_t)(uintptr_t)src & 15u)) & 15u) >> 2;
+        if (head > n) head = n;
+      }
+      for (uint32_t i0 = 0; i0 < n; i0 += (i0 < head ? head : 32 * U)) {
         Elem e[U];
         uint32_t d[U], pos[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const uint32_t i = i0 + u * 32 + lane;
-          d[u] = 0xFFFFFFFFu; pos[u] = 0; e[u] = Elem{};
-          if (i < n) { e[u] = src[i]; d[u] = split_digit(e[u], digit_pos, mask); }
+        for (int u = 0; u < U; u++) { d[u] = 0xFFFFFFFFu; pos[u] = 0; e[u] = Elem{}; }
+        if (sizeof(Elem) == 4 && i0 < head) {            // alignment step: lanes 0 .. head-1, one element each
+          if (lane < head) { e[0] = src[lane]; d[0] = split_digit(e[0], digit_pos, mask); }
+        } else if constexpr (sizeof(Elem) == 4) {        // lane takes elements i0 + 4*lane .. +3
+          const uint32_t i = i0 + 4 * lane;
+          if (i + 3 < n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < U; u++) { memcpy(&e[u], &w[u], 4); d[u] = split_digit(e[u], digit_pos, mask); }
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+              if (i + u < n) { e[u] = src[i + u]; d[u] = split_digit(e[u], digit_pos, mask); }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * 32 + lane;
+            if (i < n) { e[u] = src[i]; d[u] = split_digit(e[u], digit_pos, mask); }
+          }
         }
         for (uint32_t j = 0; j < nbins; j++) {
           uint32_t base = __shfl_sync(0xffffffffu, cur, j), tot = 0;
