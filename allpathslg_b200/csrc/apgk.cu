@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -87,7 +88,8 @@ struct apgk_ctx {
   bool part_ready = false;
   uint64_t part_n = 0;       // elements in B, grouped by the nb1 buckets (sizes in segtot)
   DevBuf piece_off, piece_tmp, piece_ptrs, C2, sub_sizes;
-  void* count_src = nullptr;  // elements count_buckets reads (B, or C2 on the peer-memory path)
+  void* count_src = nullptr;
+  uint32_t bucket_lo = 0, bucket_hi = 0;  // shard's bucket range for count_buckets (0,0 = all)  // elements count_buckets reads (B, or C2 on the peer-memory path)
   // ---- owner partition state
   uint32_t owner_ranks = 0;
   uint32_t owner_tiles = 0;
@@ -133,8 +135,20 @@ void stage_flush(apgk_ctx* c, int s) {
     c->stage_ms[s] += ms;
   c->ev_used[s] = false;
 }
-void stage_begin(apgk_ctx* c, int s) { stage_flush(c, s); cudaEventRecord(c->ev[s][0], c->stream); c->ev_used[s] = true; }
-void stage_end(apgk_ctx* c, int s) { cudaEventRecord(c->ev[s][1], c->stream); }
+static const bool kTrace = getenv("APGK_TRACE") != nullptr;  // host wall clock at every stage boundary, to stderr
+static double trace_now() {
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+void stage_begin(apgk_ctx* c, int s) {
+  stage_flush(c, s);
+  if (kTrace) fprintf(stderr, "[apgk %.2f] begin %s\n", trace_now(), kStageNames[s]);
+  cudaEventRecord(c->ev[s][0], c->stream); c->ev_used[s] = true;
+}
+void stage_end(apgk_ctx* c, int s) {
+  cudaEventRecord(c->ev[s][1], c->stream);
+  if (kTrace) fprintf(stderr, "[apgk %.2f] end   %s\n", trace_now(), kStageNames[s]);
+}
 
 int words_for(int K) { return (2 * K + 63) / 64; }
 
@@ -593,7 +607,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
     stage_end(c, ST_SCATTER1);
 
     if (mode == RUN_PARTITION) { c->part_n = Nr; return APGK_OK; }
-    c->count_src = c->B.p;
+    c->count_src = c->B.p; c->bucket_lo = c->bucket_hi = 0;
     { int rc = count_buckets<W, ElemB>(c, Nr, N, n_prev); if (rc) return rc; }
   }
   c->n_distinct = n_prev;
@@ -640,7 +654,8 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
     BucketTable bt;
     bt.bofs = c->bofs.as<unsigned long long>();
     bt.bsize = c->segtot.as<unsigned long long>();
-    bt.nb = c->nb1; bt.local_max = (uint32_t)local_max;
+    bt.nb = c->bucket_hi ? c->bucket_hi : c->nb1; bt.local_max = (uint32_t)local_max; bt.b0 = c->bucket_hi ? c->bucket_lo : 0;
+    if (c->bucket_hi) CU(cudaMemsetAsync(c->nd.p, 0, ((size_t)c->nb1 + 1) * 4, c->stream));  // buckets outside the shard: no records
     CU(c->deferred.ensure(((size_t)c->nb1 + 1) * 4));
     CU(cudaMemsetAsync(c->deferred.p, 0, 4, c->stream));
     stage_begin(c, ST_LOCAL);
@@ -936,6 +951,7 @@ int count_pieces_typed(apgk_ctx* c, const void* const* bases_host, bool peer, ui
   CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
   CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)nbf + 1) * 8, c->stream));
   c->count_src = dst.p;
+  c->bucket_lo = lo << d2; c->bucket_hi = hi << d2;
   if (Nr) { int rc = count_buckets<W, ElemB>(c, Nr, Nr, n_prev); if (rc) return rc; }
   c->n_distinct = n_prev;
   c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;

@@ -230,8 +230,9 @@ __device__ uint32_t local_bucket(LocalSmem<Elem>& sm, const Elem* __restrict__ s
 struct BucketTable {
   const unsigned long long* bofs;   // [nb] absolute element offset of each bucket
   const unsigned long long* bsize;  // [nb]
-  uint32_t nb;
+  uint32_t nb;                      // buckets [b0, nb) hold data (a shard owns a sub-range of the table)
   uint32_t local_max;
+  uint32_t b0 = 0;
 };
 
 template <typename Elem>
@@ -255,9 +256,9 @@ __global__ void __launch_bounds__(LOCAL_NT) k_local(const Elem* __restrict__ src
   sm.carve(smem_raw, (int)bt.local_max);
   for (int i = threadIdx.x; i < SPEC_SMEM; i += LOCAL_NT) sm.spec[i] = 0;
   __syncthreads();
-  const uint32_t n_iter = list ? (list[0] < list_cap ? list[0] : list_cap) : bt.nb;
+  const uint32_t n_iter = list ? (list[0] < list_cap ? list[0] : list_cap) : bt.nb - bt.b0;
   for (uint32_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    const uint32_t b = list ? list[1 + it] : it;
+    const uint32_t b = list ? list[1 + it] : bt.b0 + it;
     const unsigned long long n = bt.bsize[b];
     if (n == 0) {
       if (threadIdx.x == 0) nd_out[b] = 0;

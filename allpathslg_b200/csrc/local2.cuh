@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(L2_NT) k_local2(const Elem* __restrict__ src, 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < SPEC_SMEM; i += L2_NT) sm.spec[i] = 0;
   __syncthreads();
-  for (uint32_t b = blockIdx.x; b < bt.nb; b += gridDim.x) {
+  for (uint32_t b = bt.b0 + blockIdx.x; b < bt.nb; b += gridDim.x) {
     const unsigned long long n64 = bt.bsize[b];
     if (n64 == 0) {
       if (tid == 0) nd_out[b] = 0;

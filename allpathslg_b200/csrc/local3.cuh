@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(NT, 1536 / NT) k_local3(const uint32_t* __rest
   // the current bucket is processed: a CTA otherwise sits through two dependent DRAM latencies per
   // bucket (bsize/bofs, then the keys) and three CTAs per SM do not cover them.
   unsigned long long n_nx = 0, o_nx = 0;
-  if (blockIdx.x < bt.nb) { n_nx = bt.bsize[blockIdx.x]; o_nx = bt.bofs[blockIdx.x]; }
-  for (uint32_t b = blockIdx.x; b < bt.nb; b += gridDim.x) {
+  if (bt.b0 + blockIdx.x < bt.nb) { n_nx = bt.bsize[bt.b0 + blockIdx.x]; o_nx = bt.bofs[bt.b0 + blockIdx.x]; }
+  for (uint32_t b = bt.b0 + blockIdx.x; b < bt.nb; b += gridDim.x) {
     const unsigned long long n64 = n_nx;
     const unsigned long long o = o_nx;
     {
