@@ -159,9 +159,10 @@ template <int W> struct Geo;
 #ifndef APGK_NT
 #define APGK_NT 1024
 #endif
-template <> struct Geo<1> { static constexpr int NT0 = APGK_NT; static constexpr int NT1 = APGK_NT; static constexpr uint32_t TILE1 = APGK_NT * 16; static constexpr int LM_KEY = 4096; };
-template <> struct Geo<2> { static constexpr int NT0 = 512; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 8;  static constexpr int LM_KEY = 2048; };
-template <> struct Geo<3> { static constexpr int NT0 = 256; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 5;  static constexpr int LM_KEY = 2048; };
+// NTS / NPOS: threads and window starts per thread of the level-0 SCATTER (NTS * NPOS == NT0 * 16: same tiles as the histogram)
+template <> struct Geo<1> { static constexpr int NTS = APGK_NT; static constexpr int NPOS = 16; static constexpr int NT0 = APGK_NT; static constexpr int NT1 = APGK_NT; static constexpr uint32_t TILE1 = APGK_NT * 16; static constexpr int LM_KEY = 4096; };
+template <> struct Geo<2> { static constexpr int NTS = 1024; static constexpr int NPOS = 8; static constexpr int NT0 = 512; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 8;  static constexpr int LM_KEY = 2048; };
+template <> struct Geo<3> { static constexpr int NTS = 1024; static constexpr int NPOS = 4; static constexpr int NT0 = 256; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 5;  static constexpr int LM_KEY = 2048; };
 constexpr int LM_U32 = 5120;
 constexpr int L3_NT = 512;
 constexpr int COL_NT = 1024;
@@ -568,12 +569,12 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
       } else {
         auto launch = [&](auto kern) -> int {
           { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-          kern<<<hp0.lp.n_chunks, Geo<W>::NT0, sm, c->stream>>>(read_store(c), dg0, hp0.lp, c->chunksum0.as<uint32_t>(),
+          kern<<<hp0.lp.n_chunks, Geo<W>::NTS, sm, c->stream>>>(read_store(c), dg0, hp0.lp, c->chunksum0.as<uint32_t>(),
                                                                 c->bstart64.as<uint64_t>(), c->A.as<Key<W>>());
           return APGK_OK;
         };
-        int rc = filter ? launch(k_scatter_reads<W, Geo<W>::NT0, DIGIT_BITS, true>)
-                        : launch(k_scatter_reads<W, Geo<W>::NT0, DIGIT_BITS, false>);
+        int rc = filter ? launch(k_scatter_reads<W, Geo<W>::NTS, DIGIT_BITS, true, Geo<W>::NPOS>)
+                        : launch(k_scatter_reads<W, Geo<W>::NTS, DIGIT_BITS, false, Geo<W>::NPOS>);
         if (rc) return rc;
       }
       LAUNCHED();
@@ -1025,10 +1026,10 @@ int owner_scatter_impl(apgk_ctx* c, uint64_t* d_out) {
   for (uint32_t r = 0; r < n_ranks; r++) bstart[r + 1] = bstart[r] + c->owner_counts[r];
   CU(c->bstart64.ensure(((size_t)n_ranks + 1) * 8));
   CU(cudaMemcpyAsync(c->bstart64.p, bstart.data(), ((size_t)n_ranks + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  auto kern = k_scatter_reads<W, Geo<W>::NT0, DIGIT_OWNER, false>;
+  auto kern = k_scatter_reads<W, Geo<W>::NTS, DIGIT_OWNER, false, Geo<W>::NPOS>;
   const size_t sm = scatter_smem_bytes<Key<W>>((uint32_t)Geo<W>::NT0 * POS_PER_THREAD, (int)n_ranks);
   { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-  kern<<<c->owner_plan.lp.n_chunks, Geo<W>::NT0, sm, c->stream>>>(read_store(c), dg, c->owner_plan.lp,
+  kern<<<c->owner_plan.lp.n_chunks, Geo<W>::NTS, sm, c->stream>>>(read_store(c), dg, c->owner_plan.lp,
                                                                   c->chunksum.as<uint32_t>(), c->bstart64.as<uint64_t>(),
                                                                   (Key<W>*)d_out);
   LAUNCHED();

@@ -41,10 +41,29 @@ APGK_HD void load_window16(const uint32_t* __restrict__ bases32, uint64_t p, int
   win.v0 = funnel_r(bases32[vi], bases32[vi + 1], ks);
 }
 
-// Calls f(j, canonical, canonical_is_reverse) for j = 0..15 (window start p+j).
+// Same for ANY window start p (not only multiples of 16): the words are funnel-shifted so that base p
+// sits at bit 0, after which extractN below runs unchanged.  Used when a thread owns fewer than 16
+// window starts (multi-word k-mers: 16 keys per thread do not fit the register file).
+// bases32 must be readable (zero padded) for 2W+4 words past the last base.
+template <int W>
+APGK_HD void load_window_at(const uint32_t* __restrict__ bases32, uint64_t p, int K, Window16<W>& win) {
+  const uint64_t wi = p >> 4;
+  const uint32_t sh = 2u * (uint32_t)(p & 15);
+  uint32_t raw[2 * W + 2];
+#pragma unroll
+  for (int m = 0; m < 2 * W + 2; m++) raw[m] = bases32[wi + m];
+#pragma unroll
+  for (int m = 0; m < 2 * W + 1; m++) win.w[m] = funnel_r(raw[m], raw[m + 1], sh);
+  const uint64_t q = p + (uint64_t)K;
+  const uint64_t vi = q >> 4;
+  const uint32_t ks = 2u * (uint32_t)(q & 15);
+  win.v0 = funnel_r(bases32[vi], bases32[vi + 1], ks);
+}
+
+// Calls f(j, canonical, canonical_is_reverse) for j = 0..NPOS-1 (window start p+j).
 // Validity of each window is the caller's business (see window_valid_mask16).
-template <int W, typename F>
-APGK_HD void extract16(const Window16<W>& win, int K, F&& f) {
+template <int W, int NPOS, typename F>
+APGK_HD void extractN(const Window16<W>& win, int K, F&& f) {
   const int topbits = 2 * K - 64 * (W - 1);
   const uint64_t topmask = lowmask64(topbits);
   // ---- forward k-mer of window 0: reverse the 2-bit groups of the LE window
@@ -65,7 +84,7 @@ APGK_HD void extract16(const Window16<W>& win, int K, F&& f) {
     }
   }
 #pragma unroll
-  for (int j = 0; j < POS_PER_THREAD; j++) {
+  for (int j = 0; j < NPOS; j++) {
     // ---- reverse complement of window j straight from the stream
     Key<W> rc;
 #pragma unroll
@@ -81,7 +100,7 @@ APGK_HD void extract16(const Window16<W>& win, int K, F&& f) {
     for (int i = 0; i < W; i++) c.w[i] = use_rc ? rc.w[i] : fw.w[i];
     f(j, c, use_rc);
     // ---- roll the forward k-mer to window j+1
-    if (j + 1 < POS_PER_THREAD) {
+    if (j + 1 < NPOS) {
       const uint64_t b = (win.v0 >> (2 * j)) & 3u;
 #pragma unroll
       for (int i = 0; i < W - 1; i++) fw.w[i] = (fw.w[i] << 2) | (fw.w[i + 1] >> 62);
@@ -90,6 +109,9 @@ APGK_HD void extract16(const Window16<W>& win, int K, F&& f) {
     }
   }
 }
+
+template <int W, typename F>
+APGK_HD void extract16(const Window16<W>& win, int K, F&& f) { extractN<W, POS_PER_THREAD>(win, K, static_cast<F&&>(f)); }
 
 // Level-0 digits without building the k-mers.  The top D bits of canonical = min(fw, rc) are
 // min(top D bits of fw, top D bits of rc): if the tops differ they decide the comparison, if they are

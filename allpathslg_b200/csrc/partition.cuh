@@ -432,34 +432,38 @@ __device__ __forceinline__ uint32_t tile_scan(int bins, unsigned long long* G, u
 // Software-pipelined over tiles like k_scatter_keys below: the extraction and ranking of tile t+1
 // (ALU + shared atomics) is interleaved, position by position, with the write-out of tile t
 // (LDS -> LDS -> STG), so the one resident CTA per SM overlaps its compute with its stores.
-template <int W, int NT, int MODE, bool FILTER>
+// NPOS window starts per thread (16 for one-word k-mers; 8 / 4 for two / three words so that the keys
+// of a tile still fit the registers of a 1024-thread CTA -- with 16 the W=2 kernel spilled 200 bytes/thread).
+template <int W, int NT, int MODE, bool FILTER, int NPOS = POS_PER_THREAD>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp,
                                                       const uint32_t* __restrict__ chunkpref,
                                                       const uint64_t* __restrict__ bstart64, Key<W>* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Key<W>* stage; uint32_t* cnt2; unsigned long long* G; unsigned long long* Gabs; uint32_t* scratch;
   const int bins = lp.bins;
-  scatter_smem_carve<Key<W>>(smem_raw, NT * POS_PER_THREAD, bins, stage, cnt2, G, Gabs, scratch);
+  scatter_smem_carve<Key<W>>(smem_raw, NT * NPOS, bins, stage, cnt2, G, Gabs, scratch);
   int s; uint32_t t0, t1;
   chunk_tiles(lp, blockIdx.x, s, t0, t1);
   chunk_begin<NT>(chunkpref + (size_t)blockIdx.x * bins, bstart64, 0ull, bins, Gabs, cnt2);
   constexpr uint32_t ES = (uint32_t)sizeof(Key<W>);
   const uint32_t stage_a = smem_u32(stage), G_a = smem_u32(G), cnt2_a = smem_u32(cnt2);
   const uint64_t pol_st = APGK_ST_HINT == 1 ? l2_policy_evict_last() : (APGK_ST_HINT == 2 ? l2_policy_evict_first() : 0ull);
-  Key<W> key[POS_PER_THREAD];
-  uint32_t rk[POS_PER_THREAD / 2];  // two 16-bit ranks per register
+  Key<W> key[NPOS];
+  uint32_t rk[NPOS / 2];  // two 16-bit ranks per register
   uint32_t valid = 0;               // bit j: window j of the tile in key[] is a k-mer of this round
   // tile t: 16 windows per thread -> key[], valid; each k-mer takes its rank inside (tile, bin) from one
   // shared atomic.  between(j) runs after window j (the write-out of the previous tile hooks in here).
   auto extract_rank = [&](uint32_t t, uint32_t cnt_a, auto&& between) {
-    const uint64_t p = ((uint64_t)t * NT + threadIdx.x) * POS_PER_THREAD;
+    const uint64_t p = ((uint64_t)t * NT + threadIdx.x) * NPOS;
     const bool inside = p < rs.total_bases;
     valid = inside ? window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases) : 0u;
+    if (NPOS < 16) valid &= (1u << NPOS) - 1u;
 #pragma unroll
-    for (int j = 0; j < POS_PER_THREAD / 2; j++) rk[j] = 0;
+    for (int j = 0; j < NPOS / 2; j++) rk[j] = 0;
     Window16<W> win;
-    load_window16<W>(rs.bases32, inside ? p : 0ull, rs.K, win);
-    extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool) {
+    if (NPOS == 16) load_window16<W>(rs.bases32, inside ? p : 0ull, rs.K, win);
+    else load_window_at<W>(rs.bases32, inside ? p : 0ull, rs.K, win);
+    extractN<W, NPOS>(win, rs.K, [&](int j, const Key<W>& c, bool) {
       key[j] = c;
       const uint32_t d = dg(c);
       if (FILTER) valid &= ~((uint32_t)((d - dg.flo) >= dg.fwidth) << j);  // belongs to another round
@@ -480,13 +484,14 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
     // ---- place the keys in bin order in the stage
     // (the shared-memory asm statements keep their program order: batch the loads by hand so that
     // eight LDS are in flight instead of one LDS -> STS chain at a time)
+    constexpr int PB = NPOS >= 8 ? 8 : NPOS;
 #pragma unroll
-    for (int j0 = 0; j0 < POS_PER_THREAD; j0 += 8) {
-      uint32_t first[8];
+    for (int j0 = 0; j0 < NPOS; j0 += PB) {
+      uint32_t first[PB];
 #pragma unroll
-      for (int j = j0; j < j0 + 8; j++) first[j - j0] = lds_u32(cnt_a + 4 * dg(key[j]));
+      for (int j = j0; j < j0 + PB; j++) first[j - j0] = lds_u32(cnt_a + 4 * dg(key[j]));
 #pragma unroll
-      for (int j = j0; j < j0 + 8; j++) {
+      for (int j = j0; j < j0 + PB; j++) {
         const uint32_t slot = first[j - j0] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
         SmemElem<Key<W>>::st_if(stage_a + slot * ES, key[j], valid & (1u << j));
       }
@@ -513,16 +518,16 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_reads(ReadS
     };
     if (t + 1 < t1) {
       if (t + 2 < t1) {  // the bases / start bits of tile t+2 toward L1
-        const uint64_t pn = ((uint64_t)(t + 2) * NT + threadIdx.x) * POS_PER_THREAD;
+        const uint64_t pn = ((uint64_t)(t + 2) * NT + threadIdx.x) * NPOS;
         if (pn < rs.total_bases) {
-          if ((threadIdx.x & 7) == 0) prefetch_l1(rs.bases32 + (pn >> 4));   // 8 threads share a 32-byte sector
-          if ((threadIdx.x & 15) == 0) prefetch_l1(rs.starts32 + (pn >> 5));
+          if ((threadIdx.x % (128 / NPOS)) == 0) prefetch_l1(rs.bases32 + (pn >> 4));   // threads sharing a 32-byte sector
+          if ((threadIdx.x % (256 / NPOS)) == 0) prefetch_l1(rs.starts32 + (pn >> 5));
         }
       }
       extract_rank(t + 1, cnt_next_a, write_out);
     } else {
 #pragma unroll
-      for (int j = 0; j < POS_PER_THREAD; j++) write_out(j);
+      for (int j = 0; j < NPOS; j++) write_out(j);
     }
   }
 }
