@@ -77,6 +77,7 @@ SYMBOLS = {
     "apgk_device_copy_to_host": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "apgk_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "apgk_host_free": (C.c_int, [_vp]),
+    "apgk_debug_counters": (C.c_int, [_vp, _vp, C.c_int]),
     "apgk_debug_host_extract": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp]),
     "apgk_debug_host_topdigits": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_int, _vp]),
     "apgk_debug_host_canonical": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),

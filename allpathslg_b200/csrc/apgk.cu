@@ -164,6 +164,17 @@ template <> struct Geo<1> { static constexpr int NTS = APGK_NT; static constexpr
 template <> struct Geo<2> { static constexpr int NTS = 1024; static constexpr int NPOS = 8; static constexpr int NT0 = 512; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 8;  static constexpr int LM_KEY = 2048; };
 template <> struct Geo<3> { static constexpr int NTS = 1024; static constexpr int NPOS = 4; static constexpr int NT0 = 256; static constexpr int NT1 = 512; static constexpr uint32_t TILE1 = 512 * 5;  static constexpr int LM_KEY = 2048; };
 constexpr int LM_U32 = 5120;
+constexpr int LM_KEY4 = 3072;   // k_local4 (full-key elements): 12 bytes per slot, three CTAs per SM
+// k_local4 is used for one-word keys only (K = 27..32).  For multi-word k-mers at high coverage its
+// monotone rows overflow all the time: the sequencing-error variants of one genomic window share their
+// leading ~26+ bases, i.e. they are ~10 distinct keys that belong in the SAME row (K=96, 24 M x 250 bp:
+// 2.4 row overflows per bucket, 9 s) -- those keep the k_local2 / k_local / k_big path.  APGK_LOCAL4=all
+// forces it everywhere (tests), APGK_NO_LOCAL4 switches it off.
+static bool use_local4(int W) {
+  static const bool off = getenv("APGK_NO_LOCAL4") != nullptr;
+  static const bool all = getenv("APGK_LOCAL4") != nullptr && !strcmp(getenv("APGK_LOCAL4"), "all");
+  return !off && (W == 1 || all);
+}
 constexpr int L3_NT = 512;
 constexpr int COL_NT = 1024;
 
@@ -356,7 +367,8 @@ bool select_geometry(apgk_ctx* c, uint64_t upper, int forced_P) {
   }
   const bool u32 = (W == 1 && c->geom.REM <= 32);
   if (!u32) {
-    P = choose_prefix_bits(c, upper, Geo<W>::LM_KEY, false);
+    // k_local4 splits oversize ranges, so the average bucket may sit near its table's capacity
+    P = use_local4(W) ? choose_prefix_bits(c, upper, LM_KEY4 * 3 / 4, true) : choose_prefix_bits(c, upper, Geo<W>::LM_KEY, false);
     make_geom(c, P);
   }
   return u32;
@@ -415,7 +427,7 @@ template <int W, typename ElemB>
 int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode) {
   const KeyGeom g = c->geom;
   const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
-  int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : Geo<W>::LM_KEY;
+  int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : (use_local4(W) ? LM_KEY4 : Geo<W>::LM_KEY);
   int l3_nt = L3_NT;
   if (std::is_same<ElemB, uint32_t>::value) {  // tuning knobs
     if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) local_max = atoi(e); }
@@ -628,13 +640,14 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
     if (const char* e = getenv("APGK_L3_NT")) { if (atoi(e) == 256 || atoi(e) == 512) l3_nt = atoi(e); }
   }
   const bool use_l3 = std::is_same<ElemB, uint32_t>::value && g.REM >= 1 && g.REM <= 31;
+  const bool use_l4 = !std::is_same<ElemB, uint32_t>::value && use_local4(W) && g.pad == 0 && g.REM >= 1;
   const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
   // bucket classification (oversize list)
   const uint32_t big_cap = (uint32_t)(Nr / local_max + 16);
   CU(c->big_list.ensure((size_t)big_cap * 4));
   CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
   k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
-                                                         use_l3 ? 0xFFFFFFFFu : (uint32_t)local_max,
+                                                         (use_l3 || use_l4) ? 0xFFFFFFFFu : (uint32_t)local_max,
                                                          c->big_list.as<uint32_t>(), big_cap,
                                                          c->stats.as<unsigned long long>());
   LAUNCHED();
@@ -674,6 +687,18 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
         };
         int rc3 = l3_nt == 256 ? launch3(k_local3<256, W>, 256) : launch3(k_local3<512, W>, 512);
         if (rc3) return rc3;
+        LAUNCHED();
+      }
+    } else if (use_l4) {
+      // full-key elements: tag-hash kernel; it takes every bucket size (range splitting)
+      if constexpr (!std::is_same<ElemB, uint32_t>::value) {
+        auto kern4 = k_local4<512, W>;
+        const size_t sm4 = Local4Smem::bytes(local_max, W);
+        { int rc = set_smem(c, kern4, sm4); if (rc) return rc; }
+        int occ4 = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, kern4, 512, sm4));
+        const uint32_t grid4 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ4, 1)));
+        kern4<<<grid4, 512, sm4, c->stream>>>((const Key<W>*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>());
         LAUNCHED();
       }
     } else {
@@ -1530,6 +1555,15 @@ int apgk_host_alloc(void** p, size_t bytes) {
 int apgk_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? APGK_OK : APGK_E_CUDA; }
 
 // ---------------------------------------------------------------- host test hooks
+int apgk_debug_counters(apgk_ctx* c, uint64_t* out8, int reset) {
+  if (!c || !out8) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyFromSymbol(out8, g_l4_dbg, 64));
+  if (reset) { unsigned long long z[8] = {0}; CU(cudaMemcpyToSymbol(g_l4_dbg, z, 64)); }
+  return APGK_OK;
+}
+
 int apgk_debug_host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, uint64_t* kmers_out,
                             uint8_t* valid_out) {
   if (!packed || !off || K < 1 || K > APGK_MAX_K) return APGK_E_ARG;

@@ -3,7 +3,7 @@
 // correction makes against it ("k-mer frequency tables consumed by FindErrors",
 // BASELINE.json north_star; SURVEY.md section 3.2 -- no file:line available).
 #pragma once
-#include "local3.cuh"
+#include "local4.cuh"
 
 namespace apgk {
 

@@ -266,6 +266,11 @@ class KmerCounter:
     def reset_counters(self):
         self._L.apgk_reset_counters(self._h)
 
+    def debug_counters(self, reset=True):
+        out = np.zeros(8, dtype=np.uint64)
+        self._ck(self._L.apgk_debug_counters(self._h, out.ctypes.data, 1 if reset else 0))
+        return dict(passes=int(out[0]), row_overflows=int(out[1]), tag_collisions=int(out[2]), buckets=int(out[3]))
+
     def geometry(self):
         g = (C.c_int32 * 8)()
         self._ck(self._L.apgk_geometry(self._h, g))

@@ -213,6 +213,9 @@ int apgk_device_copy_to_host(apgk_ctx* ctx, void* dst_host, const void* src_dev,
 int apgk_host_alloc(void** p, size_t bytes);
 int apgk_host_free(void* p);
 
+/* Diagnostics of the full-key per-bucket kernel since the last reset: out8[0] passes, [1] passes that
+ * overflowed a row (range split), [2] passes redone for a tag collision, [3] buckets. */
+int apgk_debug_counters(apgk_ctx* ctx, uint64_t* out8, int reset);
 /* ---- test hooks: run the device code's inline helpers on the HOST (no GPU needed).  They exist
  * so the CPU test-suite can check extraction against the oracle; the library never calls them. */
 int apgk_debug_host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K,
