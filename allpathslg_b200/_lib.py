@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libapgk.so")
 
 APGK_OK = 0
 E_ARG, E_CUDA, E_NOMEM, E_STATE, E_RANGE = -1, -2, -3, -4, -5
-WANT_SPECTRUM, WANT_COUNTS = 1, 2
+WANT_SPECTRUM, WANT_COUNTS, ASYNC_INGEST = 1, 2, 4
 N_STAGES = 12
 MAX_K = 96
 

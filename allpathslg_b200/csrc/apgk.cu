@@ -70,6 +70,12 @@ struct apgk_ctx {
   // ---- read store
   DevBuf bases, starts, staging, off_dev;
   uint64_t total_bases = 0, n_reads = 0;
+  // ---- streamed ingest (APGK_ASYNC_INGEST): copies in flight on copy_stream, one event per slice
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_main = nullptr;
+  std::vector<cudaEvent_t> slice_ev;
+  std::vector<uint64_t> slice_end;   // bases resident once slice i has landed
+  size_t n_slices = 0;               // pending slices (0 = nothing in flight)
   // ---- pipeline buffers
   DevBuf A, B, T, chunksum, chunksum0, plan0, out_off_local, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
       scratch, stacks, spec_dense, spec_ovf, misc, deferred;
@@ -243,6 +249,15 @@ ReadStore read_store(const apgk_ctx* c) {
   rs.total_bases = c->total_bases;
   rs.K = c->cfg.K;
   return rs;
+}
+
+// streamed ingest: make the context's stream wait for every copy still in flight
+int wait_ingest(apgk_ctx* c) {
+  if (c->n_slices) {
+    CU(cudaStreamWaitEvent(c->stream, c->slice_ev[c->n_slices - 1], 0));
+    c->n_slices = 0;
+  }
+  return APGK_OK;
 }
 
 int choose_prefix_bits(const apgk_ctx* c, uint64_t upper, int local_max, bool l3) {
@@ -482,8 +497,29 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
   } else {
     // cheap formulation when the digit is a clean prefix of the real k-mer (no left padding, <= 8 bases)
     const int top_bits = (g.pad == 0 && g.D0 <= 16 && c->cfg.K >= (g.D0 + 1) / 2 && !getenv("APGK_NO_TOPDIGITS")) ? g.D0 : 0;
-    k_hist_reads<W, Geo<W>::NT0, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT0, bins0 * 4, c->stream>>>(
-        read_store(c), dg0, hp0.lp, top_bits, c->chunksum0.as<uint32_t>());
+    if (c->n_slices == 0) {
+      k_hist_reads<W, Geo<W>::NT0, DIGIT_BITS><<<hp0.lp.n_chunks, Geo<W>::NT0, bins0 * 4, c->stream>>>(
+          read_store(c), dg0, hp0.lp, top_bits, c->chunksum0.as<uint32_t>());
+    } else {
+      // streamed ingest: the chunks whose windows lie inside the slices that have landed, slice after slice
+      const uint64_t reach = (uint64_t)c->cfg.K + 256;  // a window start reads at most K + 48 bases ahead
+      uint32_t c_lo = 0;
+      for (size_t i = 0; i < c->n_slices; i++) {
+        CU(cudaStreamWaitEvent(c->stream, c->slice_ev[i], 0));
+        uint32_t c_hi = hp0.lp.n_chunks;
+        if (i + 1 < c->n_slices) {
+          const uint64_t safe = c->slice_end[i] > reach ? c->slice_end[i] - reach : 0;
+          c_hi = (uint32_t)std::min<uint64_t>(hp0.lp.n_chunks, safe / ((uint64_t)tile0 * hp0.lp.chunk_tiles));
+        }
+        if (c_hi > c_lo) {
+          k_hist_reads<W, Geo<W>::NT0, DIGIT_BITS><<<c_hi - c_lo, Geo<W>::NT0, bins0 * 4, c->stream>>>(
+              read_store(c), dg0, hp0.lp, top_bits, c->chunksum0.as<uint32_t>(), c_lo);
+          c->launches++;
+          c_lo = c_hi;
+        }
+      }
+      c->n_slices = 0;
+    }
   }
   LAUNCHED();
   stage_end(c, ST_HIST0);
@@ -850,6 +886,7 @@ int lookup_impl(apgk_ctx* c, const uint64_t* kmers, uint64_t n, int canon, uint3
 template <int W>
 int read_freqs_impl(apgk_ctx* c, uint64_t first, uint64_t n, uint32_t* out) {
   if (!n) return APGK_OK;
+  { int rc = wait_ingest(c); if (rc) return rc; }
   DevBuf r;
   CU(r.ensure(n * 4));
   constexpr int NT = 128;
@@ -1006,6 +1043,7 @@ int count_pieces_impl(apgk_ctx* c, const void* const* bases_host, bool peer, uin
 // ---------------------------------------------------------------- owner partition (multi-GPU shuffle, sender side)
 template <int W>
 int owner_plan_impl(apgk_ctx* c, uint32_t n_ranks, uint64_t* counts_out) {
+  { int rc = wait_ingest(c); if (rc) return rc; }
   DigitSpec ds{DIGIT_OWNER, 0, 0, 0, n_ranks};
   const DigitFn<DIGIT_OWNER> dg = make_digit_fn<DIGIT_OWNER>(ds);
   const uint32_t tile0 = (uint32_t)Geo<W>::NT0 * POS_PER_THREAD;
@@ -1116,6 +1154,8 @@ int apgk_create(const apgk_config* cfg, apgk_ctx** out) {
   c->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return APGK_E_CUDA; }
   for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventCreate(&c->ev[s][0]); cudaEventCreate(&c->ev[s][1]); }
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { apgk_destroy(c); return APGK_E_CUDA; }
+  cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
   if (cfg->reserve_bases && ensure_store(c, cfg->reserve_bases) != APGK_OK) {
     apgk_destroy(c);
     return APGK_E_NOMEM;
@@ -1134,6 +1174,9 @@ void apgk_destroy(apgk_ctx* c) {
                    &c->out_keys, &c->out_cnt, &c->owner_plan_dev};
   for (DevBuf* b : all) b->release();
   for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (cudaEvent_t e : c->slice_ev) cudaEventDestroy(e);
+  if (c->ev_main) cudaEventDestroy(c->ev_main);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1143,6 +1186,7 @@ const char* apgk_last_error(const apgk_ctx* c) { return c ? c->err.c_str() : "nu
 int apgk_reset(apgk_ctx* c) {
   if (!c) return APGK_E_ARG;
   CU(cudaSetDevice(c->device));
+  { int rc = wait_ingest(c); if (rc) return rc; }
   if (c->total_bases) {
     CU(cudaMemsetAsync(c->bases.p, 0, std::min(c->bases.cap, (size_t)((c->total_bases + 31) / 32) * 8 + 256), c->stream));
     CU(cudaMemsetAsync(c->starts.p, 0, std::min(c->starts.cap, (size_t)((c->total_bases + 31) / 32) * 4 + 256), c->stream));
@@ -1156,6 +1200,7 @@ int apgk_add_reads(apgk_ctx* c, const uint8_t* packed, const uint64_t* off, uint
   if (!c || (!packed && n_reads) || (!off && n_reads)) return APGK_E_ARG;
   if (!n_reads) return APGK_OK;
   CU(cudaSetDevice(c->device));
+  { int rc = wait_ingest(c); if (rc) return rc; }
   for (uint64_t r = 0; r < n_reads; r++)
     if (off[r + 1] < off[r]) FAIL(APGK_E_ARG, "read offsets must be non-decreasing (read %llu)", (unsigned long long)r);
   const uint64_t nb = off[n_reads] - off[0];
@@ -1181,6 +1226,40 @@ int apgk_add_reads_uniform(apgk_ctx* c, const uint8_t* packed, uint64_t first_ba
   CU(cudaSetDevice(c->device));
   const uint64_t nb = n_reads * (uint64_t)read_len;
   const uint64_t dst0 = c->total_bases;
+  const bool aligned = ((2 * dst0) & 7) == 0 && ((2 * first_base) & 7) == 0 && ((2 * nb) & 7) == 0;
+  if ((c->cfg.flags & APGK_ASYNC_INGEST) && aligned && c->n_slices == 0) {
+    // streamed ingest: the copy goes out in slices on its own stream; finish / partition follow it slice by slice
+    { int rc = ensure_store(c, dst0 + nb); if (rc) return rc; }
+    const size_t nbytes = (size_t)(nb / 4);
+    const size_t n_sl = std::max<size_t>(1, std::min<size_t>(16, nbytes >> 24));  // slices of >= 16 MB
+    while (c->slice_ev.size() < n_sl) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->slice_ev.push_back(e);
+    }
+    c->slice_end.assign(n_sl, 0);
+    CU(cudaEventRecord(c->ev_main, c->stream));            // the store's memsets / earlier kernels come first
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    const size_t per = ((nbytes / n_sl) + 4095) & ~(size_t)4095;
+    uint8_t* dst = c->bases.as<uint8_t>() + (2 * dst0 >> 3);
+    const uint8_t* src = packed + (2 * first_base >> 3);
+    size_t done = 0;
+    for (size_t i = 0; i < n_sl; i++) {
+      const size_t len = (i + 1 == n_sl) ? nbytes - done : std::min(per, nbytes - done);
+      if (len) CU(cudaMemcpyAsync(dst + done, src + done, len, cudaMemcpyHostToDevice, c->copy_stream));
+      done += len;
+      CU(cudaEventRecord(c->slice_ev[i], c->copy_stream));
+      c->slice_end[i] = dst0 + (uint64_t)done * 4;
+    }
+    k_mark_starts_uniform<<<(unsigned)((n_reads + 255) / 256), 256, 0, c->stream>>>(n_reads, read_len, dst0,
+                                                                                   c->starts.as<uint32_t>());
+    LAUNCHED();
+    c->total_bases += nb; c->n_reads += n_reads;
+    invalidate_results(c);
+    c->n_slices = n_sl;
+    return APGK_OK;
+  }
+  { int rc = wait_ingest(c); if (rc) return rc; }
   int rc = append_bases(c, packed, first_base, nb);
   if (rc) return rc;
   k_mark_starts_uniform<<<(unsigned)((n_reads + 255) / 256), 256, 0, c->stream>>>(n_reads, read_len, dst0,
@@ -1198,6 +1277,7 @@ int apgk_synth_reads(apgk_ctx* c, const apgk_synth_params* p, uint64_t r0, uint6
   if (p->read_len == 0 || p->genome_len < p->read_len) FAIL(APGK_E_ARG, "genome shorter than a read");
   if (c->total_bases % 16) FAIL(APGK_E_STATE, "apgk_synth_reads needs the store to hold a multiple of 16 bases");
   CU(cudaSetDevice(c->device));
+  { int rc = wait_ingest(c); if (rc) return rc; }
   const uint64_t nb = n_reads * (uint64_t)p->read_len;
   int rc = ensure_store(c, c->total_bases + nb);
   if (rc) return rc;
@@ -1217,6 +1297,7 @@ int apgk_synth_reads(apgk_ctx* c, const apgk_synth_params* p, uint64_t r0, uint6
 int apgk_export_reads(apgk_ctx* c, uint8_t* out) {
   if (!c || !out) return APGK_E_ARG;
   CU(cudaSetDevice(c->device));
+  { int rc = wait_ingest(c); if (rc) return rc; }
   if (c->total_bases) {
     CU(cudaMemcpyAsync(out, c->bases.p, ((c->total_bases + 31) / 32) * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

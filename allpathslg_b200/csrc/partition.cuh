@@ -322,14 +322,15 @@ struct ReadStore {
 // bits of the canonical k-mer and nothing else of the k-mer is needed.
 template <int W, int NT, int MODE>
 __global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> dg, LevelPlan lp, int top_bits,
-                                                   uint32_t* __restrict__ chunksum) {
+                                                   uint32_t* __restrict__ chunksum, uint32_t chunk0 = 0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* hist = (uint32_t*)smem_raw;
   const int bins = lp.bins;
   for (int i = threadIdx.x; i < bins; i += NT) hist[i] = 0;
   __syncthreads();
   int s; uint32_t t0, t1;
-  chunk_tiles(lp, blockIdx.x, s, t0, t1);
+  const uint32_t chunk = blockIdx.x + chunk0;  // a launch may cover a slice of the chunks (streamed ingest)
+  chunk_tiles(lp, chunk, s, t0, t1);
   const uint32_t hist_a = smem_u32(hist);
   for (uint32_t t = t0; t < t1; t++) {
     const uint64_t p = ((uint64_t)t * NT + threadIdx.x) * POS_PER_THREAD;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(NT) k_hist_reads(ReadStore rs, DigitFn<MODE> d
     }
   }
   __syncthreads();
-  uint32_t* row = chunksum + (size_t)blockIdx.x * bins;
+  uint32_t* row = chunksum + (size_t)chunk * bins;
   for (int i = threadIdx.x; i < bins; i += NT) row[i] = hist[i];
 }
 

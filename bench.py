@@ -71,6 +71,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
@@ -86,6 +87,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """forget the samples taken so far (warm-up)"""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -96,7 +101,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:] or self.lines[-1:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -190,7 +195,8 @@ def run_ours(args):
 
     genome = GENOME_PER_GPU * n_gpus
     sp = synth_params(genome, READ_LEN)
-    kc = KmerCounter(K, device=local_rank, want_counts=True, reserve_bases=READS_PER_GPU * READ_LEN)
+    kc = KmerCounter(K, device=local_rank, want_counts=True, reserve_bases=READS_PER_GPU * READ_LEN,
+                     async_ingest=True)  # e2e: the level-0 histogram follows the H2D copy slice by slice
     kc.synth_reads(sp, rank * READS_PER_GPU, READS_PER_GPU)
     total_bases, _ = kc.read_store_info()
 
@@ -208,11 +214,14 @@ def run_ours(args):
         return ni, tm
 
     # ---------------- value: inputs resident in HBM
-    for _ in range(args.warmup):
-        step_resident()
+    # nvidia-smi starts BEFORE the warm-up (its NVML initialisation can stall the driver for tens of
+    # milliseconds); only the samples taken during the timed region are used
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    sampler.mark()
     kc.reset_counters()
     stage_acc = {}
     shard_acc = {}

@@ -55,6 +55,11 @@ extern "C" {
 
 #define APGK_WANT_SPECTRUM 1u /* always produced */
 #define APGK_WANT_COUNTS 2u   /* also build the sorted (k-mer, count) table + lookup index */
+/* Streamed ingest: apgk_add_reads_uniform (byte-aligned appends) returns before its host-to-device copy
+ * has completed.  `packed` must then stay valid -- and should be pinned (apgk_host_alloc) -- until the
+ * next apgk_finish / apgk_partition has returned; that call runs its level-0 histogram slice by slice
+ * behind the copy instead of after it.  Every other call waits for the copy first. */
+#define APGK_ASYNC_INGEST 4u
 
 #define APGK_MAX_K 96
 

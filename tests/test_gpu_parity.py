@@ -352,6 +352,37 @@ def test_strand_and_order_invariance(oracle):
                 assert (cur[0][0] == ref[0][0]).all() and (cur[0][1] == ref[0][1]).all() and (cur[1] == ref[1]).all()
 
 
+def test_streamed_ingest_matches(oracle):
+    """APGK_ASYNC_INGEST: add_reads_uniform returns before its copy has landed and finish follows the copy
+    slice by slice; results must be identical, also after reset + re-ingest and with a sync append behind."""
+    import torch
+
+    from allpathslg_b200 import KmerCounter
+
+    L, n = 100, 400_000
+    sp = oracle.synth_params(2_000_000, L)
+    p, o = oracle.synth_reads(sp, 0, n)
+    ek, ec, en = oracle.count(p, o, 25)
+    host = torch.from_numpy(p.copy()).pin_memory()
+    kc = KmerCounter(25, async_ingest=True)
+    for _ in range(2):
+        kc.reset()
+        kc.add_reads_uniform(host.data_ptr(), n, L)
+        kc.finish()
+        gk, gc = kc.counts()
+        assert kc.totals() == (en, len(ek)) and (gk == ek).all() and (gc.astype(np.uint64) == ec).all()
+    # a second, synchronous append behind a pending streamed one, then read_freqs (which must wait for the copy)
+    kc.reset()
+    half = n // 2
+    kc.add_reads_uniform(host.data_ptr(), half, L)
+    p2, _ = oracle.synth_reads(sp, half, n - half)
+    kc.add_reads_uniform(p2, n - half, L)
+    kc.finish()
+    assert kc.totals() == (en, len(ek))
+    assert (kc.spectrum() == oracle.spectrum(ec)).all()
+    kc.close()
+
+
 # ------------------------------------------------------------------ multi-GPU building blocks on one GPU
 @pytest.mark.parametrize("K,world", [(25, 2), (25, 8), (64, 4), (96, 3)])
 def test_owner_partition_and_key_ingest(oracle, K, world):
