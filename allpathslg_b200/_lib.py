@@ -49,6 +49,10 @@ SYMBOLS = {
     "apgk_counts_copy": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp]),
     "apgk_lookup": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp]),
     "apgk_read_freqs": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "apgk_build_occurrences": (C.c_int, [_vp]),
+    "apgk_occurrences_info": (C.c_int, [_vp, _u64p, _u64p, C.POINTER(C.c_float)]),
+    "apgk_occurrences_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
+    "apgk_occurrences_copy": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp]),
     "apgk_owner_plan": (C.c_int, [_vp, C.c_uint32, _vp]),
     "apgk_owner_scatter": (C.c_int, [_vp, _vp]),
     "apgk_key_buffer": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
@@ -81,6 +85,7 @@ SYMBOLS = {
     "apgk_debug_host_extract": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp]),
     "apgk_debug_host_topdigits": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_int, _vp]),
     "apgk_debug_host_canonical": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
+    "apgk_debug_host_table_find": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_int, _vp, C.c_uint64, _vp]),
     "apgk_debug_host_synth": (C.c_int, [C.POINTER(SynthParams), C.c_uint64, C.c_uint64, _vp]),
 }
 

@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "../../include/apgk.h"
-#include "table.cuh"
+#include "occ.cuh"
 
 using namespace apgk;
 
@@ -82,6 +82,14 @@ struct apgk_ctx {
   // ---- results
   DevBuf out_keys, out_cnt;
   bool finished = false, have_table = false;
+  bool table_from_reads = false;   // the table counts exactly the windows of this context's read store
+  // ---- occurrence records (apgk_build_occurrences): run offsets + (position << 1 | rc) per instance, in A
+  DevBuf occ_off, rank_cnt, rank_dir, empty_dev, occ_tmp;
+  bool have_occ = false;
+  uint64_t n_occ = 0, n_big_runs = 0;
+  float occ_ms[4]{};
+  cudaEvent_t occ_ev[5]{};
+  std::vector<uint64_t> empty_nb;  // per read without bases: number of reads WITH bases before it
   uint64_t n_instances = 0, n_distinct = 0;
   KeyGeom geom{};
   uint32_t nb1 = 0;          // number of level-1 buckets
@@ -344,6 +352,7 @@ int append_bases(apgk_ctx* c, const uint8_t* packed, uint64_t first_base, uint64
 
 void invalidate_results(apgk_ctx* c) {
   c->finished = false; c->have_table = false; c->spec_loaded = false;
+  c->table_from_reads = false; c->have_occ = false; c->n_occ = 0;
   c->n_instances = c->n_distinct = 0;
   c->owner_ranks = 0;
   c->part_ready = false; c->part_n = 0;
@@ -921,6 +930,109 @@ int scan_u32(apgk_ctx* c, const uint32_t* in, uint64_t n, unsigned long long* ou
   return APGK_OK;
 }
 
+// ---------------------------------------------------------------- occurrence records
+template <int W>
+int build_occurrences_impl(apgk_ctx* c) {
+  const uint64_t N = c->n_instances, D = c->n_distinct;
+  c->have_occ = false; c->n_occ = 0; c->n_big_runs = 0;
+  for (float& m : c->occ_ms) m = 0;
+  { int rc = wait_ingest(c); if (rc) return rc; }
+  for (cudaEvent_t& e : c->occ_ev) if (!e) CU(cudaEventCreate(&e));
+  CU(c->occ_off.ensure((D + 1) * 8));
+  if (!N) {
+    CU(cudaMemsetAsync(c->occ_off.p, 0, (D + 1) * 8, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_occ = true;
+    return APGK_OK;
+  }
+  // run offsets = exclusive scan of the counts
+  CU(cudaEventRecord(c->occ_ev[0], c->stream));
+  unsigned long long total = 0;
+  { int rc = scan_u32(c, c->out_cnt.as<uint32_t>(), D, c->occ_off.as<unsigned long long>(), &total); if (rc) return rc; }
+  if (total != N) FAIL(APGK_E_RANGE, "occurrences: counts sum to %llu, instances %llu (a count saturated)", total, (unsigned long long)N);
+  // A (level-0 keys, dead after finish) holds the occurrences, T the per-run cursors, B the big-run list
+  const size_t list_cap = (size_t)(N / OCC_SMALL_MAX) + 1;
+  CU(c->A.ensure(N * 8));
+  CU(c->T.ensure(D * 4));
+  CU(c->B.ensure((list_cap + 4) * 8));
+  unsigned long long* counters = c->B.as<unsigned long long>();
+  CU(cudaMemsetAsync(c->T.p, 0, D * 4, c->stream));
+  CU(cudaMemsetAsync(counters, 0, 32, c->stream));
+  CU(cudaEventRecord(c->occ_ev[1], c->stream));
+  {
+    constexpr int NT = 128;
+    const uint64_t threads = (c->total_bases + POS_PER_THREAD - 1) / POS_PER_THREAD;
+    k_occ_fill<W, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(
+        read_store(c), freq_table<W>(c), c->occ_off.as<unsigned long long>(), c->T.as<uint32_t>(),
+        c->A.as<unsigned long long>(), counters);
+    LAUNCHED();
+  }
+  CU(cudaEventRecord(c->occ_ev[2], c->stream));
+  k_occ_sort_small<<<(unsigned)((D + 127) / 128), 128, 0, c->stream>>>(c->occ_off.as<unsigned long long>(), D,
+                                                                      c->A.as<unsigned long long>(), counters + 4, counters);
+  LAUNCHED();
+  CU(cudaEventRecord(c->occ_ev[3], c->stream));
+  k_occ_sort_big<OCC_BIG_NT><<<c->n_sm * 2, OCC_BIG_NT, 0, c->stream>>>(c->occ_off.as<unsigned long long>(), counters + 4, counters,
+                                                                      c->A.as<unsigned long long>());
+  LAUNCHED();
+  CU(cudaEventRecord(c->occ_ev[4], c->stream));
+  // rank directory over the start bitmap: read id of a global base position
+  {
+    const uint64_t words = (c->total_bases + 31) / 32;
+    const uint64_t n_blocks = words / RANK_BLOCK_WORDS + 1;   // covers word index `words` as well; the bitmap is zero padded
+    CU(c->rank_cnt.ensure(n_blocks * 4));
+    CU(c->rank_dir.ensure((n_blocks + 1) * 8));
+    k_start_blocks<<<(unsigned)((n_blocks + 255) / 256), 256, 0, c->stream>>>(c->starts.as<uint32_t>(), n_blocks,
+                                                                            c->rank_cnt.as<uint32_t>());
+    LAUNCHED();
+    int rc = scan_u32(c, c->rank_cnt.as<uint32_t>(), n_blocks, c->rank_dir.as<unsigned long long>(), nullptr);
+    if (rc) return rc;
+    if (!c->empty_nb.empty()) {
+      CU(c->empty_dev.ensure(c->empty_nb.size() * 8));
+      CU(cudaMemcpyAsync(c->empty_dev.p, c->empty_nb.data(), c->empty_nb.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  unsigned long long h[3] = {0, 0, 0};
+  CU(cudaMemcpyAsync(h, counters, 24, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->occ_ms[i], c->occ_ev[i], c->occ_ev[i + 1]);
+  if (h[1] || h[2])
+    FAIL(APGK_E_STATE, "occurrences: %llu windows missing from the table, %llu slots past a run (table does not match the read store)",
+         h[1], h[2]);
+  c->n_big_runs = h[0];
+  c->n_occ = N;
+  c->have_occ = true;
+  return APGK_OK;
+}
+
+int occurrences_copy_impl(apgk_ctx* c, uint64_t first, uint64_t n_kmers, uint64_t* run_off_out, uint32_t* read_id_out,
+                          int32_t* pos_out) {
+  std::vector<unsigned long long> ends(2, 0);
+  const unsigned long long* off = c->occ_off.as<unsigned long long>();
+  CU(cudaMemcpyAsync(&ends[0], off + first, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&ends[1], off + first + n_kmers, 8, cudaMemcpyDeviceToHost, c->stream));
+  if (run_off_out)
+    CU(cudaMemcpyAsync(run_off_out, off + first, (n_kmers + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (!read_id_out && !pos_out) return APGK_OK;
+  const uint64_t o0 = ends[0], n = ends[1] - ends[0];
+  const uint64_t CH = 1ull << 26;  // occurrences translated per step (768 MB of device scratch at most)
+  CU(c->occ_tmp.ensure(std::min(n, CH) * 8 + 8));
+  uint32_t* d_id = c->occ_tmp.as<uint32_t>();
+  for (uint64_t done = 0; done < n; done += CH) {
+    const uint64_t m = std::min(CH, n - done);
+    int32_t* d_pos = (int32_t*)(d_id + m);
+    k_occ_translate<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(
+        c->A.as<unsigned long long>() + o0 + done, m, c->starts.as<uint32_t>(), c->rank_dir.as<unsigned long long>(),
+        c->empty_dev.as<unsigned long long>(), (uint32_t)c->empty_nb.size(), d_id, d_pos);
+    LAUNCHED();
+    if (read_id_out) CU(cudaMemcpyAsync(read_id_out + done, d_id, m * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (pos_out) CU(cudaMemcpyAsync(pos_out + done, d_pos, m * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return APGK_OK;
+}
+
 // split bits actually used for a request (same on every rank: it depends on the geometry only)
 int effective_split_bits(const apgk_ctx* c, int d2) {
   d2 = std::max(0, std::min(d2, 5));
@@ -1105,6 +1217,19 @@ int owner_scatter_impl(apgk_ctx* c, uint64_t* d_out) {
 
 namespace {
 template <int W>
+static void host_table_find(int K, const uint64_t* sorted, uint64_t n, int P, const uint64_t* q, uint64_t nq, uint64_t* out) {
+  const int TB = std::max(2 * K, P), pad = TB - 2 * K, REM = TB - P;
+  std::vector<unsigned long long> index(((size_t)1 << P) + 1, 0);
+  const Key<W>* keys = (const Key<W>*)sorted;
+  for (uint64_t i = 0; i < n; i++) index[digit_of(keys[i], REM, P, pad) + 1]++;
+  for (size_t b = 0; b < ((size_t)1 << P); b++) index[b + 1] += index[b];
+  FreqTable<W> t;
+  t.keys = keys; t.counts = nullptr; t.index = index.data(); t.nb = 1u << P;
+  t.prefix_pos = REM; t.prefix_len = P; t.pad = pad; t.D1 = 0;
+  for (uint64_t i = 0; i < nq; i++) out[i] = table_find_index(t, ((const Key<W>*)q)[i]);
+}
+
+template <int W>
 static void host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, uint64_t* kmers_out,
                          uint8_t* valid_out) {
   const uint64_t b0 = off[0], total = off[n_reads] - b0;
@@ -1171,8 +1296,10 @@ void apgk_destroy(apgk_ctx* c) {
   DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum, &c->chunksum0, &c->plan0, &c->out_off_local,
                    &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
                    &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc, &c->deferred,
-                   &c->out_keys, &c->out_cnt, &c->owner_plan_dev};
+                   &c->out_keys, &c->out_cnt, &c->owner_plan_dev, &c->piece_off, &c->piece_tmp, &c->piece_ptrs, &c->C2, &c->sub_sizes,
+                   &c->occ_off, &c->rank_cnt, &c->rank_dir, &c->empty_dev, &c->occ_tmp};
   for (DevBuf* b : all) b->release();
+  for (cudaEvent_t e : c->occ_ev) if (e) cudaEventDestroy(e);
   for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   for (cudaEvent_t e : c->slice_ev) cudaEventDestroy(e);
@@ -1192,6 +1319,7 @@ int apgk_reset(apgk_ctx* c) {
     CU(cudaMemsetAsync(c->starts.p, 0, std::min(c->starts.cap, (size_t)((c->total_bases + 31) / 32) * 4 + 256), c->stream));
   }
   c->total_bases = 0; c->n_reads = 0;
+  c->empty_nb.clear();
   invalidate_results(c);
   return APGK_OK;
 }
@@ -1215,6 +1343,8 @@ int apgk_add_reads(apgk_ctx* c, const uint8_t* packed, const uint64_t* off, uint
     LAUNCHED();
   }
   CU(cudaStreamSynchronize(c->stream));  // inputs are only borrowed for the duration of the call
+  for (uint64_t r = 0; r < n_reads; r++)   // reads without bases own no start bit: remember where they sit (occurrence read ids)
+    if (off[r + 1] == off[r]) c->empty_nb.push_back(c->n_reads + r - c->empty_nb.size());
   c->total_bases += nb; c->n_reads += n_reads;
   invalidate_results(c);
   return APGK_OK;
@@ -1315,12 +1445,14 @@ int apgk_read_store_info(const apgk_ctx* c, uint64_t* total_bases, uint64_t* n_r
 int apgk_finish(apgk_ctx* c) {
   if (!c) return APGK_E_ARG;
   CU(cudaSetDevice(c->device));
+  int rc = APGK_E_ARG;
   switch (c->W) {
-    case 1: return finish_impl<1>(c, nullptr, 0);
-    case 2: return finish_impl<2>(c, nullptr, 0);
-    case 3: return finish_impl<3>(c, nullptr, 0);
+    case 1: rc = finish_impl<1>(c, nullptr, 0); break;
+    case 2: rc = finish_impl<2>(c, nullptr, 0); break;
+    case 3: rc = finish_impl<3>(c, nullptr, 0); break;
   }
-  return APGK_E_ARG;
+  if (rc == APGK_OK) c->table_from_reads = true;
+  return rc;
 }
 
 int apgk_finish_keys_device(apgk_ctx* c, const uint64_t* d_keys, uint64_t n) {
@@ -1530,6 +1662,48 @@ int apgk_read_freqs(apgk_ctx* c, uint64_t first_base, uint64_t n_bases, uint32_t
   return APGK_E_ARG;
 }
 
+int apgk_build_occurrences(apgk_ctx* c) {
+  if (!c) return APGK_E_ARG;
+  if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
+  if (!c->table_from_reads)
+    FAIL(APGK_E_STATE, "occurrences need a table counted from this context's read store (apgk_finish, not a shard or a key array)");
+  if (c->n_reads > 0xFFFFFFFFull) FAIL(APGK_E_RANGE, "occurrences: read ids are 32-bit, %llu reads", (unsigned long long)c->n_reads);
+  CU(cudaSetDevice(c->device));
+  switch (c->W) {
+    case 1: return build_occurrences_impl<1>(c);
+    case 2: return build_occurrences_impl<2>(c);
+    case 3: return build_occurrences_impl<3>(c);
+  }
+  return APGK_E_ARG;
+}
+
+int apgk_occurrences_info(const apgk_ctx* c, uint64_t* n_occ, uint64_t* n_big_runs, float* ms4) {
+  if (!c) return APGK_E_ARG;
+  if (!c->have_occ) return APGK_E_STATE;
+  if (n_occ) *n_occ = c->n_occ;
+  if (n_big_runs) *n_big_runs = c->n_big_runs;
+  if (ms4) for (int i = 0; i < 4; i++) ms4[i] = c->occ_ms[i];
+  return APGK_OK;
+}
+
+int apgk_occurrences_device(apgk_ctx* c, const uint64_t** d_run_off, const uint64_t** d_occ, uint64_t* n_occ) {
+  if (!c) return APGK_E_ARG;
+  if (!c->have_occ) FAIL(APGK_E_STATE, "no occurrences: call apgk_build_occurrences first");
+  if (d_run_off) *d_run_off = c->occ_off.as<uint64_t>();
+  if (d_occ) *d_occ = c->n_occ ? c->A.as<uint64_t>() : nullptr;
+  if (n_occ) *n_occ = c->n_occ;
+  return APGK_OK;
+}
+
+int apgk_occurrences_copy(apgk_ctx* c, uint64_t first_kmer, uint64_t n_kmers, uint64_t* run_off_out, uint32_t* read_id_out,
+                          int32_t* pos_out) {
+  if (!c) return APGK_E_ARG;
+  if (!c->have_occ) FAIL(APGK_E_STATE, "no occurrences: call apgk_build_occurrences first");
+  if (first_kmer > c->n_distinct || n_kmers > c->n_distinct - first_kmer) FAIL(APGK_E_ARG, "k-mer range beyond the table");
+  CU(cudaSetDevice(c->device));
+  return occurrences_copy_impl(c, first_kmer, n_kmers, run_off_out, read_id_out, pos_out);
+}
+
 int apgk_owner_plan(apgk_ctx* c, uint32_t n_ranks, uint64_t* counts_out) {
   if (!c || !counts_out || n_ranks < 1 || n_ranks > 1024) return APGK_E_ARG;
   CU(cudaSetDevice(c->device));
@@ -1680,6 +1854,18 @@ int apgk_debug_host_canonical(int K, const uint64_t* kmers, uint64_t n, uint64_t
     if (W == 1) { Key<1> k; k.w[0] = kmers[i]; k = key_canonical(k, K); out[i] = k.w[0]; }
     else if (W == 2) { Key<2> k; memcpy(k.w, kmers + 2 * i, 16); k = key_canonical(k, K); memcpy(out + 2 * i, k.w, 16); }
     else { Key<3> k; memcpy(k.w, kmers + 3 * i, 24); k = key_canonical(k, K); memcpy(out + 3 * i, k.w, 24); }
+  }
+  return APGK_OK;
+}
+
+int apgk_debug_host_table_find(int K, const uint64_t* sorted_kmers, uint64_t n, int prefix_bits, const uint64_t* queries,
+                               uint64_t n_q, uint64_t* idx_out) {
+  if (K < 1 || K > APGK_MAX_K || prefix_bits < 1 || prefix_bits > 24) return APGK_E_ARG;
+  if (words_for(K) > 1 && prefix_bits > 2 * K) return APGK_E_ARG;
+  switch (words_for(K)) {
+    case 1: host_table_find<1>(K, sorted_kmers, n, prefix_bits, queries, n_q, idx_out); break;
+    case 2: host_table_find<2>(K, sorted_kmers, n, prefix_bits, queries, n_q, idx_out); break;
+    case 3: host_table_find<3>(K, sorted_kmers, n, prefix_bits, queries, n_q, idx_out); break;
   }
   return APGK_OK;
 }

@@ -314,17 +314,56 @@ struct FreqTable {
   int D1;
 };
 
+// Index of canonical k-mer c in the table, ~0 if absent.  The prefix index narrows the search to one
+// level-1 bucket; inside it the keys are close to uniformly spread over the remainder space, so the
+// search starts at the interpolated slot (next 16 key bits), brackets the answer by galloping (8, 16,
+// 32 ... slots) and finishes with a binary search inside the bracket: ~3 dependent DRAM sectors per
+// query instead of ~10 for a plain binary search over a ~600-key bucket.  Correct for any key
+// distribution (a skewed bucket only gallops further).  Host-callable for the CPU test of the search.
 template <int W>
-__device__ __forceinline__ uint32_t table_find(const FreqTable<W>& t, const Key<W>& c) {
+APGK_HD unsigned long long table_find_index(const FreqTable<W>& t, const Key<W>& c) {
   // prefix bucket = (digit0 << D1) | digit1 = bits [prefix_pos, prefix_pos + prefix_len) of the virtual key
   const uint32_t b = digit_of(c, t.prefix_pos, t.prefix_len, t.pad);
-  unsigned long long lo = t.index[b], hi = t.index[b + 1];
+  const unsigned long long lo0 = t.index[b], hi0 = t.index[b + 1];
+  unsigned long long lo = lo0, hi = hi0;  // invariant: keys below lo are < c, keys from hi on are >= c
+  if (hi - lo > 16) {
+    const int fb = t.prefix_pos < 16 ? t.prefix_pos : 16;
+    const unsigned long long frac = digit_of(c, t.prefix_pos - fb, fb, t.pad);
+    const unsigned long long g = lo + (((hi - lo) * frac) >> fb);  // lo0 <= g < hi0
+    unsigned long long step = 8;
+    if (key_less(t.keys[g], c)) {
+      lo = g + 1;
+      for (;;) {
+        const unsigned long long h = hi0 - lo > step ? lo + step : hi0;
+        if (h == lo) { hi = lo; break; }
+        if (key_less(t.keys[h - 1], c)) {
+          lo = h;
+          if (h == hi0) { hi = h; break; }
+          step <<= 1;
+        } else { hi = h - 1; break; }
+      }
+    } else {
+      hi = g;
+      for (;;) {
+        if (hi == lo0) { lo = lo0; break; }
+        const unsigned long long l = hi - lo0 > step ? hi - step : lo0;
+        if (key_less(t.keys[l], c)) { lo = l + 1; break; }
+        hi = l;
+        step <<= 1;
+      }
+    }
+  }
   while (lo < hi) {
-    unsigned long long mid = (lo + hi) >> 1;
+    const unsigned long long mid = (lo + hi) >> 1;
     if (key_less(t.keys[mid], c)) lo = mid + 1; else hi = mid;
   }
-  if (lo < t.index[b + 1] && key_eq(t.keys[lo], c)) return t.counts[lo];
-  return 0u;
+  if (lo < hi0 && key_eq(t.keys[lo], c)) return lo;
+  return ~0ull;
+}
+template <int W>
+APGK_HD uint32_t table_find(const FreqTable<W>& t, const Key<W>& c) {
+  const unsigned long long i = table_find_index(t, c);
+  return i == ~0ull ? 0u : t.counts[i];
 }
 
 template <int W>

@@ -171,6 +171,41 @@ class KmerCounter:
         self._ck(self._L.apgk_read_freqs(self._h, first_base, n_bases, out.ctypes.data))
         return out[:n_bases]
 
+    # -- occurrence records: (read id, signed position) of every instance, grouped by k-mer
+    def build_occurrences(self):
+        """Second sweep over the read store: every window takes a slot in its k-mer's run (needs finish()
+        with want_counts).  -> dict(n_occ, n_big_runs, ms={scan, fill, sort, sort_big})."""
+        self._ck(self._L.apgk_build_occurrences(self._h))
+        return self.occurrences_info()
+
+    def occurrences_info(self):
+        n, nb = C.c_uint64(), C.c_uint64()
+        ms = (C.c_float * 4)()
+        self._ck(self._L.apgk_occurrences_info(self._h, C.byref(n), C.byref(nb), ms))
+        return dict(n_occ=n.value, n_big_runs=nb.value, ms=dict(zip(("scan", "fill", "sort", "sort_big"), [float(x) for x in ms])))
+
+    def occurrences(self, first=0, n=None):
+        """-> (run_off uint64[n+1] rebased to 0, read_id uint32[m], pos int32[m]) for k-mers [first, first+n) of
+        the sorted table; k-mer first+i owns slots [run_off[i], run_off[i+1]), ascending by (read id, position);
+        pos is 1-based, negative when the canonical form is the reverse complement of the read's window."""
+        _, nd = self.totals()
+        if n is None:
+            n = nd - first
+        ro = np.zeros(n + 1, dtype=np.uint64)
+        self._ck(self._L.apgk_occurrences_copy(self._h, first, n, ro.ctypes.data, None, None))
+        m = int(ro[-1] - ro[0])
+        rid = np.zeros(max(m, 1), dtype=np.uint32)
+        pos = np.zeros(max(m, 1), dtype=np.int32)
+        if m:
+            self._ck(self._L.apgk_occurrences_copy(self._h, first, n, None, rid.ctypes.data, pos.ctypes.data))
+        return ro - ro[0], rid[:m], pos[:m]
+
+    def occurrences_device(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        n = C.c_uint64()
+        self._ck(self._L.apgk_occurrences_device(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     # -- multi-GPU building blocks
     def owner_plan(self, n_ranks):
         out = np.zeros(n_ranks, dtype=np.uint64)
@@ -362,14 +397,21 @@ class KmerSpectrum:
         return dict(f_min=f_min, kmer_coverage=float(f_peak), genome_size=g, coverage=cov)
 
 
-def SortKmers(packed, off, K, device=0):
-    """Mirror of the reference's SortKmers builder for the counting contract: all canonical
-    k-mers of the reads, sorted ascending, with their multiplicities.
-    -> (kmers uint64[n, W], counts uint32[n])."""
+def SortKmers(packed, off, K, device=0, records=False):
+    """Mirror of the reference's SortKmers builder: all canonical k-mers of the reads, sorted ascending.
+    records=False (the counting contract) -> (kmers uint64[n, W], counts uint32[n]).
+    records=True (the full kmer-record vector: one record per INSTANCE, sorted by k-mer, ties by
+    (read id, position)) -> (kmers uint64[N, W], read_id uint32[N], pos int32[N]); pos is 1-based and
+    negative when the canonical k-mer is the reverse complement of the read's window."""
     with KmerCounter(K, device=device, want_counts=True) as kc:
         kc.add_reads(packed, off)
         kc.finish()
-        return kc.counts()
+        k, c = kc.counts()
+        if not records:
+            return k, c
+        kc.build_occurrences()
+        _, rid, pos = kc.occurrences()
+        return np.repeat(k, c.astype(np.int64), axis=0), rid, pos
 
 
 class KmerParcelsBuilder:
@@ -382,6 +424,7 @@ class KmerParcelsBuilder:
         self._kc = KmerCounter(K, device=device, want_counts=True)
         self._kc.add_reads(packed, off)
         self._built = False
+        self._occ = False
 
     def Build(self):
         self._kc.finish()
@@ -399,6 +442,16 @@ class KmerParcelsBuilder:
 
     def Records(self, first=0, n=None):
         return self._kc.counts(first, n)
+
+    def Batches(self, first=0, n=None):
+        """The batches of k-mers [first, first+n): (kmers, run_off, read_id, pos) -- k-mer i's instances are
+        (read_id, pos)[run_off[i]:run_off[i+1]] (KmerParcels' "k-mer + list of (read id, position)")."""
+        if not self._occ:
+            self._kc.build_occurrences()
+            self._occ = True
+        k, _ = self._kc.counts(first, n)
+        ro, rid, pos = self._kc.occurrences(first, n)
+        return k, ro, rid, pos
 
     def close(self):
         self._kc.close()

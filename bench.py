@@ -166,7 +166,8 @@ def workload_config(n_gpus):
                         % (GENOME_PER_GPU // 1_000_000, READS_PER_GPU // 1_000_000, READ_LEN,
                            READS_PER_GPU * READ_LEN // GENOME_PER_GPU, K),
             "K": K, "reads_per_gpu": READS_PER_GPU, "read_len": READ_LEN, "genome_len": GENOME_PER_GPU * n_gpus,
-            "sharding": "hash(canonical k-mer) %% %d, NCCL all-to-all" % n_gpus if n_gpus > 1 else "single GPU",
+            "sharding": ("canonical k-mer prefix ranges over %d ranks (balanced splitters), one exchange fused into "
+                         "the gather kernel over NVLink peer memory" % n_gpus) if n_gpus > 1 else "single GPU",
             "l2_policy": "inputs (1.5 GB packed reads, 36 GB keys) exceed the 126 MB L2; no flush needed"}
 
 
@@ -288,6 +289,21 @@ def run_ours(args):
     # exact size-independent invariant: sum f * spectrum[f] == instances
     inv_ok = int((spec * np.arange(len(spec), dtype=np.uint64)).sum()) == n_inst_total
 
+    # ---------------- occurrence records (SortKmers / KmerParcels payload): second sweep over the reads, N=1 only.
+    # Not part of the headline step; reported beside it.
+    records = None
+    if world == 1 and os.environ.get("APGK_BENCH_RECORDS", "1") != "0":
+        kc.build_occurrences()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        info = kc.build_occurrences()
+        torch.cuda.synchronize()
+        dt_r = time.perf_counter() - t0
+        records = {"what": "(read id, signed position) of every k-mer instance grouped by k-mer: table lookup sweep + per-run sort",
+                   "ms": round(dt_r * 1e3, 2), "value": round(info["n_occ"] / dt_r / 1e9, 3), "unit": "G records/s",
+                   "stage_ms": {k_: round(v, 2) for k_, v in info["ms"].items()}, "n_big_runs": info["n_big_runs"],
+                   "bytes_out": int(info["n_occ"]) * 8}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -338,6 +354,7 @@ def run_ours(args):
                          "sample": "first %d reads (%d k-mer instances) of the workload, oracle port "
                                    "(not the reference's code: parity unpinned)" % (CPU_SAMPLE_READS, cb_inst)},
         "geometry": geo, "shard_ms": dict({k_: round(v / args.steps, 2) for k_, v in shard_acc.items()}, **{k_: (list(v) if isinstance(v, tuple) else v) for k_, v in shard_info.items()}) if shard_acc else None,
+        "records": records,
         "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }

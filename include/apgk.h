@@ -19,6 +19,8 @@
  *   apgk_spectrum*       <- class KmerSpectrum (src/kmers/KmerSpectra.h [BJ name, U path])
  *   apgk_counts_*        <- the sorted (k-mer, frequency) records: vec<kmer_record>,
  *                           KmerParcelReader batches, KmerKmerFreq vectors [U]
+ *   apgk_*occurrences*   <- the (read id, signed position) payload of SortKmers' kmer records and
+ *                           KmerParcels' batches (src/kmers/KmerRecord.h, kmer_parcels/ [U])
  *   apgk_lookup*, apgk_read_freqs*
  *                        <- the k-mer frequency tables FindErrors queries per read
  *                           position (src/paths/FindErrors*.cc [BJ name, U path])
@@ -128,6 +130,27 @@ int apgk_lookup(apgk_ctx* ctx, const uint64_t* kmers, uint64_t n, int canonicali
  * 0xFFFFFFFF where the window crosses a read end.  out is a HOST buffer of n_bases entries. */
 int apgk_read_freqs(apgk_ctx* ctx, uint64_t first_base, uint64_t n_bases, uint32_t* out);
 
+/* ---- k-mer occurrence records: the payload half of the reference's SortKmers records (k-mer, read id,
+ * signed position) and KmerParcels batches (k-mer + list of (read id, position)) [BJ names, U layout;
+ * SURVEY.md section 8(a) rows 1-2, 8(f) rank 2].  Needs a context finished by apgk_finish with
+ * APGK_WANT_COUNTS whose read store is still in place.  For distinct k-mer i of the sorted table, its
+ * count[i] instances occupy slots [run_off[i], run_off[i+1]) of the occurrence list, ascending by
+ * (read id, position); run_off[n_distinct] == n_instances.  Read ids number the reads in the order they
+ * were added (reads without bases included).  pos is 1-based within the read and NEGATIVE when the
+ * canonical form is the reverse complement of the read's window (a palindrome counts as forward). */
+int apgk_build_occurrences(apgk_ctx* ctx);
+/* n_occ = n_instances; n_big_runs = runs sorted by the CTA-wide network (> 256 instances);
+ * ms4 = device milliseconds of {run-offset scan, fill sweep, per-run sort, big-run sort}. */
+int apgk_occurrences_info(const apgk_ctx* ctx, uint64_t* n_occ, uint64_t* n_big_runs, float* ms4);
+/* DEVICE pointers, library-owned until the next finish / reset: run offsets (uint64[n_distinct+1]) and
+ * the occurrences encoded as (global base position in the read store << 1) | canonical_is_reverse. */
+int apgk_occurrences_device(apgk_ctx* ctx, const uint64_t** d_run_off, const uint64_t** d_occ, uint64_t* n_occ);
+/* HOST copies for k-mers [first_kmer, first_kmer + n_kmers): run_off_out[n_kmers+1] (absolute slots; may
+ * be NULL), and read_id_out / pos_out for slots [run_off[first_kmer], run_off[first_kmer+n_kmers)) (both
+ * NULL = offsets only, to size the buffers). */
+int apgk_occurrences_copy(apgk_ctx* ctx, uint64_t first_kmer, uint64_t n_kmers, uint64_t* run_off_out,
+                          uint32_t* read_id_out, int32_t* pos_out);
+
 /* ---- multi-GPU building blocks (one context per rank; the exchange itself is the caller's,
  * e.g. NCCL all-to-all).  Canonical k-mers are owned by rank hash(kmer) % n_ranks. */
 /* Pass 1: per-owner instance counts of this rank's reads (counts_out[n_ranks], host). */
@@ -229,6 +252,10 @@ int apgk_debug_host_canonical(int K, const uint64_t* kmers, uint64_t n, uint64_t
 /* level-0 digit (top D bits of the canonical k-mer) of every window start, via the cheap top-bits identity */
 int apgk_debug_host_topdigits(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, int D,
                               uint32_t* digits_out /* total_bases */);
+/* table_find_index (the interpolated search of the lookups) on the HOST over a sorted key array with a
+ * prefix index of prefix_bits bits built here; idx_out[i] = index of query i or UINT64_MAX. */
+int apgk_debug_host_table_find(int K, const uint64_t* sorted_kmers, uint64_t n, int prefix_bits, const uint64_t* queries,
+                               uint64_t n_q, uint64_t* idx_out);
 int apgk_debug_host_synth(const apgk_synth_params* p, uint64_t r0, uint64_t n_reads, uint8_t* packed_out);
 
 #ifdef __cplusplus

@@ -137,7 +137,40 @@ void SortKmers(const vecbasevector& reads, std::vector<kmer_count<(2 * K + 63) /
   }
 }
 
-// `KmerParcelsBuilder`: construct, Build(), then read totals / spectrum / records.
+// One record of the full SortKmers output: one per k-mer INSTANCE.  pos is 1-based in the read and
+// negative when the canonical k-mer is the reverse complement of the read's window.
+template <int W>
+struct kmer_record {
+  uint64_t kmer[W];
+  uint32_t read_id;
+  int32_t pos;
+};
+
+// `SortKmers`, record form: every instance, ascending by k-mer, ties by (read id, position).
+template <int K>
+void SortKmers(const vecbasevector& reads, std::vector<kmer_record<(2 * K + 63) / 64>>& R, int device = 0) {
+  constexpr int W = (2 * K + 63) / 64;
+  Engine e(K, /*want_counts=*/true, device);
+  e.AddReads(reads);
+  e.Finish();
+  e.ck(apgk_build_occurrences(e.ctx()));
+  uint64_t ni = 0, nd = 0;
+  e.ck(apgk_totals(e.ctx(), &ni, &nd));
+  std::vector<uint64_t> k(nd * W + 1), off(nd + 1);
+  std::vector<uint32_t> id(ni + 1);
+  std::vector<int32_t> pos(ni + 1);
+  e.ck(apgk_counts_copy(e.ctx(), 0, nd, k.data(), nullptr));
+  e.ck(apgk_occurrences_copy(e.ctx(), 0, nd, off.data(), id.data(), pos.data()));
+  R.resize(ni);
+  for (uint64_t i = 0; i < nd; i++)
+    for (uint64_t s = off[i]; s < off[i + 1]; s++) {
+      for (int j = 0; j < W; j++) R[s].kmer[j] = k[i * W + j];
+      R[s].read_id = id[s];
+      R[s].pos = pos[s];
+    }
+}
+
+// `KmerParcelsBuilder`: construct, Build(), then read totals / spectrum / records / batches.
 class KmerParcelsBuilder {
  public:
   KmerParcelsBuilder(int K, const vecbasevector& reads, int /*n_threads: the GPU decides*/ = 0, int device = 0)
@@ -150,11 +183,23 @@ class KmerParcelsBuilder {
   void Records(uint64_t first, uint64_t n, uint64_t* kmers_out, uint32_t* counts_out) const {
     e_.ck(apgk_counts_copy(e_.ctx(), first, n, kmers_out, counts_out));
   }
+  // batches of k-mers [first, first+n): k-mer first+i occurs at (read_ids, positions)[run_off[i]-run_off[0] ...
+  // run_off[i+1]-run_off[0]); run_off has n+1 entries
+  void Batches(uint64_t first, uint64_t n, std::vector<uint64_t>& run_off, std::vector<uint32_t>& read_ids,
+               std::vector<int32_t>& positions) {
+    if (!occ_) { e_.ck(apgk_build_occurrences(e_.ctx())); occ_ = true; }
+    run_off.assign(n + 1, 0);
+    e_.ck(apgk_occurrences_copy(e_.ctx(), first, n, run_off.data(), nullptr, nullptr));
+    const uint64_t m = run_off[n] - run_off[0];
+    read_ids.assign(m + 1, 0); positions.assign(m + 1, 0);
+    e_.ck(apgk_occurrences_copy(e_.ctx(), first, n, nullptr, read_ids.data(), positions.data()));
+    read_ids.resize(m); positions.resize(m);
+  }
   const Engine& engine() const { return e_; }
 
  private:
   Engine e_;
-  bool built_ = false;
+  bool built_ = false, occ_ = false;
 };
 
 // The k-mer frequency table error correction queries.

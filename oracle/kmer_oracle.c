@@ -395,6 +395,61 @@ void oracle_read_freqs(const uint8_t* packed, const uint64_t* off, uint64_t n_re
   }
 }
 
+/* Occurrence records: the (read id, signed position) payload of every k-mer instance, grouped by
+ * canonical k-mer in table order (kmers = the sorted distinct k-mers oracle_count returned) and, inside
+ * a k-mer's run, ascending by (read id, position).  pos is 1-based in the read, negative when the
+ * canonical form is the reverse complement of the read's window, positive otherwise (palindromes
+ * included).  run_off_out[n_distinct + 1]; read_id_out / pos_out hold one entry per instance.
+ * Restates the record layout SURVEY.md section 8(a) attributes to SortKmers / KmerParcels ([U]: no
+ * reference source was available -- parity unpinned).  Reads are walked in order, so each run fills
+ * in (read id, position) order by construction. */
+int oracle_occurrences(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, int K, const uint64_t* kmers,
+                       uint64_t n_distinct, uint64_t* run_off_out, uint32_t* read_id_out, int32_t* pos_out) {
+  if (K < 1 || K > 32 * MAXW) return -1;
+  int W = (2 * K + 63) / 64;
+  int topbits = 2 * K - 64 * (W - 1);
+  uint64_t topmask = topbits == 64 ? ~0ull : ((1ull << topbits) - 1);
+  int topshift = topbits - 2;
+  uint64_t* cur = (uint64_t*)calloc(n_distinct + 1, 8);
+  if (!cur) return -2;
+  for (int pass = 0; pass < 2; pass++) {
+    for (uint64_t r = 0; r < n_reads; r++) {
+      uint64_t b0 = off[r], b1 = off[r + 1];
+      if (b1 - b0 < (uint64_t)K) continue;
+      uint64_t fw[MAXW] = {0, 0, 0, 0}, rc[MAXW] = {0, 0, 0, 0};
+      for (uint64_t q = b0; q < b1; q++) {
+        uint32_t b = get_base(packed, q);
+        roll_fw(fw, W, topmask, b);
+        roll_rc(rc, W, topshift, b);
+        if (q - b0 + 1 < (uint64_t)K) continue;
+        int use_rc = cmp_w(rc, fw, W) < 0;
+        const uint64_t* c = use_rc ? rc : fw;
+        uint64_t lo = 0, hi = n_distinct;
+        while (lo < hi) {
+          uint64_t mid = (lo + hi) / 2;
+          if (cmp_w(kmers + mid * W, c, W) < 0) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= n_distinct || cmp_w(kmers + lo * W, c, W) != 0) { free(cur); return -3; }
+        if (pass == 0) {
+          cur[lo]++;
+        } else {
+          uint64_t slot = cur[lo]++;
+          int32_t p1 = (int32_t)(q - b0 + 1 - (uint64_t)K) + 1;
+          read_id_out[slot] = (uint32_t)r;
+          pos_out[slot] = use_rc ? -p1 : p1;
+        }
+      }
+    }
+    if (pass == 0) {
+      uint64_t run = 0;
+      for (uint64_t i = 0; i < n_distinct; i++) { uint64_t v = cur[i]; run_off_out[i] = run; cur[i] = run; run += v; }
+      run_off_out[n_distinct] = run;
+    }
+  }
+  free(cur);
+  return 0;
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

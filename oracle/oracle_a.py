@@ -60,6 +60,9 @@ def lib():
                                         C.c_uint64, C.c_void_p]
         L.oracle_canonical.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_occurrences.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_occurrences.restype = C.c_int
         _lib = L
     return _lib
 
@@ -137,6 +140,24 @@ def read_freqs(packed, off, K, kmers, counts):
     lib().oracle_read_freqs(packed.ctypes.data, off.ctypes.data, len(off) - 1, K, kmers.ctypes.data,
                             counts.ctypes.data, len(counts), out.ctypes.data)
     return out[:total]
+
+
+def occurrences(packed, off, K, kmers, n_instances):
+    """-> (run_off uint64[n_distinct+1], read_id uint32[n_instances], pos int32[n_instances]): the instances of
+    every distinct k-mer of `kmers` (table order), ascending by (read id, position) inside a k-mer; pos is
+    1-based, negative when the canonical form is the reverse complement of the read's window."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    nd = kmers.size // n_words(K)
+    run_off = np.zeros(nd + 1, dtype=np.uint64)
+    rid = np.zeros(max(n_instances, 1), dtype=np.uint32)
+    pos = np.zeros(max(n_instances, 1), dtype=np.int32)
+    rc = lib().oracle_occurrences(packed.ctypes.data, off.ctypes.data, len(off) - 1, K, kmers.ctypes.data, nd,
+                                  run_off.ctypes.data, rid.ctypes.data, pos.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle_occurrences failed rc=%d" % rc)
+    return run_off, rid[:n_instances], pos[:n_instances]
 
 
 def canonical(kmer_words, K):

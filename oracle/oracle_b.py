@@ -55,3 +55,16 @@ def spectrum(pairs):
     for _, n in pairs:
         s[n] += 1
     return s
+
+
+def occurrences(reads, K):
+    """-> sorted list of (kmer_int, [(read_id, signed_pos), ...]): every instance of every canonical k-mer,
+    instances in (read id, position) order; signed_pos is 1-based, negative when the canonical string is the
+    reverse complement of the read's window (a palindrome is forward)."""
+    d = {}
+    for r, s in enumerate(reads):
+        for p in range(0, len(s) - K + 1):
+            w = s[p:p + K]
+            c = canonical_str(w)
+            d.setdefault(c, []).append((r, (p + 1) if c == w else -(p + 1)))
+    return sorted((kmer_to_int(k), v) for k, v in d.items())

@@ -17,6 +17,13 @@ int main() {
     REQUIRE(R.size() == 2 && R[0].kmer[0] == 1 && R[0].count == 2 && R[1].kmer[0] == 6 && R[1].count == 1);
     KmerSpectrum s(2); s.FromReads(r);
     REQUIRE(s.size() == 3 && s[1] == 1 && s[2] == 1 && s.NumInstances() == 3 && s.NumDistinct() == 2);
+    // record form: AC at +1 (forward) and at -3 (GT read backwards), the palindrome CG at +2
+    std::vector<kmer_record<1>> Q;
+    SortKmers<2>(r, Q);
+    REQUIRE(Q.size() == 3);
+    REQUIRE(Q[0].kmer[0] == 1 && Q[0].read_id == 0 && Q[0].pos == 1);
+    REQUIRE(Q[1].kmer[0] == 1 && Q[1].read_id == 0 && Q[1].pos == -3);
+    REQUIRE(Q[2].kmer[0] == 6 && Q[2].read_id == 0 && Q[2].pos == 2);
   }
   {  // GATTACA + its reverse complement, K=4 -> four k-mers, each seen twice
     vecbasevector r; r.push_back("GATTACA"); r.push_back("TGTAATC");
@@ -29,6 +36,17 @@ int main() {
     for (int i = 0; i < 4; i++) REQUIRE(k[i] == want[i] && c[i] == 2);
     KmerSpectrum s = b.Spectrum();
     REQUIRE(s.size() == 3 && s[2] == 4);
+    // batches: every k-mer once in each read, on opposite strands, at mirrored positions (p+1) + (4-p) = 5
+    std::vector<uint64_t> off; std::vector<uint32_t> ids; std::vector<int32_t> pos;
+    b.Batches(0, 4, off, ids, pos);
+    REQUIRE(off.size() == 5 && ids.size() == 8 && pos.size() == 8);
+    for (int i = 0; i < 4; i++) {
+      REQUIRE(off[i + 1] - off[i] == 2);
+      const uint64_t o = off[i] - off[0];
+      REQUIRE(ids[o] == 0 && ids[o + 1] == 1);
+      REQUIRE((pos[o] > 0) != (pos[o + 1] > 0));
+      REQUIRE(std::abs(pos[o]) + std::abs(pos[o + 1]) == 5);
+    }
   }
   {  // frequency table: random reads, K=24; every window's frequency >= 1, and equals Freq() of that window
     std::mt19937_64 g(7);

@@ -41,6 +41,68 @@ HAND = [
 ]
 
 
+# ---- (a2) hand-computed OCCURRENCE records: per k-mer (table order) the list of (read id, signed position);
+# position 1-based, negative when the canonical k-mer is the reverse complement of the read's window.
+OCC_HAND = [
+    # ACGT K=2: AC forward at 1; GT at 3 is AC read backwards; the palindrome CG counts as forward.
+    dict(reads=["ACGT"], K=2, kmers=[1, 6], occ=[[[0, 1], [0, -3]], [[0, 2]]]),
+    # GATTACA: GATT->AATC(rc) ATTA(fw) TTAC->GTAA(rc) TACA(fw); TGTAATC: TGTA->TACA(rc) GTAA(fw) TAAT->ATTA(rc) AATC(fw)
+    dict(reads=["GATTACA", "TGTAATC"], K=4, kmers=[13, 60, 176, 196],
+         occ=[[[0, -1], [1, 4]], [[0, 2], [1, -3]], [[0, -3], [1, 2]], [[0, 4], [1, -1]]]),
+    # a read shorter than K still owns read id 0
+    dict(reads=["AC", "ACG"], K=3, kmers=[6], occ=[[[1, 1]]]),
+    # reads without bases keep their ids; TT is AA read backwards
+    dict(reads=["", "AAAA", "", "TTTT"], K=2, kmers=[0], occ=[[[1, 1], [1, 2], [1, 3], [3, -1], [3, -2], [3, -3]]]),
+]
+
+
+def occ_digest(run_off, rid, pos):
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(run_off, dtype=np.uint64).tobytes())
+    h.update(np.ascontiguousarray(rid, dtype=np.uint32).tobytes())
+    h.update(np.ascontiguousarray(pos, dtype=np.int32).tobytes())
+    return h.hexdigest()
+
+
+def occ_from_b(reads, K):
+    """oracle B's occurrences flattened to oracle A's array form."""
+    ob = B.occurrences(reads, K)
+    ro = np.zeros(len(ob) + 1, dtype=np.uint64)
+    rid, pos = [], []
+    for i, (_, lst) in enumerate(ob):
+        ro[i + 1] = ro[i] + np.uint64(len(lst))
+        rid += [r for r, _ in lst]
+        pos += [q for _, q in lst]
+    return [k for k, _ in ob], ro, np.array(rid, dtype=np.uint32), np.array(pos, dtype=np.int32)
+
+
+def check_occ_hand(v):
+    kb, ro, rid, pos = occ_from_b(v["reads"], v["K"])
+    assert kb == v["kmers"], (v, kb)
+    flat = [x for lst in v["occ"] for x in lst]
+    assert [int(x) for x in ro] == [0] + list(np.cumsum([len(l) for l in v["occ"]])), (v, ro)
+    assert [[int(a), int(b)] for a, b in zip(rid, pos)] == flat, (v, rid, pos)
+    p, o = A.pack_strings(v["reads"])
+    k, c, n = A.count(p, o, v["K"])
+    aro, arid, apos = A.occurrences(p, o, v["K"], k, n)
+    assert (aro == ro).all() and (arid == rid).all() and (apos == pos).all(), (v, aro, arid, apos)
+
+
+def occ_synth_vector(s):
+    sp = A.synth_params(s["genome_len"], s["read_len"])
+    p, o = A.synth_reads(sp, 0, s["n_reads"])
+    k, c, n = A.count(p, o, s["K"])
+    aro, arid, apos = A.occurrences(p, o, s["K"], k, n)
+    _, ro, rid, pos = occ_from_b(B.unpack_reads(p, o), s["K"])
+    assert (aro == ro).all() and (arid == rid).all() and (apos == pos).all(), "oracles disagree on occurrences"
+    out = dict(s)
+    out.update(n_instances=int(n), n_distinct=len(k), occ_sha256=occ_digest(aro, arid, apos),
+               first_occ=[[int(a), int(b)] for a, b in zip(arid[:4], apos[:4])])
+    return out
+
+
 def check_hand(v):
     pairs = B.count_reads(v["reads"], v["K"])
     assert [k for k, _ in pairs] == v["kmers"], (v, pairs)
@@ -82,8 +144,11 @@ def synth_vector(s):
 def main():
     for v in HAND:
         check_hand(v)
+    for v in OCC_HAND:
+        check_occ_hand(v)
     out = dict(note="parity unpinned: hand-computed + two-oracle-agreement vectors, not reference outputs",
-               hand=HAND, synth=[synth_vector(s) for s in SYNTH])
+               hand=HAND, synth=[synth_vector(s) for s in SYNTH], occ_hand=OCC_HAND,
+               occ_synth=[occ_synth_vector(s) for s in (SYNTH[0], SYNTH[2], SYNTH[3])])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "known_answers.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)

@@ -156,3 +156,41 @@ def test_kmer_spectrum_text_roundtrip(tmp_path):
     assert s.n_distinct() == 49 and s.n_instances() == 10 + 6 + 35 + 120 + 63
     est = s.estimate(read_len=100)
     assert est["kmer_coverage"] == 6.0
+
+
+@pytest.mark.parametrize("K,P", [(25, 20), (25, 8), (13, 10), (5, 12), (3, 4), (31, 16), (32, 12), (33, 10), (48, 14), (64, 20), (96, 11)])
+def test_table_search_on_host(apgk_lib, K, P):
+    """table_find_index (prefix index + interpolated start + galloping bracket + binary search: the search
+    every frequency-table lookup and the occurrence sweep run on the device) executed on the host, against
+    a dict, for uniform and heavily skewed key sets, hits and misses."""
+    rng = np.random.default_rng(K * 131 + P)
+    W = (2 * K + 63) // 64
+    bits = 2 * K
+    for n in (0, 1, 5, 17, 40, 1000, 60000):
+        if W == 1:
+            keys = np.unique(rng.integers(0, 1 << min(bits, 63), size=n, dtype=np.uint64)).reshape(-1, 1)
+        else:
+            top = bits - 64 * (W - 1)
+            cols = [rng.integers(0, 1 << min(top, 62), size=n, dtype=np.uint64)]
+            cols += [rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+                     for _ in range(W - 1)]
+            if n > 10:
+                cols[0][: n // 2] = cols[0][0]   # half the keys in one prefix bucket, clustered
+            keys = np.unique(np.stack(cols, 1), axis=0)
+        m = len(keys)
+        if m == 0:
+            qs = np.zeros((3, W), dtype=np.uint64)
+        else:
+            miss = keys.copy()
+            miss[:, -1] ^= np.uint64(1)
+            qs = np.concatenate([keys, miss])
+            if W == 1 and bits < 64:
+                qs = qs[qs[:, 0] < np.uint64(1 << bits)]
+        qs = np.ascontiguousarray(qs)
+        keys = np.ascontiguousarray(keys)
+        out = np.zeros(len(qs), dtype=np.uint64)
+        assert apgk_lib.apgk_debug_host_table_find(K, keys.ctypes.data if m else None, m, min(P, 2 * K) if W > 1 else P,
+                                                  qs.ctypes.data, len(qs), out.ctypes.data) == 0
+        d = {tuple(k): i for i, k in enumerate(keys.tolist())}
+        exp = np.array([d.get(tuple(x), 2 ** 64 - 1) for x in qs.tolist()], dtype=np.uint64)
+        assert (out == exp).all(), (K, P, n)

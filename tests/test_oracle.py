@@ -90,3 +90,53 @@ def test_lookup_and_read_freqs(oracle):
     valid = rf != np.uint64(0xFFFFFFFFFFFFFFFF)
     assert valid.sum() == 300 * (80 - K + 1)
     assert (rf[valid] >= 1).all()
+
+
+# ------------------------------------------------------------------ occurrence records (read id, signed position)
+def _occ_lists(run_off, rid, pos):
+    return [[[int(a), int(b)] for a, b in zip(rid[int(run_off[i]):int(run_off[i + 1])], pos[int(run_off[i]):int(run_off[i + 1])])]
+            for i in range(len(run_off) - 1)]
+
+
+@pytest.mark.parametrize("v", GOLD["occ_hand"], ids=lambda v: "%s-K%d" % ("+".join(v["reads"]), v["K"]))
+def test_occurrence_hand_vectors(oracle, v):
+    p, o = oracle.pack_strings(v["reads"])
+    k, c, n = oracle.count(p, o, v["K"])
+    assert [_to_int(r) for r in k] == v["kmers"]
+    ro, rid, pos = oracle.occurrences(p, o, v["K"], k, n)
+    assert _occ_lists(ro, rid, pos) == v["occ"]
+    assert [[[r, q] for r, q in lst] for _, lst in B.occurrences(v["reads"], v["K"])] == v["occ"]
+
+
+@pytest.mark.parametrize("s", GOLD["occ_synth"], ids=lambda s: "G%d-K%d" % (s["genome_len"], s["K"]))
+def test_occurrence_synth_golden(oracle, s):
+    import hashlib
+
+    sp = oracle.synth_params(s["genome_len"], s["read_len"])
+    p, o = oracle.synth_reads(sp, 0, s["n_reads"])
+    k, c, n = oracle.count(p, o, s["K"])
+    ro, rid, pos = oracle.occurrences(p, o, s["K"], k, n)
+    assert n == s["n_instances"] and len(k) == s["n_distinct"]
+    h = hashlib.sha256(ro.tobytes() + rid.tobytes() + pos.tobytes()).hexdigest()
+    assert h == s["occ_sha256"]
+    assert (np.diff(ro.astype(np.int64)) == c.astype(np.int64)).all()  # run lengths are the counts
+
+
+@pytest.mark.parametrize("K", [1, 2, 7, 25, 32, 33, 64, 65, 96])
+def test_occurrences_a_matches_b(oracle, K):
+    rnd = random.Random(100 + K)
+    reads = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([0, 1, K - 1, K, K + 1, K + 9, 140]))) for _ in range(40)]
+    reads += ["", "A" * (K + 25), "ACGT" * 30, "CG" * (K + 3), ""]
+    reads.append(reads[4].translate(str.maketrans("ACGT", "TGCA"))[::-1])
+    p, o = oracle.pack_strings(reads)
+    k, c, n = oracle.count(p, o, K)
+    ro, rid, pos = oracle.occurrences(p, o, K, k, n)
+    ob = B.occurrences(reads, K)
+    assert [_to_int(r) for r in k] == [x for x, _ in ob]
+    assert _occ_lists(ro, rid, pos) == [[[r, q] for r, q in lst] for _, lst in ob]
+    # every record points at a window whose canonical form is its k-mer, on the strand its sign says
+    for i, (kv, lst) in enumerate(ob):
+        for r, q in lst:
+            w = reads[r][abs(q) - 1:abs(q) - 1 + K]
+            assert len(w) == K and B.kmer_to_int(B.canonical_str(w)) == kv
+            assert (q > 0) == (B.canonical_str(w) == w)
