@@ -84,11 +84,11 @@ struct apgk_ctx {
   bool finished = false, have_table = false;
   bool table_from_reads = false;   // the table counts exactly the windows of this context's read store
   // ---- occurrence records (apgk_build_occurrences): run offsets + (position << 1 | rc) per instance, in A
-  DevBuf occ_off, rank_cnt, rank_dir, empty_dev, occ_tmp;
+  DevBuf occ, occ_pos, occ_off, occ_cnt, occ_bstart, occ_bcur, rank_cnt, rank_dir, empty_dev, occ_tmp;
   bool have_occ = false;
   uint64_t n_occ = 0, n_big_runs = 0;
-  float occ_ms[4]{};
-  cudaEvent_t occ_ev[5]{};
+  float occ_ms[5]{};
+  cudaEvent_t occ_ev[6]{};
   std::vector<uint64_t> empty_nb;  // per read without bases: number of reads WITH bases before it
   uint64_t n_instances = 0, n_distinct = 0;
   KeyGeom geom{};
@@ -931,7 +931,9 @@ int scan_u32(apgk_ctx* c, const uint32_t* in, uint64_t n, unsigned long long* ou
 }
 
 // ---------------------------------------------------------------- occurrence records
-template <int W>
+static const bool kOccDirect = getenv("APGK_OCC_DIRECT") != nullptr;  // first version: lookup + slot + store straight from the sweep
+
+template <int W, typename Elem>
 int build_occurrences_impl(apgk_ctx* c) {
   const uint64_t N = c->n_instances, D = c->n_distinct;
   c->have_occ = false; c->n_occ = 0; c->n_big_runs = 0;
@@ -945,37 +947,69 @@ int build_occurrences_impl(apgk_ctx* c) {
     c->have_occ = true;
     return APGK_OK;
   }
+  unsigned long long* run_off = c->occ_off.as<unsigned long long>();
   // run offsets = exclusive scan of the counts
   CU(cudaEventRecord(c->occ_ev[0], c->stream));
   unsigned long long total = 0;
-  { int rc = scan_u32(c, c->out_cnt.as<uint32_t>(), D, c->occ_off.as<unsigned long long>(), &total); if (rc) return rc; }
+  { int rc = scan_u32(c, c->out_cnt.as<uint32_t>(), D, run_off, &total); if (rc) return rc; }
   if (total != N) FAIL(APGK_E_RANGE, "occurrences: counts sum to %llu, instances %llu (a count saturated)", total, (unsigned long long)N);
-  // A (level-0 keys, dead after finish) holds the occurrences, T the per-run cursors, B the big-run list
-  const size_t list_cap = (size_t)(N / OCC_SMALL_MAX) + 1;
-  CU(c->A.ensure(N * 8));
+  // Buffers.  The pipeline's A / B / T are dead after finish and reused: elements in B (32-bit remainders) or A
+  // (full keys), the positions on their way to their bucket in A or occ_pos, the per-run cursors of the
+  // global-table path in T, the big-run list in B once the placement is done.
+  constexpr bool U32 = sizeof(Elem) == 4;
+  const uint32_t nb = c->nb1;
+  CU(c->occ.ensure(N * 8));
   CU(c->T.ensure(D * 4));
-  CU(c->B.ensure((list_cap + 4) * 8));
-  unsigned long long* counters = c->B.as<unsigned long long>();
+  CU(c->occ_cnt.ensure(64));
+  unsigned long long* counters = c->occ_cnt.as<unsigned long long>();
   CU(cudaMemsetAsync(c->T.p, 0, D * 4, c->stream));
   CU(cudaMemsetAsync(counters, 0, 32, c->stream));
-  CU(cudaEventRecord(c->occ_ev[1], c->stream));
-  {
-    constexpr int NT = 128;
-    const uint64_t threads = (c->total_bases + POS_PER_THREAD - 1) / POS_PER_THREAD;
-    k_occ_fill<W, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(
-        read_store(c), freq_table<W>(c), c->occ_off.as<unsigned long long>(), c->T.as<uint32_t>(),
-        c->A.as<unsigned long long>(), counters);
+  unsigned long long* occ = c->occ.as<unsigned long long>();
+  const uint64_t threads = (c->total_bases + POS_PER_THREAD - 1) / POS_PER_THREAD;
+  constexpr int NT = 128;
+  if (kOccDirect) {
+    CU(cudaEventRecord(c->occ_ev[1], c->stream));
+    k_occ_fill<W, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(read_store(c), freq_table<W>(c), run_off,
+                                                                               c->T.as<uint32_t>(), occ, counters);
+    LAUNCHED();
+    CU(cudaEventRecord(c->occ_ev[2], c->stream));
+  } else {
+    Elem* elems;
+    unsigned long long* pos_tmp;
+    if (U32) {
+      CU(c->B.ensure(N * 4));
+      CU(c->A.ensure(N * 8));
+      elems = c->B.as<Elem>(); pos_tmp = c->A.as<unsigned long long>();
+    } else {
+      CU(c->A.ensure(N * sizeof(Elem)));
+      CU(c->occ_pos.ensure(N * 8));
+      elems = c->A.as<Elem>(); pos_tmp = c->occ_pos.as<unsigned long long>();
+    }
+    CU(c->occ_bstart.ensure(((size_t)nb + 1) * 8));
+    CU(c->occ_bcur.ensure((size_t)nb * 8));
+    CU(cudaMemsetAsync(c->occ_bcur.p, 0, (size_t)nb * 8, c->stream));
+    k_occ_bstart<<<(nb + 1 + 255) / 256, 256, 0, c->stream>>>(c->out_off.as<unsigned long long>(), run_off, nb,
+                                                           c->occ_bstart.as<unsigned long long>());
+    LAUNCHED();
+    CU(cudaEventRecord(c->occ_ev[1], c->stream));
+    k_occ_scatter<W, Elem, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(
+        read_store(c), freq_table<W>(c), c->occ_bstart.as<unsigned long long>(), c->occ_bcur.as<unsigned long long>(), elems,
+        pos_tmp, counters);
+    LAUNCHED();
+    CU(cudaEventRecord(c->occ_ev[2], c->stream));
+    k_occ_place<W, Elem, OCC_PLACE_NT><<<std::min<uint32_t>(nb, (uint32_t)c->n_sm * 8), OCC_PLACE_NT, 0, c->stream>>>(
+        freq_table<W>(c), run_off, c->occ_bstart.as<unsigned long long>(), elems, pos_tmp, c->T.as<uint32_t>(), occ, counters);
     LAUNCHED();
   }
-  CU(cudaEventRecord(c->occ_ev[2], c->stream));
-  k_occ_sort_small<<<(unsigned)((D + 127) / 128), 128, 0, c->stream>>>(c->occ_off.as<unsigned long long>(), D,
-                                                                      c->A.as<unsigned long long>(), counters + 4, counters);
-  LAUNCHED();
   CU(cudaEventRecord(c->occ_ev[3], c->stream));
-  k_occ_sort_big<OCC_BIG_NT><<<c->n_sm * 2, OCC_BIG_NT, 0, c->stream>>>(c->occ_off.as<unsigned long long>(), counters + 4, counters,
-                                                                      c->A.as<unsigned long long>());
+  const size_t list_cap = (size_t)(N / OCC_SMALL_MAX) + 1;
+  CU(c->B.ensure(list_cap * 8));
+  k_occ_sort_small<<<(unsigned)((D + 127) / 128), 128, 0, c->stream>>>(run_off, D, occ, c->B.as<unsigned long long>(), counters);
   LAUNCHED();
   CU(cudaEventRecord(c->occ_ev[4], c->stream));
+  k_occ_sort_big<OCC_BIG_NT><<<c->n_sm * 2, OCC_BIG_NT, 0, c->stream>>>(run_off, c->B.as<unsigned long long>(), counters, occ);
+  LAUNCHED();
+  CU(cudaEventRecord(c->occ_ev[5], c->stream));
   // rank directory over the start bitmap: read id of a global base position
   {
     const uint64_t words = (c->total_bases + 31) / 32;
@@ -995,7 +1029,7 @@ int build_occurrences_impl(apgk_ctx* c) {
   unsigned long long h[3] = {0, 0, 0};
   CU(cudaMemcpyAsync(h, counters, 24, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->occ_ms[i], c->occ_ev[i], c->occ_ev[i + 1]);
+  for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->occ_ms[i], c->occ_ev[i], c->occ_ev[i + 1]);
   if (h[1] || h[2])
     FAIL(APGK_E_STATE, "occurrences: %llu windows missing from the table, %llu slots past a run (table does not match the read store)",
          h[1], h[2]);
@@ -1023,7 +1057,7 @@ int occurrences_copy_impl(apgk_ctx* c, uint64_t first, uint64_t n_kmers, uint64_
     const uint64_t m = std::min(CH, n - done);
     int32_t* d_pos = (int32_t*)(d_id + m);
     k_occ_translate<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(
-        c->A.as<unsigned long long>() + o0 + done, m, c->starts.as<uint32_t>(), c->rank_dir.as<unsigned long long>(),
+        c->occ.as<unsigned long long>() + o0 + done, m, c->starts.as<uint32_t>(), c->rank_dir.as<unsigned long long>(),
         c->empty_dev.as<unsigned long long>(), (uint32_t)c->empty_nb.size(), d_id, d_pos);
     LAUNCHED();
     if (read_id_out) CU(cudaMemcpyAsync(read_id_out + done, d_id, m * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1297,7 +1331,8 @@ void apgk_destroy(apgk_ctx* c) {
                    &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
                    &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc, &c->deferred,
                    &c->out_keys, &c->out_cnt, &c->owner_plan_dev, &c->piece_off, &c->piece_tmp, &c->piece_ptrs, &c->C2, &c->sub_sizes,
-                   &c->occ_off, &c->rank_cnt, &c->rank_dir, &c->empty_dev, &c->occ_tmp};
+                   &c->occ, &c->occ_pos, &c->occ_off, &c->occ_cnt, &c->occ_bstart, &c->occ_bcur, &c->rank_cnt, &c->rank_dir, &c->empty_dev,
+                   &c->occ_tmp};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->occ_ev) if (e) cudaEventDestroy(e);
   for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
@@ -1670,19 +1705,19 @@ int apgk_build_occurrences(apgk_ctx* c) {
   if (c->n_reads > 0xFFFFFFFFull) FAIL(APGK_E_RANGE, "occurrences: read ids are 32-bit, %llu reads", (unsigned long long)c->n_reads);
   CU(cudaSetDevice(c->device));
   switch (c->W) {
-    case 1: return build_occurrences_impl<1>(c);
-    case 2: return build_occurrences_impl<2>(c);
-    case 3: return build_occurrences_impl<3>(c);
+    case 1: return c->geom.REM <= 32 ? build_occurrences_impl<1, uint32_t>(c) : build_occurrences_impl<1, Key<1>>(c);
+    case 2: return build_occurrences_impl<2, Key<2>>(c);
+    case 3: return build_occurrences_impl<3, Key<3>>(c);
   }
   return APGK_E_ARG;
 }
 
-int apgk_occurrences_info(const apgk_ctx* c, uint64_t* n_occ, uint64_t* n_big_runs, float* ms4) {
+int apgk_occurrences_info(const apgk_ctx* c, uint64_t* n_occ, uint64_t* n_big_runs, float* ms5) {
   if (!c) return APGK_E_ARG;
   if (!c->have_occ) return APGK_E_STATE;
   if (n_occ) *n_occ = c->n_occ;
   if (n_big_runs) *n_big_runs = c->n_big_runs;
-  if (ms4) for (int i = 0; i < 4; i++) ms4[i] = c->occ_ms[i];
+  if (ms5) for (int i = 0; i < 5; i++) ms5[i] = c->occ_ms[i];
   return APGK_OK;
 }
 
@@ -1690,7 +1725,7 @@ int apgk_occurrences_device(apgk_ctx* c, const uint64_t** d_run_off, const uint6
   if (!c) return APGK_E_ARG;
   if (!c->have_occ) FAIL(APGK_E_STATE, "no occurrences: call apgk_build_occurrences first");
   if (d_run_off) *d_run_off = c->occ_off.as<uint64_t>();
-  if (d_occ) *d_occ = c->n_occ ? c->A.as<uint64_t>() : nullptr;
+  if (d_occ) *d_occ = c->n_occ ? c->occ.as<uint64_t>() : nullptr;
   if (n_occ) *n_occ = c->n_occ;
   return APGK_OK;
 }

@@ -7,9 +7,17 @@
 // B200 formulation: the (k-mer, count) table already exists, so the payload is not carried through
 // the partition passes (that would double their HBM traffic).  Instead
 //   run_off   = exclusive scan of the counts                      (one run of slots per distinct k-mer)
-//   k_occ_fill: second sweep over the read store; every window looks its canonical k-mer up in the
-//               table (interpolated search, table.cuh), takes a slot of that k-mer's run with one
-//               atomic and stores (global base position << 1 | canonical-is-reverse)
+//   bstart[b] = run_off[index[b]]: the slots of prefix bucket b are one contiguous region
+//   k_occ_scatter: second sweep over the read store; every window goes to ITS BUCKET's region (one
+//               global atomic on the bucket's cursor -- 2^P counters, L2 resident) as an element
+//               (32-bit remainder or full key) plus (global base position << 1 | canonical-is-reverse)
+//   k_occ_place: one CTA per bucket; the bucket's table keys sit in shared memory as sorted
+//               remainders, every element finds its k-mer by binary search there, takes a slot of that
+//               k-mer's run with a shared-memory atomic and writes its position -- all global traffic
+//               is sequential per bucket.  Buckets with more keys than the shared table holds, and
+//               full-key elements, search the table in global memory instead (same result).
+//   (k_occ_fill, the first version, does lookup + slot + store straight from the sweep: every step a
+//    random DRAM access, 973 ms for 4.56 G instances; kept behind APGK_OCC_DIRECT=1 as a cross-check.)
 //   k_occ_sort_small / k_occ_sort_big: each run ascending by position.  The sweep visits positions
 //               in ascending order, so runs arrive almost sorted: one thread per run does an
 //               insertion sort that is linear on sorted input; runs above OCC_SMALL_MAX go to a
@@ -51,6 +59,113 @@ __global__ void __launch_bounds__(NT) k_occ_fill(ReadStore rs, FreqTable<W> t, c
       }
     }
   });
+}
+
+// ---------------------------------------------------------------- two-phase build: scatter to buckets, place per bucket
+constexpr int OCC_PLACE_NT = 256;
+constexpr uint32_t OCC_PLACE_CAP = 2048;   // distinct k-mers of a bucket the shared-memory table holds (24 KB)
+
+// level-1 element of a canonical k-mer: the remainder below the prefix (one-word keys, REM <= 32) or the key
+template <typename Elem, int W> struct OccElem;
+template <int W> struct OccElem<uint32_t, W> {
+  static APGK_HD uint32_t make(const Key<W>& c, int rem_bits, int pad) { return (uint32_t)((c.w[0] << pad) & lowmask64(rem_bits)); }
+  static APGK_HD Key<W> key(uint32_t e, uint32_t b, int rem_bits, int pad) {
+    Key<W> k;
+    k.w[0] = ((rem_bits >= 64 ? 0ull : ((uint64_t)b << rem_bits)) | e) >> pad;
+    return k;
+  }
+};
+template <int W> struct OccElem<Key<W>, W> {
+  static APGK_HD Key<W> make(const Key<W>& c, int, int) { return c; }
+  static APGK_HD Key<W> key(const Key<W>& e, uint32_t, int, int) { return e; }
+};
+
+// bstart[b] = first slot of prefix bucket b (b = 0 .. nb)
+__global__ void k_occ_bstart(const unsigned long long* __restrict__ index, const unsigned long long* __restrict__ run_off,
+                             uint32_t nb, unsigned long long* __restrict__ bstart) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= nb) bstart[b] = run_off[index[b]];
+}
+
+template <int W, typename Elem, int NT>
+__global__ void __launch_bounds__(NT) k_occ_scatter(ReadStore rs, FreqTable<W> t, const unsigned long long* __restrict__ bstart,
+                                                    unsigned long long* __restrict__ bcur, Elem* __restrict__ elems,
+                                                    unsigned long long* __restrict__ pos_tmp,
+                                                    unsigned long long* __restrict__ counters) {
+  const uint64_t p = ((uint64_t)blockIdx.x * NT + threadIdx.x) * POS_PER_THREAD;
+  if (p >= rs.total_bases) return;
+  const uint32_t valid = window_valid_mask16(rs.starts32, p, rs.K, rs.total_bases);
+  if (!valid) return;
+  Window16<W> win;
+  load_window16<W>(rs.bases32, p, rs.K, win);
+  extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool use_rc) {
+    if ((valid >> j) & 1u) {
+      const uint32_t b = digit_of(c, t.prefix_pos, t.prefix_len, t.pad);
+      const unsigned long long o = bstart[b] + atomicAdd(&bcur[b], 1ull);
+      if (o < bstart[b + 1]) {
+        elems[o] = OccElem<Elem, W>::make(c, t.prefix_pos, t.pad);
+        pos_tmp[o] = ((p + (uint64_t)j) << 1) | (use_rc ? 1ull : 0ull);
+      } else {
+        atomicAdd(&counters[2], 1ull);
+      }
+    }
+  });
+}
+
+template <int W, typename Elem, int NT>
+__global__ void __launch_bounds__(NT) k_occ_place(FreqTable<W> t, const unsigned long long* __restrict__ run_off,
+                                                  const unsigned long long* __restrict__ bstart, const Elem* __restrict__ elems,
+                                                  const unsigned long long* __restrict__ pos_tmp, uint32_t* __restrict__ cursor,
+                                                  unsigned long long* __restrict__ occ, unsigned long long* __restrict__ counters) {
+  constexpr bool U32 = sizeof(Elem) == 4;
+  __shared__ uint32_t sh_rem[U32 ? OCC_PLACE_CAP : 1], sh_off[U32 ? OCC_PLACE_CAP : 1], sh_cur[U32 ? OCC_PLACE_CAP : 1];
+  for (uint32_t b = blockIdx.x; b < t.nb; b += gridDim.x) {
+    const unsigned long long e0 = bstart[b], n = bstart[b + 1] - e0;
+    if (!n) continue;
+    const unsigned long long t0 = t.index[b], d = t.index[b + 1] - t0;
+    bool in_sh = false;
+    if constexpr (U32) in_sh = d <= OCC_PLACE_CAP && n < (1ull << 32);
+    if (in_sh) {
+      if constexpr (U32) {
+        for (uint32_t j = threadIdx.x; j < (uint32_t)d; j += NT) {
+          sh_rem[j] = OccElem<Elem, W>::make(t.keys[t0 + j], t.prefix_pos, t.pad);
+          sh_off[j] = (uint32_t)(run_off[t0 + j] - e0);
+          sh_cur[j] = 0;
+        }
+        __syncthreads();
+        for (unsigned long long i = threadIdx.x; i < n; i += NT) {
+          const uint32_t r = elems[e0 + i];
+          const unsigned long long pv = pos_tmp[e0 + i];
+          uint32_t lo = 0, hi = (uint32_t)d;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sh_rem[mid] < r) lo = mid + 1; else hi = mid;
+          }
+          if (lo < (uint32_t)d && sh_rem[lo] == r) {
+            const uint32_t slot = atomicAdd(&sh_cur[lo], 1u);
+            const unsigned long long o = e0 + sh_off[lo] + slot;
+            if (o < run_off[t0 + lo + 1]) occ[o] = pv; else atomicAdd(&counters[2], 1ull);
+          } else {
+            atomicAdd(&counters[1], 1ull);
+          }
+        }
+        __syncthreads();
+      }
+    } else {
+      for (unsigned long long i = threadIdx.x; i < n; i += NT) {
+        const Key<W> c = OccElem<Elem, W>::key(elems[e0 + i], b, t.prefix_pos, t.pad);
+        const unsigned long long pv = pos_tmp[e0 + i];
+        const unsigned long long idx = table_find_index(t, c);
+        if (idx == ~0ull) {
+          atomicAdd(&counters[1], 1ull);
+        } else {
+          const uint32_t slot = atomicAdd(&cursor[idx], 1u);
+          const unsigned long long o = run_off[idx] + slot;
+          if (o < run_off[idx + 1]) occ[o] = pv; else atomicAdd(&counters[2], 1ull);
+        }
+      }
+    }
+  }
 }
 
 // One thread per run.  Insertion sort straight on the run: linear when it arrived sorted.

@@ -174,15 +174,15 @@ class KmerCounter:
     # -- occurrence records: (read id, signed position) of every instance, grouped by k-mer
     def build_occurrences(self):
         """Second sweep over the read store: every window takes a slot in its k-mer's run (needs finish()
-        with want_counts).  -> dict(n_occ, n_big_runs, ms={scan, fill, sort, sort_big})."""
+        with want_counts).  -> dict(n_occ, n_big_runs, ms={scan, scatter, place, sort, sort_big})."""
         self._ck(self._L.apgk_build_occurrences(self._h))
         return self.occurrences_info()
 
     def occurrences_info(self):
         n, nb = C.c_uint64(), C.c_uint64()
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 5)()
         self._ck(self._L.apgk_occurrences_info(self._h, C.byref(n), C.byref(nb), ms))
-        return dict(n_occ=n.value, n_big_runs=nb.value, ms=dict(zip(("scan", "fill", "sort", "sort_big"), [float(x) for x in ms])))
+        return dict(n_occ=n.value, n_big_runs=nb.value, ms=dict(zip(("scan", "scatter", "place", "sort", "sort_big"), [float(x) for x in ms])))
 
     def occurrences(self, first=0, n=None):
         """-> (run_off uint64[n+1] rebased to 0, read_id uint32[m], pos int32[m]) for k-mers [first, first+n) of

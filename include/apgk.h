@@ -140,8 +140,9 @@ int apgk_read_freqs(apgk_ctx* ctx, uint64_t first_base, uint64_t n_bases, uint32
  * canonical form is the reverse complement of the read's window (a palindrome counts as forward). */
 int apgk_build_occurrences(apgk_ctx* ctx);
 /* n_occ = n_instances; n_big_runs = runs sorted by the CTA-wide network (> 256 instances);
- * ms4 = device milliseconds of {run-offset scan, fill sweep, per-run sort, big-run sort}. */
-int apgk_occurrences_info(const apgk_ctx* ctx, uint64_t* n_occ, uint64_t* n_big_runs, float* ms4);
+ * ms5 = device milliseconds of {run-offset scan, sweep of the reads (scatter to buckets), per-bucket
+ * placement, per-run sort, big-run sort}. */
+int apgk_occurrences_info(const apgk_ctx* ctx, uint64_t* n_occ, uint64_t* n_big_runs, float* ms5);
 /* DEVICE pointers, library-owned until the next finish / reset: run offsets (uint64[n_distinct+1]) and
  * the occurrences encoded as (global base position in the read store << 1) | canonical_is_reverse. */
 int apgk_occurrences_device(apgk_ctx* ctx, const uint64_t** d_run_off, const uint64_t** d_occ, uint64_t* n_occ);

@@ -104,6 +104,17 @@ def test_occurrences_long_runs(oracle, K):
     kc.close()
 
 
+@pytest.mark.parametrize("K,prefix_bits", [(16, 2), (13, 4), (25, 6), (31, 8)])
+def test_occurrences_buckets_beyond_the_shared_table(oracle, K, prefix_bits):
+    """Few prefix bits: thousands of distinct k-mers per bucket, more than k_occ_place keeps in shared memory
+    (those buckets search the table in global memory); K=31 uses full-key elements."""
+    sp = oracle.synth_params(60_000, 100)
+    p, o = oracle.synth_reads(sp, 0, 12_000)
+    kc = _counter(p, o, K, uniform=(12_000, 100), prefix_bits=prefix_bits)
+    _assert_occ_equal(oracle, kc, p, o, K)
+    kc.close()
+
+
 @pytest.mark.parametrize("K,L,n", [(25, 100, 400_000), (20, 250, 60_000), (48, 150, 100_000), (96, 250, 50_000)])
 def test_occurrences_synthetic_coverage(oracle, K, L, n):
     """BASELINE configs scaled to what the single-threaded oracle walks in seconds: 20x coverage with planted
@@ -229,3 +240,39 @@ def test_reference_named_record_entry_points(oracle):
     assert (bk == ek[100:1100]).all() and (bro == ero[100:1101] - ero[100]).all()
     assert (brid == erid[int(ero[100]):int(ero[1100])]).all() and (bpos == epos[int(ero[100]):int(ero[1100])]).all()
     b.close()
+
+
+def test_direct_sweep_agrees_with_two_phase_build(oracle, tmp_path):
+    """APGK_OCC_DIRECT=1 selects the first implementation (lookup + slot + store straight from the sweep of
+    the reads); it is read at library load, so it runs in a child process.  Both device paths must give the
+    same records as the oracle."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib; sys.path.insert(0, %r)\n"
+        "from oracle import oracle_a as A\n"
+        "from allpathslg_b200 import KmerCounter\n"
+        "for K, L, n in ((25, 100, 30000), (40, 120, 8000)):\n"
+        "    p, o = A.synth_reads(A.synth_params(n * L // 20, L), 0, n)\n"
+        "    kc = KmerCounter(K); kc.add_reads(p, o); kc.finish(); info = kc.build_occurrences()\n"
+        "    ro, rid, pos = kc.occurrences()\n"
+        "    print(K, info['ms']['place'] == 0.0, hashlib.sha256(ro.tobytes() + rid.tobytes() + pos.tobytes()).hexdigest())\n"
+    ) % root
+    outs = {}
+    for mode in ("direct", "two-phase"):
+        env = dict(os.environ)
+        env.pop("APGK_OCC_DIRECT", None)
+        if mode == "direct":
+            env["APGK_OCC_DIRECT"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs[mode] = [ln.split() for ln in r.stdout.strip().splitlines()]
+    assert [x[1] for x in outs["direct"]] == ["True", "True"] and [x[1] for x in outs["two-phase"]] == ["False", "False"]
+    assert [x[2] for x in outs["direct"]] == [x[2] for x in outs["two-phase"]]
+    for (K, L, n), row in zip(((25, 100, 30000), (40, 120, 8000)), outs["two-phase"]):
+        p, o = oracle.synth_reads(oracle.synth_params(n * L // 20, L), 0, n)
+        ek, ec, en = oracle.count(p, o, K)
+        ero, erid, epos = oracle.occurrences(p, o, K, ek, en)
+        assert row[2] == hashlib.sha256(ero.tobytes() + erid.tobytes() + epos.tobytes()).hexdigest()
