@@ -976,8 +976,13 @@ int build_occurrences_impl(apgk_ctx* c) {
   } else {
     Elem* elems;
     unsigned long long* pos_tmp;
+    int pack_bits = 0;
     if (U32) {
-      CU(c->B.ensure(N * 4));
+      // position bits: (q << 1 | rc) of the last base; remainder and position share one word when they fit
+      int pos_bits = 1;
+      while (pos_bits < 64 && (2 * c->total_bases) >> pos_bits) pos_bits++;
+      if (c->geom.REM + pos_bits <= 64 && !getenv("APGK_OCC_NOPACK")) pack_bits = pos_bits;
+      if (!pack_bits) CU(c->B.ensure(N * 4));
       CU(c->A.ensure(N * 8));
       elems = c->B.as<Elem>(); pos_tmp = c->A.as<unsigned long long>();
     } else {
@@ -987,18 +992,18 @@ int build_occurrences_impl(apgk_ctx* c) {
     }
     CU(c->occ_bstart.ensure(((size_t)nb + 1) * 8));
     CU(c->occ_bcur.ensure((size_t)nb * 8));
-    CU(cudaMemsetAsync(c->occ_bcur.p, 0, (size_t)nb * 8, c->stream));
     k_occ_bstart<<<(nb + 1 + 255) / 256, 256, 0, c->stream>>>(c->out_off.as<unsigned long long>(), run_off, nb,
-                                                           c->occ_bstart.as<unsigned long long>());
+                                                           c->occ_bstart.as<unsigned long long>(),
+                                                           c->occ_bcur.as<unsigned long long>());
     LAUNCHED();
     CU(cudaEventRecord(c->occ_ev[1], c->stream));
     k_occ_scatter<W, Elem, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(
-        read_store(c), freq_table<W>(c), c->occ_bstart.as<unsigned long long>(), c->occ_bcur.as<unsigned long long>(), elems,
-        pos_tmp, counters);
+        read_store(c), freq_table<W>(c), c->occ_bcur.as<unsigned long long>(), elems, pos_tmp, pack_bits, N, counters);
     LAUNCHED();
     CU(cudaEventRecord(c->occ_ev[2], c->stream));
     k_occ_place<W, Elem, OCC_PLACE_NT><<<std::min<uint32_t>(nb, (uint32_t)c->n_sm * 8), OCC_PLACE_NT, 0, c->stream>>>(
-        freq_table<W>(c), run_off, c->occ_bstart.as<unsigned long long>(), elems, pos_tmp, c->T.as<uint32_t>(), occ, counters);
+        freq_table<W>(c), run_off, c->occ_bstart.as<unsigned long long>(), elems, pos_tmp, pack_bits, c->T.as<uint32_t>(), occ,
+        counters);
     LAUNCHED();
   }
   CU(cudaEventRecord(c->occ_ev[3], c->stream));
@@ -1030,6 +1035,7 @@ int build_occurrences_impl(apgk_ctx* c) {
   CU(cudaMemcpyAsync(h, counters, 24, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->occ_ms[i], c->occ_ev[i], c->occ_ev[i + 1]);
+  if (kOccDirect) c->occ_ms[2] = 0;  // no placement pass in the direct form
   if (h[1] || h[2])
     FAIL(APGK_E_STATE, "occurrences: %llu windows missing from the table, %llu slots past a run (table does not match the read store)",
          h[1], h[2]);

@@ -80,17 +80,25 @@ template <int W> struct OccElem<Key<W>, W> {
   static APGK_HD Key<W> key(const Key<W>& e, uint32_t, int, int) { return e; }
 };
 
-// bstart[b] = first slot of prefix bucket b (b = 0 .. nb)
+// bstart[b] = first slot of prefix bucket b (b = 0 .. nb); bcur[b] = the bucket's write cursor, starting there
 __global__ void k_occ_bstart(const unsigned long long* __restrict__ index, const unsigned long long* __restrict__ run_off,
-                             uint32_t nb, unsigned long long* __restrict__ bstart) {
+                             uint32_t nb, unsigned long long* __restrict__ bstart, unsigned long long* __restrict__ bcur) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b <= nb) bstart[b] = run_off[index[b]];
+  if (b > nb) return;
+  const unsigned long long v = run_off[index[b]];
+  bstart[b] = v;
+  if (b < nb) bcur[b] = v;
 }
 
+// Sweep of the reads: every window takes the next slot of its prefix bucket (ONE 64-bit global atomic on a
+// cursor that holds absolute slots: 2^P counters, L2 resident) and stores its element there.  pack_bits > 0
+// (32-bit remainders whose REM bits fit above the position in one word): pos_tmp[o] = rem << pack_bits | pos,
+// one 8-byte store per window; else the element and the position go to two arrays.  A slot can only run
+// past its bucket if the table does not match the read store; k_occ_place would then miss the k-mer.
 template <int W, typename Elem, int NT>
-__global__ void __launch_bounds__(NT) k_occ_scatter(ReadStore rs, FreqTable<W> t, const unsigned long long* __restrict__ bstart,
-                                                    unsigned long long* __restrict__ bcur, Elem* __restrict__ elems,
-                                                    unsigned long long* __restrict__ pos_tmp,
+__global__ void __launch_bounds__(NT) k_occ_scatter(ReadStore rs, FreqTable<W> t, unsigned long long* __restrict__ bcur,
+                                                    Elem* __restrict__ elems, unsigned long long* __restrict__ pos_tmp,
+                                                    int pack_bits, unsigned long long n_slots,
                                                     unsigned long long* __restrict__ counters) {
   const uint64_t p = ((uint64_t)blockIdx.x * NT + threadIdx.x) * POS_PER_THREAD;
   if (p >= rs.total_bases) return;
@@ -101,24 +109,37 @@ __global__ void __launch_bounds__(NT) k_occ_scatter(ReadStore rs, FreqTable<W> t
   extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool use_rc) {
     if ((valid >> j) & 1u) {
       const uint32_t b = digit_of(c, t.prefix_pos, t.prefix_len, t.pad);
-      const unsigned long long o = bstart[b] + atomicAdd(&bcur[b], 1ull);
-      if (o < bstart[b + 1]) {
-        elems[o] = OccElem<Elem, W>::make(c, t.prefix_pos, t.pad);
-        pos_tmp[o] = ((p + (uint64_t)j) << 1) | (use_rc ? 1ull : 0ull);
-      } else {
+      const unsigned long long o = atomicAdd(&bcur[b], 1ull);
+      const unsigned long long pv = ((p + (uint64_t)j) << 1) | (use_rc ? 1ull : 0ull);
+      if (o >= n_slots) {
         atomicAdd(&counters[2], 1ull);
+      } else if constexpr (sizeof(Elem) == 4) {
+        const uint32_t r = OccElem<Elem, W>::make(c, t.prefix_pos, t.pad);
+        if (pack_bits) {
+          pos_tmp[o] = ((unsigned long long)r << pack_bits) | pv;
+        } else {
+          elems[o] = r;
+          pos_tmp[o] = pv;
+        }
+      } else {
+        elems[o] = OccElem<Elem, W>::make(c, t.prefix_pos, t.pad);
+        pos_tmp[o] = pv;
       }
     }
   });
 }
 
+// One CTA per prefix bucket.  The CTA walks the bucket's elements NT at a time with a barrier per step,
+// so slots are handed out in (nearly) element order and the runs stay almost sorted for the sort pass.
 template <int W, typename Elem, int NT>
 __global__ void __launch_bounds__(NT) k_occ_place(FreqTable<W> t, const unsigned long long* __restrict__ run_off,
                                                   const unsigned long long* __restrict__ bstart, const Elem* __restrict__ elems,
-                                                  const unsigned long long* __restrict__ pos_tmp, uint32_t* __restrict__ cursor,
-                                                  unsigned long long* __restrict__ occ, unsigned long long* __restrict__ counters) {
+                                                  const unsigned long long* __restrict__ pos_tmp, int pack_bits,
+                                                  uint32_t* __restrict__ cursor, unsigned long long* __restrict__ occ,
+                                                  unsigned long long* __restrict__ counters) {
   constexpr bool U32 = sizeof(Elem) == 4;
-  __shared__ uint32_t sh_rem[U32 ? OCC_PLACE_CAP : 1], sh_off[U32 ? OCC_PLACE_CAP : 1], sh_cur[U32 ? OCC_PLACE_CAP : 1];
+  __shared__ uint32_t sh_rem[U32 ? OCC_PLACE_CAP : 1], sh_off[U32 ? OCC_PLACE_CAP + 1 : 1], sh_cur[U32 ? OCC_PLACE_CAP : 1];
+  const unsigned long long pos_mask = pack_bits ? ((1ull << pack_bits) - 1ull) : ~0ull;
   for (uint32_t b = blockIdx.x; b < t.nb; b += gridDim.x) {
     const unsigned long long e0 = bstart[b], n = bstart[b + 1] - e0;
     if (!n) continue;
@@ -127,42 +148,58 @@ __global__ void __launch_bounds__(NT) k_occ_place(FreqTable<W> t, const unsigned
     if constexpr (U32) in_sh = d <= OCC_PLACE_CAP && n < (1ull << 32);
     if (in_sh) {
       if constexpr (U32) {
-        for (uint32_t j = threadIdx.x; j < (uint32_t)d; j += NT) {
-          sh_rem[j] = OccElem<Elem, W>::make(t.keys[t0 + j], t.prefix_pos, t.pad);
+        for (uint32_t j = threadIdx.x; j <= (uint32_t)d; j += NT) {
           sh_off[j] = (uint32_t)(run_off[t0 + j] - e0);
-          sh_cur[j] = 0;
-        }
-        __syncthreads();
-        for (unsigned long long i = threadIdx.x; i < n; i += NT) {
-          const uint32_t r = elems[e0 + i];
-          const unsigned long long pv = pos_tmp[e0 + i];
-          uint32_t lo = 0, hi = (uint32_t)d;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sh_rem[mid] < r) lo = mid + 1; else hi = mid;
-          }
-          if (lo < (uint32_t)d && sh_rem[lo] == r) {
-            const uint32_t slot = atomicAdd(&sh_cur[lo], 1u);
-            const unsigned long long o = e0 + sh_off[lo] + slot;
-            if (o < run_off[t0 + lo + 1]) occ[o] = pv; else atomicAdd(&counters[2], 1ull);
-          } else {
-            atomicAdd(&counters[1], 1ull);
+          if (j < (uint32_t)d) {
+            sh_rem[j] = OccElem<Elem, W>::make(t.keys[t0 + j], t.prefix_pos, t.pad);
+            sh_cur[j] = 0;
           }
         }
         __syncthreads();
+        for (unsigned long long i0 = 0; i0 < n; i0 += NT) {
+          const unsigned long long i = i0 + threadIdx.x;
+          if (i < n) {
+            unsigned long long pv = pos_tmp[e0 + i];
+            uint32_t r;
+            if (pack_bits) { r = (uint32_t)(pv >> pack_bits); pv &= pos_mask; } else { r = elems[e0 + i]; }
+            uint32_t lo = 0, hi = (uint32_t)d;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (sh_rem[mid] < r) lo = mid + 1; else hi = mid;
+            }
+            if (lo < (uint32_t)d && sh_rem[lo] == r) {
+              const uint32_t slot = sh_off[lo] + atomicAdd(&sh_cur[lo], 1u);
+              if (slot < sh_off[lo + 1]) occ[e0 + slot] = pv; else atomicAdd(&counters[2], 1ull);
+            } else {
+              atomicAdd(&counters[1], 1ull);
+            }
+          }
+          __syncthreads();
+        }
       }
     } else {
-      for (unsigned long long i = threadIdx.x; i < n; i += NT) {
-        const Key<W> c = OccElem<Elem, W>::key(elems[e0 + i], b, t.prefix_pos, t.pad);
-        const unsigned long long pv = pos_tmp[e0 + i];
-        const unsigned long long idx = table_find_index(t, c);
-        if (idx == ~0ull) {
-          atomicAdd(&counters[1], 1ull);
-        } else {
-          const uint32_t slot = atomicAdd(&cursor[idx], 1u);
-          const unsigned long long o = run_off[idx] + slot;
-          if (o < run_off[idx + 1]) occ[o] = pv; else atomicAdd(&counters[2], 1ull);
+      for (unsigned long long i0 = 0; i0 < n; i0 += NT) {
+        const unsigned long long i = i0 + threadIdx.x;
+        if (i < n) {
+          unsigned long long pv = pos_tmp[e0 + i];
+          Key<W> c;
+          if constexpr (U32) {
+            uint32_t r;
+            if (pack_bits) { r = (uint32_t)(pv >> pack_bits); pv &= pos_mask; } else { r = elems[e0 + i]; }
+            c = OccElem<Elem, W>::key(r, b, t.prefix_pos, t.pad);
+          } else {
+            c = elems[e0 + i];
+          }
+          const unsigned long long idx = table_find_index(t, c);
+          if (idx == ~0ull) {
+            atomicAdd(&counters[1], 1ull);
+          } else {
+            const uint32_t slot = atomicAdd(&cursor[idx], 1u);
+            const unsigned long long o = run_off[idx] + slot;
+            if (o < run_off[idx + 1]) occ[o] = pv; else atomicAdd(&counters[2], 1ull);
+          }
         }
+        __syncthreads();
       }
     }
   }

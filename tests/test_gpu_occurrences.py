@@ -261,16 +261,19 @@ def test_direct_sweep_agrees_with_two_phase_build(oracle, tmp_path):
         "    print(K, info['ms']['place'] == 0.0, hashlib.sha256(ro.tobytes() + rid.tobytes() + pos.tobytes()).hexdigest())\n"
     ) % root
     outs = {}
-    for mode in ("direct", "two-phase"):
+    for mode in ("direct", "two-phase", "two-phase-unpacked"):
         env = dict(os.environ)
         env.pop("APGK_OCC_DIRECT", None)
+        env.pop("APGK_OCC_NOPACK", None)
         if mode == "direct":
             env["APGK_OCC_DIRECT"] = "1"
+        if mode == "two-phase-unpacked":   # remainder and position in two arrays (what > 2^31 bases with REM = 32 use)
+            env["APGK_OCC_NOPACK"] = "1"
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr
         outs[mode] = [ln.split() for ln in r.stdout.strip().splitlines()]
     assert [x[1] for x in outs["direct"]] == ["True", "True"] and [x[1] for x in outs["two-phase"]] == ["False", "False"]
-    assert [x[2] for x in outs["direct"]] == [x[2] for x in outs["two-phase"]]
+    assert [x[2] for x in outs["direct"]] == [x[2] for x in outs["two-phase"]] == [x[2] for x in outs["two-phase-unpacked"]]
     for (K, L, n), row in zip(((25, 100, 30000), (40, 120, 8000)), outs["two-phase"]):
         p, o = oracle.synth_reads(oracle.synth_params(n * L // 20, L), 0, n)
         ek, ec, en = oracle.count(p, o, K)
