@@ -345,7 +345,11 @@ def run_ours(args):
     line = {
         "metric": "k-mer spectrum throughput (K=25), k-mer instances counted per second",
         "value": round(value, 3), "unit": "Gk-mers/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_step, 3),
+        "timing": "host clock between barrier + cuda synchronize on both sides (max over ranks); device_ms_per_step and "
+                  "roofline.stages are CUDA-event intervals on the library's own stream",
+        "device_ms_per_step": round(stage_ms.get("total", 0.0), 3) if world == 1 else None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(n_gpus),
         "e2e": {"value": round(e2e_val, 3), "unit": "Gk-mers/s", "h2d_bytes_per_step": int(nbytes) * n_gpus,
                 "d2h_bytes_per_step": int(spec_bytes) * n_gpus, "steps": e2e_steps},
