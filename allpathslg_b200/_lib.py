@@ -49,6 +49,7 @@ SYMBOLS = {
     "apgk_counts_copy": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp]),
     "apgk_lookup": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp]),
     "apgk_read_freqs": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "apgk_read_freqs_device": (C.c_int, [_vp, _vp, C.POINTER(C.c_float)]),
     "apgk_build_occurrences": (C.c_int, [_vp]),
     "apgk_occurrences_info": (C.c_int, [_vp, _u64p, _u64p, C.POINTER(C.c_float)]),
     "apgk_occurrences_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),

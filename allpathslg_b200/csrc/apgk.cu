@@ -88,6 +88,7 @@ struct apgk_ctx {
   bool have_occ = false;
   uint64_t n_occ = 0, n_big_runs = 0;
   float occ_ms[5]{};
+  float freq_ms[3]{};              // last bulk read_freqs: {memset + scan, sweep, placement}
   cudaEvent_t occ_ev[6]{};
   std::vector<uint64_t> empty_nb;  // per read without bases: number of reads WITH bases before it
   uint64_t n_instances = 0, n_distinct = 0;
@@ -931,7 +932,63 @@ int scan_u32(apgk_ctx* c, const uint32_t* in, uint64_t n, unsigned long long* ou
 }
 
 // ---------------------------------------------------------------- occurrence records
+static const bool kFreqDirect = getenv("APGK_FREQ_DIRECT") != nullptr;  // whole-store read_freqs by per-window table search
 static const bool kOccDirect = getenv("APGK_OCC_DIRECT") != nullptr;  // first version: lookup + slot + store straight from the sweep
+
+struct OccScatter {
+  void* elems = nullptr;
+  unsigned long long* pos_tmp = nullptr;
+  int pack_bits = 0;
+};
+
+// run offsets = exclusive scan of the counts, in c->occ_off; fails if a count saturated
+int occ_run_offsets(apgk_ctx* c) {
+  const uint64_t N = c->n_instances, D = c->n_distinct;
+  CU(c->occ_off.ensure((D + 1) * 8));
+  unsigned long long total = 0;
+  { int rc = scan_u32(c, c->out_cnt.as<uint32_t>(), D, c->occ_off.as<unsigned long long>(), &total); if (rc) return rc; }
+  if (total != N) FAIL(APGK_E_RANGE, "counts sum to %llu, instances %llu (a count saturated)", total, (unsigned long long)N);
+  return APGK_OK;
+}
+
+// Phase 1 of the two-phase forms: the sweep of the reads that sends every window to its prefix bucket's region.
+// The pipeline's A / B are dead after finish and reused: elements in B (32-bit remainders; unused when remainder
+// and position share a word) or A (full keys), the positions on their way to their bucket in A or occ_pos.
+template <int W, typename Elem>
+int occ_scatter_phase(apgk_ctx* c, unsigned long long* counters, OccScatter& o) {
+  const uint64_t N = c->n_instances;
+  const uint32_t nb = c->nb1;
+  constexpr bool U32 = sizeof(Elem) == 4;
+  unsigned long long* run_off = c->occ_off.as<unsigned long long>();
+  o.pack_bits = 0;
+  if (U32) {
+    // position bits: (q << 1 | rc) of the last base; remainder and position share one word when they fit
+    int pos_bits = 1;
+    while (pos_bits < 64 && (2 * c->total_bases) >> pos_bits) pos_bits++;
+    if (c->geom.REM + pos_bits <= 64 && !getenv("APGK_OCC_NOPACK")) o.pack_bits = pos_bits;
+    if (!o.pack_bits) CU(c->B.ensure(N * 4));
+    CU(c->A.ensure(N * 8));
+    o.elems = c->B.p; o.pos_tmp = c->A.as<unsigned long long>();
+  } else {
+    CU(c->A.ensure(N * sizeof(Elem)));
+    CU(c->occ_pos.ensure(N * 8));
+    o.elems = c->A.p; o.pos_tmp = c->occ_pos.as<unsigned long long>();
+  }
+  CU(c->occ_bstart.ensure(((size_t)nb + 1) * 8));
+  CU(c->occ_bcur.ensure((size_t)nb * 8));
+  k_occ_bstart<<<(nb + 1 + 255) / 256, 256, 0, c->stream>>>(c->out_off.as<unsigned long long>(), run_off, nb,
+                                                         c->occ_bstart.as<unsigned long long>(),
+                                                         c->occ_bcur.as<unsigned long long>());
+  LAUNCHED();
+  CU(cudaEventRecord(c->occ_ev[1], c->stream));
+  constexpr int NT = 128;
+  const uint64_t threads = (c->total_bases + POS_PER_THREAD - 1) / POS_PER_THREAD;
+  k_occ_scatter<W, Elem, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(
+      read_store(c), freq_table<W>(c), c->occ_bcur.as<unsigned long long>(), (Elem*)o.elems, o.pos_tmp, o.pack_bits, N, counters);
+  LAUNCHED();
+  CU(cudaEventRecord(c->occ_ev[2], c->stream));
+  return APGK_OK;
+}
 
 template <int W, typename Elem>
 int build_occurrences_impl(apgk_ctx* c) {
@@ -940,24 +997,17 @@ int build_occurrences_impl(apgk_ctx* c) {
   for (float& m : c->occ_ms) m = 0;
   { int rc = wait_ingest(c); if (rc) return rc; }
   for (cudaEvent_t& e : c->occ_ev) if (!e) CU(cudaEventCreate(&e));
-  CU(c->occ_off.ensure((D + 1) * 8));
   if (!N) {
+    CU(c->occ_off.ensure((D + 1) * 8));
     CU(cudaMemsetAsync(c->occ_off.p, 0, (D + 1) * 8, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->have_occ = true;
     return APGK_OK;
   }
-  unsigned long long* run_off = c->occ_off.as<unsigned long long>();
-  // run offsets = exclusive scan of the counts
   CU(cudaEventRecord(c->occ_ev[0], c->stream));
-  unsigned long long total = 0;
-  { int rc = scan_u32(c, c->out_cnt.as<uint32_t>(), D, run_off, &total); if (rc) return rc; }
-  if (total != N) FAIL(APGK_E_RANGE, "occurrences: counts sum to %llu, instances %llu (a count saturated)", total, (unsigned long long)N);
-  // Buffers.  The pipeline's A / B / T are dead after finish and reused: elements in B (32-bit remainders) or A
-  // (full keys), the positions on their way to their bucket in A or occ_pos, the per-run cursors of the
-  // global-table path in T, the big-run list in B once the placement is done.
-  constexpr bool U32 = sizeof(Elem) == 4;
-  const uint32_t nb = c->nb1;
+  { int rc = occ_run_offsets(c); if (rc) return rc; }
+  unsigned long long* run_off = c->occ_off.as<unsigned long long>();
+  // the per-run cursors of the global-table path live in T, the big-run list in B once the placement is done
   CU(c->occ.ensure(N * 8));
   CU(c->T.ensure(D * 4));
   CU(c->occ_cnt.ensure(64));
@@ -965,45 +1015,20 @@ int build_occurrences_impl(apgk_ctx* c) {
   CU(cudaMemsetAsync(c->T.p, 0, D * 4, c->stream));
   CU(cudaMemsetAsync(counters, 0, 32, c->stream));
   unsigned long long* occ = c->occ.as<unsigned long long>();
-  const uint64_t threads = (c->total_bases + POS_PER_THREAD - 1) / POS_PER_THREAD;
-  constexpr int NT = 128;
   if (kOccDirect) {
+    constexpr int NT = 128;
+    const uint64_t threads = (c->total_bases + POS_PER_THREAD - 1) / POS_PER_THREAD;
     CU(cudaEventRecord(c->occ_ev[1], c->stream));
     k_occ_fill<W, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(read_store(c), freq_table<W>(c), run_off,
                                                                                c->T.as<uint32_t>(), occ, counters);
     LAUNCHED();
     CU(cudaEventRecord(c->occ_ev[2], c->stream));
   } else {
-    Elem* elems;
-    unsigned long long* pos_tmp;
-    int pack_bits = 0;
-    if (U32) {
-      // position bits: (q << 1 | rc) of the last base; remainder and position share one word when they fit
-      int pos_bits = 1;
-      while (pos_bits < 64 && (2 * c->total_bases) >> pos_bits) pos_bits++;
-      if (c->geom.REM + pos_bits <= 64 && !getenv("APGK_OCC_NOPACK")) pack_bits = pos_bits;
-      if (!pack_bits) CU(c->B.ensure(N * 4));
-      CU(c->A.ensure(N * 8));
-      elems = c->B.as<Elem>(); pos_tmp = c->A.as<unsigned long long>();
-    } else {
-      CU(c->A.ensure(N * sizeof(Elem)));
-      CU(c->occ_pos.ensure(N * 8));
-      elems = c->A.as<Elem>(); pos_tmp = c->occ_pos.as<unsigned long long>();
-    }
-    CU(c->occ_bstart.ensure(((size_t)nb + 1) * 8));
-    CU(c->occ_bcur.ensure((size_t)nb * 8));
-    k_occ_bstart<<<(nb + 1 + 255) / 256, 256, 0, c->stream>>>(c->out_off.as<unsigned long long>(), run_off, nb,
-                                                           c->occ_bstart.as<unsigned long long>(),
-                                                           c->occ_bcur.as<unsigned long long>());
-    LAUNCHED();
-    CU(cudaEventRecord(c->occ_ev[1], c->stream));
-    k_occ_scatter<W, Elem, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(
-        read_store(c), freq_table<W>(c), c->occ_bcur.as<unsigned long long>(), elems, pos_tmp, pack_bits, N, counters);
-    LAUNCHED();
-    CU(cudaEventRecord(c->occ_ev[2], c->stream));
-    k_occ_place<W, Elem, OCC_PLACE_NT><<<std::min<uint32_t>(nb, (uint32_t)c->n_sm * 8), OCC_PLACE_NT, 0, c->stream>>>(
-        freq_table<W>(c), run_off, c->occ_bstart.as<unsigned long long>(), elems, pos_tmp, pack_bits, c->T.as<uint32_t>(), occ,
-        counters);
+    OccScatter sc;
+    { int rc = occ_scatter_phase<W, Elem>(c, counters, sc); if (rc) return rc; }
+    k_occ_place<W, Elem, OCC_PLACE_NT, false><<<std::min<uint32_t>(c->nb1, (uint32_t)c->n_sm * 8), OCC_PLACE_NT, 0, c->stream>>>(
+        freq_table<W>(c), run_off, c->occ_bstart.as<unsigned long long>(), (const Elem*)sc.elems, sc.pos_tmp, sc.pack_bits,
+        c->T.as<uint32_t>(), occ, nullptr, counters);
     LAUNCHED();
   }
   CU(cudaEventRecord(c->occ_ev[3], c->stream));
@@ -1043,6 +1068,52 @@ int build_occurrences_impl(apgk_ctx* c) {
   c->n_occ = N;
   c->have_occ = true;
   return APGK_OK;
+}
+
+// Bulk form of apgk_read_freqs: the count of the canonical k-mer at EVERY base of the store (0xFFFFFFFF where the
+// window leaves its read) into d_out (DEVICE, total_bases entries), by bucket scatter + per-bucket placement.
+template <int W, typename Elem>
+int read_freqs_bulk(apgk_ctx* c, uint32_t* d_out) {
+  const uint64_t N = c->n_instances;
+  { int rc = wait_ingest(c); if (rc) return rc; }
+  for (cudaEvent_t& e : c->occ_ev) if (!e) CU(cudaEventCreate(&e));
+  if (!c->total_bases) return APGK_OK;
+  CU(cudaEventRecord(c->occ_ev[0], c->stream));
+  CU(cudaMemsetAsync(d_out, 0xFF, c->total_bases * 4, c->stream));
+  if (N) {
+    { int rc = occ_run_offsets(c); if (rc) return rc; }
+    CU(c->occ_cnt.ensure(64));
+    unsigned long long* counters = c->occ_cnt.as<unsigned long long>();
+    CU(cudaMemsetAsync(counters, 0, 32, c->stream));
+    OccScatter sc;
+    { int rc = occ_scatter_phase<W, Elem>(c, counters, sc); if (rc) return rc; }
+    k_occ_place<W, Elem, OCC_PLACE_NT, true><<<std::min<uint32_t>(c->nb1, (uint32_t)c->n_sm * 8), OCC_PLACE_NT, 0, c->stream>>>(
+        freq_table<W>(c), c->occ_off.as<unsigned long long>(), c->occ_bstart.as<unsigned long long>(), (const Elem*)sc.elems,
+        sc.pos_tmp, sc.pack_bits, nullptr, nullptr, d_out, counters);
+    LAUNCHED();
+    CU(cudaEventRecord(c->occ_ev[3], c->stream));
+    unsigned long long h[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(h, counters, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->freq_ms[0], c->occ_ev[0], c->occ_ev[1]);
+    cudaEventElapsedTime(&c->freq_ms[1], c->occ_ev[1], c->occ_ev[2]);
+    cudaEventElapsedTime(&c->freq_ms[2], c->occ_ev[2], c->occ_ev[3]);
+    if (h[1] || h[2])
+      FAIL(APGK_E_STATE, "read_freqs: %llu windows missing from the table, %llu slots past a bucket (table does not match the read store)",
+           h[1], h[2]);
+  } else {
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return APGK_OK;
+}
+
+int read_freqs_bulk_dispatch(apgk_ctx* c, uint32_t* d_out) {
+  switch (c->W) {
+    case 1: return c->geom.REM <= 32 ? read_freqs_bulk<1, uint32_t>(c, d_out) : read_freqs_bulk<1, Key<1>>(c, d_out);
+    case 2: return read_freqs_bulk<2, Key<2>>(c, d_out);
+    case 3: return read_freqs_bulk<3, Key<3>>(c, d_out);
+  }
+  return APGK_E_ARG;
 }
 
 int occurrences_copy_impl(apgk_ctx* c, uint64_t first, uint64_t n_kmers, uint64_t* run_off_out, uint32_t* read_id_out,
@@ -1695,6 +1766,15 @@ int apgk_read_freqs(apgk_ctx* c, uint64_t first_base, uint64_t n_bases, uint32_t
   if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
   if (first_base + n_bases > c->total_bases) FAIL(APGK_E_ARG, "range beyond the read store");
   CU(cudaSetDevice(c->device));
+  if (first_base == 0 && n_bases == c->total_bases && n_bases && c->table_from_reads && !kFreqDirect) {
+    // the whole store: bulk form (bucket scatter + per-bucket placement) into a device buffer, then one copy
+    CU(c->occ_tmp.ensure(n_bases * 4));
+    int rc = read_freqs_bulk_dispatch(c, c->occ_tmp.as<uint32_t>());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, c->occ_tmp.p, n_bases * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return APGK_OK;
+  }
   switch (c->W) {
     case 1: return read_freqs_impl<1>(c, first_base, n_bases, out);
     case 2: return read_freqs_impl<2>(c, first_base, n_bases, out);
@@ -1743,6 +1823,39 @@ int apgk_occurrences_copy(apgk_ctx* c, uint64_t first_kmer, uint64_t n_kmers, ui
   if (first_kmer > c->n_distinct || n_kmers > c->n_distinct - first_kmer) FAIL(APGK_E_ARG, "k-mer range beyond the table");
   CU(cudaSetDevice(c->device));
   return occurrences_copy_impl(c, first_kmer, n_kmers, run_off_out, read_id_out, pos_out);
+}
+
+int apgk_read_freqs_device(apgk_ctx* c, uint32_t* d_out, float* ms3) {
+  if (!c || !d_out) return APGK_E_ARG;
+  if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
+  if (!c->table_from_reads)
+    FAIL(APGK_E_STATE, "the bulk form needs a table counted from this context's read store (apgk_finish, not a shard or a key array)");
+  CU(cudaSetDevice(c->device));
+  for (float& m : c->freq_ms) m = 0;
+  int rc;
+  if (kFreqDirect) {   // the per-window table search, for comparison
+    { int r2 = wait_ingest(c); if (r2) return r2; }
+    for (cudaEvent_t& e : c->occ_ev) if (!e) CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(c->occ_ev[0], c->stream));
+    constexpr int NT = 128;
+    const uint64_t threads = (c->total_bases + POS_PER_THREAD - 1) / POS_PER_THREAD;
+    if (threads) {
+      switch (c->W) {
+        case 1: k_read_freqs<1, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(read_store(c), freq_table<1>(c), 0, c->total_bases, d_out); break;
+        case 2: k_read_freqs<2, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(read_store(c), freq_table<2>(c), 0, c->total_bases, d_out); break;
+        case 3: k_read_freqs<3, NT><<<(unsigned)((threads + NT - 1) / NT), NT, 0, c->stream>>>(read_store(c), freq_table<3>(c), 0, c->total_bases, d_out); break;
+      }
+      LAUNCHED();
+    }
+    CU(cudaEventRecord(c->occ_ev[1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->freq_ms[1], c->occ_ev[0], c->occ_ev[1]);
+    rc = APGK_OK;
+  } else {
+    rc = read_freqs_bulk_dispatch(c, d_out);
+  }
+  if (ms3) for (int i = 0; i < 3; i++) ms3[i] = c->freq_ms[i];
+  return rc;
 }
 
 int apgk_owner_plan(apgk_ctx* c, uint32_t n_ranks, uint64_t* counts_out) {

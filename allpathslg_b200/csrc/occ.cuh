@@ -131,12 +131,16 @@ __global__ void __launch_bounds__(NT) k_occ_scatter(ReadStore rs, FreqTable<W> t
 
 // One CTA per prefix bucket.  The CTA walks the bucket's elements NT at a time with a barrier per step,
 // so slots are handed out in (nearly) element order and the runs stay almost sorted for the sort pass.
-template <int W, typename Elem, int NT>
+// FREQ = true is the bulk form of the frequency-table lookups error correction makes (apgk_read_freqs over
+// the whole store): instead of taking a slot, every element writes its k-mer's count -- the length of
+// the run -- to freq_out[its base position]; no atomics, no sort, and the ~10 dependent DRAM accesses of
+// a table search per window become one shared-memory search plus one 4-byte store.
+template <int W, typename Elem, int NT, bool FREQ>
 __global__ void __launch_bounds__(NT) k_occ_place(FreqTable<W> t, const unsigned long long* __restrict__ run_off,
                                                   const unsigned long long* __restrict__ bstart, const Elem* __restrict__ elems,
                                                   const unsigned long long* __restrict__ pos_tmp, int pack_bits,
                                                   uint32_t* __restrict__ cursor, unsigned long long* __restrict__ occ,
-                                                  unsigned long long* __restrict__ counters) {
+                                                  uint32_t* __restrict__ freq_out, unsigned long long* __restrict__ counters) {
   constexpr bool U32 = sizeof(Elem) == 4;
   __shared__ uint32_t sh_rem[U32 ? OCC_PLACE_CAP : 1], sh_off[U32 ? OCC_PLACE_CAP + 1 : 1], sh_cur[U32 ? OCC_PLACE_CAP : 1];
   const unsigned long long pos_mask = pack_bits ? ((1ull << pack_bits) - 1ull) : ~0ull;
@@ -168,14 +172,19 @@ __global__ void __launch_bounds__(NT) k_occ_place(FreqTable<W> t, const unsigned
               if (sh_rem[mid] < r) lo = mid + 1; else hi = mid;
             }
             if (lo < (uint32_t)d && sh_rem[lo] == r) {
-              const uint32_t slot = sh_off[lo] + atomicAdd(&sh_cur[lo], 1u);
-              if (slot < sh_off[lo + 1]) occ[e0 + slot] = pv; else atomicAdd(&counters[2], 1ull);
+              if constexpr (FREQ) {
+                freq_out[pv >> 1] = sh_off[lo + 1] - sh_off[lo];
+              } else {
+                const uint32_t slot = sh_off[lo] + atomicAdd(&sh_cur[lo], 1u);
+                if (slot < sh_off[lo + 1]) occ[e0 + slot] = pv; else atomicAdd(&counters[2], 1ull);
+              }
             } else {
               atomicAdd(&counters[1], 1ull);
             }
           }
-          __syncthreads();
+          if constexpr (!FREQ) __syncthreads();   // the lockstep only matters for the order slots are handed out in
         }
+        if constexpr (FREQ) __syncthreads();       // the shared table is reloaded for the next bucket
       }
     } else {
       for (unsigned long long i0 = 0; i0 < n; i0 += NT) {
@@ -193,13 +202,15 @@ __global__ void __launch_bounds__(NT) k_occ_place(FreqTable<W> t, const unsigned
           const unsigned long long idx = table_find_index(t, c);
           if (idx == ~0ull) {
             atomicAdd(&counters[1], 1ull);
+          } else if constexpr (FREQ) {
+            freq_out[pv >> 1] = t.counts[idx];
           } else {
             const uint32_t slot = atomicAdd(&cursor[idx], 1u);
             const unsigned long long o = run_off[idx] + slot;
             if (o < run_off[idx + 1]) occ[o] = pv; else atomicAdd(&counters[2], 1ull);
           }
         }
-        __syncthreads();
+        if constexpr (!FREQ) __syncthreads();
       }
     }
   }

@@ -171,6 +171,13 @@ class KmerCounter:
         self._ck(self._L.apgk_read_freqs(self._h, first_base, n_bases, out.ctypes.data))
         return out[:n_bases]
 
+    def read_freqs_device(self, d_out):
+        """Count of the canonical k-mer at every base of the store into a DEVICE buffer (uint32[total_bases],
+        0xFFFFFFFF where the window leaves its read).  -> device ms {clear, sweep, place}."""
+        ms = (C.c_float * 3)()
+        self._ck(self._L.apgk_read_freqs_device(self._h, d_out, ms))
+        return dict(zip(("clear", "sweep", "place"), [float(x) for x in ms]))
+
     # -- occurrence records: (read id, signed position) of every instance, grouped by k-mer
     def build_occurrences(self):
         """Second sweep over the read store: every window takes a slot in its k-mer's run (needs finish()

@@ -304,6 +304,24 @@ def run_ours(args):
                    "stage_ms": {k_: round(v, 2) for k_, v in info["ms"].items()}, "n_big_runs": info["n_big_runs"],
                    "bytes_out": int(info["n_occ"]) * 8}
 
+    # ---------------- frequency-table lookups (what error correction asks): the count of the k-mer at every base of
+    # the store into a device buffer, N=1 only; reported beside the headline
+    lookups = None
+    if world == 1 and os.environ.get("APGK_BENCH_LOOKUPS", "1") != "0":
+        out = torch.empty(total_bases, dtype=torch.int32, device="cuda")
+        kc.read_freqs_device(out.data_ptr())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lms = kc.read_freqs_device(out.data_ptr())
+        torch.cuda.synchronize()
+        dt_l = time.perf_counter() - t0
+        n_valid = int((out != -1).sum().item())
+        lookups = {"what": "k-mer frequency of every window of the reads (FindErrors table lookups), bulk form, device output",
+                   "ms": round(dt_l * 1e3, 2), "value": round(n_valid / dt_l / 1e9, 3), "unit": "G lookups/s",
+                   "stage_ms": {k_: round(v, 2) for k_, v in lms.items()}, "n_lookups": n_valid,
+                   "direct_form": "per-window table search (APGK_FREQ_DIRECT=1): see profiles/r01_occ.txt"}
+        del out
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -358,7 +376,7 @@ def run_ours(args):
                          "sample": "first %d reads (%d k-mer instances) of the workload, oracle port "
                                    "(not the reference's code: parity unpinned)" % (CPU_SAMPLE_READS, cb_inst)},
         "geometry": geo, "shard_ms": dict({k_: round(v / args.steps, 2) for k_, v in shard_acc.items()}, **{k_: (list(v) if isinstance(v, tuple) else v) for k_, v in shard_info.items()}) if shard_acc else None,
-        "records": records,
+        "records": records, "lookups": lookups,
         "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }

@@ -129,6 +129,13 @@ int apgk_lookup(apgk_ctx* ctx, const uint64_t* kmers, uint64_t n, int canonicali
 /* out[i] = count of the canonical k-mer starting at base first_base+i of the device read store,
  * 0xFFFFFFFF where the window crosses a read end.  out is a HOST buffer of n_bases entries. */
 int apgk_read_freqs(apgk_ctx* ctx, uint64_t first_base, uint64_t n_bases, uint32_t* out);
+/* The same for EVERY base of the store into a DEVICE buffer of total_bases entries (what an error
+ * corrector that keeps the reads on the GPU asks).  Bulk form: one sweep sends every window to its
+ * prefix bucket, one CTA per bucket resolves the bucket's windows against its keys in shared memory
+ * (the context's table must have been counted from its own read store by apgk_finish).  apgk_read_freqs
+ * over the whole store takes this path too.  ms3 (may be NULL) = device milliseconds of {clear + run
+ * offsets, sweep, per-bucket resolution}. */
+int apgk_read_freqs_device(apgk_ctx* ctx, uint32_t* d_out, float* ms3);
 
 /* ---- k-mer occurrence records: the payload half of the reference's SortKmers records (k-mer, read id,
  * signed position) and KmerParcels batches (k-mer + list of (read id, position)) [BJ names, U layout;

@@ -279,3 +279,33 @@ def test_direct_sweep_agrees_with_two_phase_build(oracle, tmp_path):
         ek, ec, en = oracle.count(p, o, K)
         ero, erid, epos = oracle.occurrences(p, o, K, ek, en)
         assert row[2] == hashlib.sha256(ero.tobytes() + erid.tobytes() + epos.tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("K,prefix_bits", [(25, 0), (24, 0), (16, 4), (31, 0), (48, 0), (96, 0)])
+def test_bulk_read_freqs_on_device(oracle, K, prefix_bits):
+    """apgk_read_freqs_device: the frequency of every window of the store, resolved bucket by bucket, into a
+    device buffer -- against the oracle's per-position frequencies and against the per-window table search."""
+    import torch
+
+    sp = oracle.synth_params(80_000, 100)
+    p, o = oracle.synth_reads(sp, 0, 16_000)
+    kc = _counter(p, o, K, uniform=(16_000, 100), prefix_bits=prefix_bits)
+    ek, ec, en = oracle.count(p, o, K)
+    erf = oracle.read_freqs(p, o, K, ek, ec)
+    erf32 = np.where(erf == np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0xFFFFFFFF), erf).astype(np.uint32)
+    tb, _ = kc.read_store_info()
+    out = torch.zeros(tb, dtype=torch.int32, device="cuda")
+    ms = kc.read_freqs_device(out.data_ptr())
+    assert ms["sweep"] > 0 and ms["place"] > 0
+    got = out.cpu().numpy().view(np.uint32)
+    assert (got == erf32).all()
+    half = tb // 2
+    direct = np.concatenate([kc.read_freqs(0, half), kc.read_freqs(half, tb - half)])
+    assert (direct == erf32).all()
+    # the occurrence records survive a bulk lookup in between (they share the scatter buffers, not the result)
+    kc.build_occurrences()
+    a = kc.occurrences()
+    kc.read_freqs_device(out.data_ptr())
+    b = kc.occurrences()
+    assert all((x == y).all() for x, y in zip(a, b))
+    kc.close()

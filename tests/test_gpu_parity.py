@@ -105,6 +105,12 @@ def test_ragged_reads(oracle, K, prefix_bits):
     erf = oracle.read_freqs(p, o, K, ek, ec)
     erf32 = np.where(erf == np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0xFFFFFFFF), erf).astype(np.uint32)
     assert (rf == erf32).all()
+    # the whole store goes through the bulk form (bucket scatter + per-bucket resolution); sub-ranges through the
+    # per-window table search: both must agree with the oracle
+    tb = len(erf32)
+    if tb > 40:
+        assert (kc.read_freqs(0, tb - 1) == erf32[:tb - 1]).all()
+        assert (kc.read_freqs(17, tb - 30) == erf32[17:tb - 13]).all()
     kc.close()
 
 
