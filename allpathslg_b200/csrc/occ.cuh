@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NT) k_occ_scatter(ReadStore rs, FreqTable<W> t
   extract16<W>(win, rs.K, [&](int j, const Key<W>& c, bool use_rc) {
     if ((valid >> j) & 1u) {
       const uint32_t b = digit_of(c, t.prefix_pos, t.prefix_len, t.pad);
-      const unsigned long long o = atomicAdd(&bcur[b], 1ull);
+      const unsigned long long o = atomicAdd(&bcur[b], 1ull);   // (a 32-bit relative cursor + a read of bstart[b] measured 10 % slower)
       const unsigned long long pv = ((p + (uint64_t)j) << 1) | (use_rc ? 1ull : 0ull);
       if (o >= n_slots) {
         atomicAdd(&counters[2], 1ull);
@@ -162,27 +162,38 @@ __global__ void __launch_bounds__(NT) k_occ_place(FreqTable<W> t, const unsigned
         __syncthreads();
         for (unsigned long long i0 = 0; i0 < n; i0 += NT) {
           const unsigned long long i = i0 + threadIdx.x;
+          unsigned long long pv = 0;
+          uint32_t lo = 0xFFFFFFFFu;                 // run of this thread's element (none: past the end / not found)
           if (i < n) {
-            unsigned long long pv = pos_tmp[e0 + i];
+            pv = pos_tmp[e0 + i];
             uint32_t r;
             if (pack_bits) { r = (uint32_t)(pv >> pack_bits); pv &= pos_mask; } else { r = elems[e0 + i]; }
-            uint32_t lo = 0, hi = (uint32_t)d;
+            uint32_t hi = (uint32_t)d;
+            lo = 0;
             while (lo < hi) {
               const uint32_t mid = (lo + hi) >> 1;
               if (sh_rem[mid] < r) lo = mid + 1; else hi = mid;
             }
-            if (lo < (uint32_t)d && sh_rem[lo] == r) {
-              if constexpr (FREQ) {
-                freq_out[pv >> 1] = sh_off[lo + 1] - sh_off[lo];
-              } else {
+            if (!(lo < (uint32_t)d && sh_rem[lo] == r)) {
+              atomicAdd(&counters[1], 1ull);
+              lo = 0xFFFFFFFFu;
+            }
+          }
+          if constexpr (FREQ) {
+            if (lo != 0xFFFFFFFFu) freq_out[pv >> 1] = sh_off[lo + 1] - sh_off[lo];
+          } else {
+            // Slots are handed out warp after warp (a barrier between warps), so a run receives its elements in
+            // element order: a k-mer of a 45x genome has 2-3 elements in every 256-element step, and with the
+            // warps racing most runs arrived with inversions (the sort pass then took 54 ms instead of ~15).
+#pragma unroll 1
+            for (int w = 0; w < NT / 32; w++) {
+              if ((int)(threadIdx.x >> 5) == w && lo != 0xFFFFFFFFu) {
                 const uint32_t slot = sh_off[lo] + atomicAdd(&sh_cur[lo], 1u);
                 if (slot < sh_off[lo + 1]) occ[e0 + slot] = pv; else atomicAdd(&counters[2], 1ull);
               }
-            } else {
-              atomicAdd(&counters[1], 1ull);
+              __syncthreads();
             }
           }
-          if constexpr (!FREQ) __syncthreads();   // the lockstep only matters for the order slots are handed out in
         }
         if constexpr (FREQ) __syncthreads();       // the shared table is reloaded for the next bucket
       }
