@@ -196,6 +196,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL writes its version banner / debug lines to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from allpathslg_b200 import dist as shard
 
