@@ -309,3 +309,21 @@ def test_bulk_read_freqs_on_device(oracle, K, prefix_bits):
     b = kc.occurrences()
     assert all((x == y).all() for x, y in zip(a, b))
     kc.close()
+
+
+def test_no_instances_at_all(oracle):
+    """Reads exist but none reaches K bases: an empty table, empty records, every window invalid."""
+    from allpathslg_b200 import KmerCounter
+
+    p, o = oracle.pack_strings(["ACGT", "", "ACGTACGTAC", "TT"])
+    kc = KmerCounter(25, want_counts=True)
+    kc.add_reads(p, o)
+    kc.finish()
+    assert kc.totals() == (0, 0)
+    info = kc.build_occurrences()
+    assert info["n_occ"] == 0
+    ro, rid, pos = kc.occurrences()
+    assert list(ro) == [0] and len(rid) == 0 and len(pos) == 0
+    rf = kc.read_freqs()
+    assert len(rf) == 16 and (rf == 0xFFFFFFFF).all()
+    kc.close()
