@@ -162,7 +162,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Gk-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port (spec-derived restatement); the reference source was not available: parity unpinned",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -195,9 +195,6 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-
-        # NCCL writes its version banner / debug lines to stdout by default; stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from allpathslg_b200 import dist as shard
@@ -395,13 +392,33 @@ def run_ours(args):
         "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print from C (NCCL's version banner under
+    NCCL_DEBUG) get stderr instead -- file descriptor 1 is pointed at stderr and the JSON line goes to a
+    duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
