@@ -62,6 +62,8 @@ SYMBOLS = {
     "apgk_window_upper": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "apgk_choose_prefix_bits": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_int32)]),
     "apgk_partition": (C.c_int, [_vp, C.c_int32]),
+    "apgk_partition_range": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32]),
+    "apgk_level0_totals": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "apgk_partition_info": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint32),
                                       C.POINTER(C.c_uint64)]),
     "apgk_count_pieces": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int32]),

@@ -100,6 +100,9 @@ struct apgk_ctx {
   std::vector<uint64_t> spec_host, sparse_f, sparse_n;
   bool spec_loaded = false;
   // ---- partition-only state (sharded counting: apgk_partition -> exchange -> apgk_count_pieces)
+  int force_d0_lo = -1, force_d0_hi = -1;   // apgk_partition_range: the one k-mer-space round to partition
+  std::vector<uint64_t> tot0_host;          // level-0 bucket totals of the last run over the read store
+  uint64_t last_cap_keys = 0;               // k-mer instances one round may hold (memory budget of the last run)
   bool part_ready = false;
   uint64_t part_n = 0;       // elements in B, grouped by the nb1 buckets (sizes in segtot)
   DevBuf piece_off, piece_tmp, piece_ptrs, C2, sub_sizes;
@@ -480,6 +483,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
   }
   if (hp0.lp.n_tiles == 0) {  // nothing to count
     c->n_instances = 0;
+    c->tot0_host.assign((size_t)bins0, 0);
     c->have_table = want_table != 0;
     if (mode == RUN_PARTITION) {
       CU(c->segtot.ensure((size_t)c->nb1 * 8));
@@ -549,6 +553,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
     N += tot0[d];
   }
   c->n_instances = N;
+  c->tot0_host = tot0;
   if (N == 0) {
     c->have_table = want_table != 0;
     if (mode == RUN_PARTITION) {
@@ -570,8 +575,12 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
     // temp buffers may take ~60 % of what is available; the result table gets the rest
     cap_keys = (uint64_t)((double)(fr + held) * 0.60 / (double)bytes_per_key);
   }
+  c->last_cap_keys = cap_keys;
   std::vector<std::pair<int, int>> rounds;  // [lo, hi) level-0 buckets
-  {
+  const bool forced_range = mode == RUN_PARTITION && c->force_d0_lo >= 0;
+  if (forced_range) {   // the caller runs the rounds (sharded counting: all ranks use the same ranges)
+    rounds.push_back({std::min(c->force_d0_lo, bins0), std::min(std::max(c->force_d0_hi, c->force_d0_lo), bins0)});
+  } else {
     int lo = 0; uint64_t acc = 0;
     for (int d = 0; d < bins0; d++) {
       if (acc && acc + tot0[d] > cap_keys) { rounds.push_back({lo, d}); lo = d; acc = 0; }
@@ -580,7 +589,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
     rounds.push_back({lo, bins0});
   }
   c->n_rounds = (uint32_t)rounds.size();
-  if (mode == RUN_PARTITION && rounds.size() > 1)
+  if (mode == RUN_PARTITION && rounds.size() > 1 && !forced_range)
     FAIL(APGK_E_RANGE, "apgk_partition: %zu k-mer-space rounds would be needed; the sharded exchange takes one", rounds.size());
 
   CU(c->spec_ovf.ensure(((size_t)N / SPEC_DENSE + 16) * 8));
@@ -596,7 +605,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
 
   for (size_t r = 0; r < rounds.size(); r++) {
     const int lo = rounds[r].first, hi = rounds[r].second;
-    const bool filter = rounds.size() > 1;
+    const bool filter = rounds.size() > 1 || (forced_range && (lo > 0 || hi < bins0));
     std::vector<uint64_t> tot_r(bins0, 0), bstart_r(bins0 + 1, 0);
     uint64_t Nr = 0;
     for (int d = 0; d < bins0; d++) {
@@ -604,7 +613,15 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
       if (d >= lo && d < hi) { tot_r[d] = tot0[d]; Nr += tot0[d]; }
     }
     bstart_r[bins0] = Nr;
-    if (Nr == 0) continue;
+    if (Nr == 0) {
+      if (mode == RUN_PARTITION) {   // nothing in this range: an empty partition
+        CU(c->segtot.ensure((size_t)c->nb1 * 8));
+        CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
+        c->part_n = 0;
+        return APGK_OK;
+      }
+      continue;
+    }
     CU(cudaMemcpyAsync(c->bstart64.p, bstart_r.data(), ((size_t)bins0 + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(c->A.ensure(std::max<size_t>(Nr, 1) * sizeof(Key<W>)));
@@ -1607,6 +1624,24 @@ int apgk_partition(apgk_ctx* c, int32_t prefix_bits) {
   return APGK_E_ARG;
 }
 
+int apgk_partition_range(apgk_ctx* c, int32_t prefix_bits, int32_t d0_lo, int32_t d0_hi) {
+  if (!c || prefix_bits < 2 || prefix_bits > 24 || d0_lo < 0 || d0_hi < d0_lo) return APGK_E_ARG;
+  c->force_d0_lo = d0_lo; c->force_d0_hi = d0_hi;
+  const int rc = apgk_partition(c, prefix_bits);
+  c->force_d0_lo = c->force_d0_hi = -1;
+  return rc;
+}
+int apgk_level0_totals(apgk_ctx* c, uint64_t* totals_out, uint32_t cap, uint32_t* n_level0, uint64_t* round_capacity) {
+  if (!c) return APGK_E_ARG;
+  if (c->tot0_host.empty()) FAIL(APGK_E_STATE, "no level-0 histogram yet: call apgk_partition (it may fail with APGK_E_RANGE) first");
+  if (n_level0) *n_level0 = (uint32_t)c->tot0_host.size();
+  if (round_capacity) *round_capacity = c->last_cap_keys;
+  if (totals_out) {
+    if (cap < c->tot0_host.size()) FAIL(APGK_E_ARG, "totals_out holds %u entries, %zu needed", cap, c->tot0_host.size());
+    memcpy(totals_out, c->tot0_host.data(), c->tot0_host.size() * 8);
+  }
+  return APGK_OK;
+}
 int apgk_partition_info(apgk_ctx* c, const uint64_t** d_bucket_sizes, uint64_t* n_buckets, void** d_elems,
                         uint32_t* elem_bytes, uint64_t* n_elems) {
   if (!c) return APGK_E_ARG;

@@ -10,8 +10,16 @@ cut the bucket space into `world` contiguous ranges of (nearly) equal instance c
 are all-reduced.  A k-mer's owner depends on the canonical k-mer alone, so counts are final
 without a merge.
 
-Hash form (`sharded_count_hash`, the first implementation, kept as the fallback when a rank's
-k-mers need more than one k-mer-space round): owner = hash(k-mer) % world
+K-mer-space rounds (`_sharded_count_rounds`): when a rank's k-mers do not fit the device in one go
+(`apgk_partition` answers APGK_E_RANGE), the ranks all-reduce their level-0 bucket totals, cut the
+level-0 bucket space into the same consecutive ranges everywhere (`plan_rounds`) and run the
+partition-first pipeline once per range (`apgk_partition_range`); a round's spectrum and totals are
+harvested before the next round reuses the buffers, so the context keeps the LAST round's shard table
+only (pass `on_round` to take every round's table).  Ranges ascend in k-mer order: the tables
+concatenated in (round, rank) order are the globally sorted table.
+
+Hash form (`sharded_count_hash`, the first implementation; APGK_SHARD_ROUNDS=0 selects it instead of the
+rounds): owner = hash(k-mer) % world
 (`apgk_owner_plan` / `apgk_owner_scatter`), exchange of full k-mers, then the whole pipeline again
 on the received keys (`apgk_finish_keys_device`).  It extracts and partitions every k-mer twice
 and sends 8 bytes per instance where the partition-first form sends 4.
@@ -53,11 +61,27 @@ def balanced_splitters(bucket_totals, world):
     return [int(x) for x in _splitters_tensor(bucket_totals, world).cpu()]
 
 
-def sharded_count(kc, rank, world, group=None, timings=None):
+def plan_rounds(level0_max, capacity):
+    """Cut the level-0 buckets [0, len(level0_max)) into consecutive ranges whose summed entries stay within
+    `capacity` (a single bucket above it gets a range of its own).  level0_max: per bucket, the largest count any
+    rank holds.  Deterministic in its input, so every rank derives the same rounds.  -> list of (lo, hi)."""
+    rounds, lo, acc = [], 0, 0
+    for d, t in enumerate(int(x) for x in level0_max):
+        if acc and acc + t > capacity:
+            rounds.append((lo, d))
+            lo, acc = d, 0
+        acc += t
+    rounds.append((lo, len(level0_max)))
+    return rounds
+
+
+def sharded_count(kc, rank, world, group=None, timings=None, on_round=None):
     """Run the sharded pipeline on this rank's KmerCounter `kc` (reads already in its store).
 
     Returns (spectrum uint64 array summed over all ranks, n_instances_global, n_distinct_global).
-    The rank's own shard table stays queryable in `kc` (counts of the k-mers it owns)."""
+    The rank's own shard table stays queryable in `kc` (counts of the k-mers it owns); when the k-mers need
+    several k-mer-space rounds that is the last round's shard -- `on_round(kc, i, n_rounds)` is called after
+    every round for callers that want each round's table."""
     from .kmers import ApgkError
 
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -113,9 +137,11 @@ def sharded_count(kc, rank, world, group=None, timings=None):
                        cum[:, bounds_t].reshape(-1), gathered[:, nb_all + 1:].reshape(-1)]).cpu().numpy()
     lap("w_plan")
     if int(small[0]):
-        if timings is not None:
-            timings["path"] = "hash"
-        return sharded_count_hash(kc, rank, world, group, timings)
+        if os.environ.get("APGK_SHARD_ROUNDS", "1") == "0":
+            if timings is not None:
+                timings["path"] = "hash"
+            return sharded_count_hash(kc, rank, world, group, timings)
+        return _sharded_count_rounds(kc, rank, world, P, dev, group, timings, on_round, want_peer)
     if int(small[1]) >= 2 ** 31:
         raise RuntimeError("a bucket piece holds 2^31 or more k-mers")
     bounds = [int(x) for x in small[2: 3 + world]]
@@ -179,6 +205,8 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         lap("w_count")
         e3.record()
     gather_ms = kc.stage_ms().get("owner", 0.0)
+    if on_round is not None:
+        on_round(kc, 0, 1)
     out = _reduce_results(kc, dev, group)
     lap("w_reduce")
     if timings is not None:
@@ -195,6 +223,140 @@ def sharded_count(kc, rank, world, group=None, timings=None):
         timings["bucket_range"] = (int(lo), int(hi))
         timings["prefix_bits"] = int(P)
     return out
+
+
+def _exchange_and_count(kc, rank, world, P, dev, group, want_peer):
+    """One partition-first exchange for the partition `kc` holds: all-gather of the bucket histograms, balanced
+    ranges, the owned range gathered from the peers' buffers (or through an all-to-all) and counted.
+    -> (bucket_lo, bucket_hi, path)."""
+    sizes_ptr, nb, elems_ptr, eb, n_elems = kc.partition_info()
+    sizes = _wrap(sizes_ptr, nb, "<i8", dev)
+    handle = np.zeros(64, dtype=np.uint8)
+    d2 = sub_ptr = None
+    if want_peer:
+        handle = kc.partition_export()
+        d2, sub_ptr = kc.partition_subsizes(max(0, (world - 1).bit_length()))
+    nb_all = 1 << P
+    mine = torch.empty(nb_all + 8, dtype=torch.int64, device=dev)
+    mine[:nb_all] = sizes
+    mine[nb_all:] = torch.from_numpy(handle.view(np.int64).copy()).to(dev)
+    gathered = torch.empty((world, nb_all + 8), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    all_sizes = gathered[:, :nb_all]
+    bounds_t = _splitters_tensor(all_sizes.sum(0), world)
+    cum = torch.zeros((world, nb_all + 1), dtype=torch.int64, device=dev)
+    torch.cumsum(all_sizes, 1, out=cum[:, 1:])
+    small = torch.cat([all_sizes.max().reshape(1), bounds_t, cum[:, bounds_t].reshape(-1),
+                       gathered[:, nb_all:].reshape(-1)]).cpu().numpy()
+    if int(small[0]) >= 2 ** 31:
+        raise RuntimeError("a bucket piece holds 2^31 or more k-mers")
+    bounds = [int(x) for x in small[1: 2 + world]]
+    at_bounds = small[2 + world: 2 + world + world * (world + 1)].reshape(world, world + 1)
+    handles = small[2 + world + world * (world + 1):].reshape(world, 8)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    sizes_u32 = all_sizes.to(torch.int32).contiguous()
+    peer_ptrs = None
+    if want_peer:
+        peer_ptrs = _open_peers(kc, rank, world, handles)
+        ok = torch.tensor([1 if peer_ptrs is not None else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if not int(ok.item()):
+            peer_ptrs = None
+    if peer_ptrs is not None:
+        sub = _wrap(sub_ptr, nb_all << d2, "<i4", dev)
+        sub_recv = torch.empty(world * ((hi - lo) << d2) + 1, dtype=torch.int32, device=dev)
+        dist.all_to_all_single(sub_recv[: world * ((hi - lo) << d2)], sub,
+                               output_split_sizes=[(hi - lo) << d2] * world,
+                               input_split_sizes=[(bounds[r + 1] - bounds[r]) << d2 for r in range(world)], group=group)
+        torch.cuda.current_stream().synchronize()
+        kc.count_pieces_peer(peer_ptrs, sizes_u32.data_ptr(), at_bounds[:, rank].astype(np.uint64), lo, hi,
+                             split_bits=d2, d_sub_sizes=sub_recv.data_ptr())
+        return lo, hi, "peer"
+    send_counts = (at_bounds[rank, 1:] - at_bounds[rank, :-1]).astype(np.int64)
+    recv_counts = (at_bounds[:, rank + 1] - at_bounds[:, rank]).astype(np.int64)
+    n_recv = int(recv_counts.sum())
+    words = 1 if eb == 4 else eb // 8
+    tstr, tdt = ("<i4", torch.int32) if eb == 4 else ("<i8", torch.int64)
+    send = _wrap(elems_ptr, max(n_elems, 1) * words, tstr, dev) if elems_ptr else torch.empty(1, dtype=tdt, device=dev)
+    need = max(n_recv, 1) * eb
+    buf = getattr(kc, "_recv_buf", None)
+    if buf is None or buf.numel() * 8 < need:
+        kc._recv_buf = None
+        del buf
+        torch.cuda.empty_cache()
+        buf = torch.empty(int(need * 1.02) // 8 + 1024, dtype=torch.int64, device=dev)
+        kc._recv_buf = buf
+    recv = buf.view(tdt)
+    dist.all_to_all_single(recv[: n_recv * words], send[: n_elems * words],
+                           output_split_sizes=[int(c) * words for c in recv_counts],
+                           input_split_sizes=[int(c) * words for c in send_counts], group=group)
+    torch.cuda.current_stream().synchronize()
+    del send
+    seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
+    kc.count_pieces(recv.data_ptr(), world, sizes_u32.data_ptr(), seg_off, lo, hi)
+    return lo, hi, "nccl"
+
+
+def _sharded_count_rounds(kc, rank, world, P, dev, group, timings, on_round, want_peer):
+    """The partition-first pipeline in k-mer-space rounds (see the module docstring)."""
+    tot0, cap = kc.level0_totals()
+    t = torch.from_numpy(np.concatenate([tot0.astype(np.int64), [-(cap if cap else 2 ** 62)]])).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)   # per bucket: the largest share; smallest capacity (as -cap)
+    t = t.cpu().numpy()
+    cap_all = int(-t[-1])
+    forced = int(os.environ.get("APGK_SHARD_ROUND_KEYS", "0"))
+    # a round holds this rank's partition AND the shard it receives (about the same size): half the budget each
+    capacity = forced if forced > 0 else max(1, cap_all // 2)
+    rounds = plan_rounds(t[:-1], capacity)
+    spec = {}
+    ni = nd = 0
+    path = "?"
+    ranges = []
+    for i, (lo0, hi0) in enumerate(rounds):
+        kc.partition_range(P, lo0, hi0)
+        blo, bhi, path = _exchange_and_count(kc, rank, world, P, dev, group, want_peer)
+        ranges.append((blo, bhi))
+        a, b = kc.totals()
+        ni += a
+        nd += b
+        f, m = kc.spectrum_sparse()
+        for x, y in zip(f.tolist(), m.tolist()):
+            spec[x] = spec.get(x, 0) + y
+        if on_round is not None:
+            on_round(kc, i, len(rounds))
+        dist.barrier(group=group)   # the peers are done reading this round's partition buffers
+    # global sums: the dense part in one all-reduce with the totals, the (rare) frequencies beyond it gathered
+    DENSE = 65536
+    dense = np.zeros(DENSE + 2, dtype=np.int64)
+    far = {}
+    for x, y in spec.items():
+        if x < DENSE:
+            dense[x] = y
+        else:
+            far[x] = y
+    dense[DENSE], dense[DENSE + 1] = ni, nd
+    td = torch.from_numpy(dense).to(dev)
+    dist.all_reduce(td, op=dist.ReduceOp.SUM, group=group)
+    dense = td.cpu().numpy()
+    far_all = [None] * world
+    dist.all_gather_object(far_all, far, group=group)
+    far = {}
+    for d_ in far_all:
+        for x, y in d_.items():
+            far[x] = far.get(x, 0) + y
+    nz = np.nonzero(dense[:DENSE])[0]
+    top = max([int(nz.max()) if len(nz) else 0] + list(far.keys()))
+    out = np.zeros(top + 1, dtype=np.uint64)
+    out[: min(top + 1, DENSE)] = dense[: min(top + 1, DENSE)].astype(np.uint64)
+    for x, y in far.items():
+        out[x] = y
+    if timings is not None:
+        timings["path"] = "partition-first/rounds/" + path
+        timings["n_rounds"] = len(rounds)
+        timings["prefix_bits"] = int(P)
+        timings["level0_rounds"] = [tuple(r) for r in rounds]
+        timings["bucket_ranges"] = ranges
+    return out, int(dense[DENSE]), int(dense[DENSE + 1])
 
 
 def _open_peers(kc, rank, world, handles):

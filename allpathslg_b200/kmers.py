@@ -243,6 +243,19 @@ class KmerCounter:
         """levels 0+1 only; raises ApgkError (code APGK_E_RANGE) if one k-mer-space round is not enough"""
         self._ck(self._L.apgk_partition(self._h, prefix_bits))
 
+    def partition_range(self, prefix_bits, d0_lo, d0_hi):
+        """Levels 0 + 1 restricted to the level-0 buckets [d0_lo, d0_hi): one k-mer-space round of the sharded form."""
+        self._ck(self._L.apgk_partition_range(self._h, prefix_bits, d0_lo, d0_hi))
+
+    def level0_totals(self):
+        """-> (uint64[2^D0] instances per level-0 bucket of the last partition call, round capacity in instances)."""
+        n = C.c_uint32()
+        cap = C.c_uint64()
+        self._ck(self._L.apgk_level0_totals(self._h, None, 0, C.byref(n), C.byref(cap)))
+        out = np.zeros(n.value, dtype=np.uint64)
+        self._ck(self._L.apgk_level0_totals(self._h, out.ctypes.data, n.value, None, None))
+        return out, cap.value
+
     def partition_info(self):
         """-> (d_bucket_sizes ptr (uint64[n_buckets]), n_buckets, d_elems ptr, elem_bytes, n_elems)"""
         a, b = C.c_void_p(), C.c_void_p()

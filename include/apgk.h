@@ -194,6 +194,16 @@ int apgk_choose_prefix_bits(apgk_ctx* ctx, uint64_t upper, int32_t* prefix_bits)
 /* Levels 0+1 over the read store with 2^prefix_bits buckets (0 = choose).  APGK_E_RANGE when the
  * k-mers would need more than one k-mer-space round on this device. */
 int apgk_partition(apgk_ctx* ctx, int32_t prefix_bits);
+/* K-mer-space rounds of the sharded form (a rank whose k-mers do not fit one round): the same two levels
+ * restricted to the level-0 buckets [d0_lo, d0_hi) -- the leading D0 bits of the canonical k-mer, D0 as
+ * apgk_geometry reports it for this prefix_bits.  Buckets outside the range come out empty.  The caller runs
+ * the rounds: partition_range -> exchange -> apgk_count_pieces* -> harvest the round's spectrum / table ->
+ * next range (allpathslg_b200.dist does, with the same ranges on every rank). */
+int apgk_partition_range(apgk_ctx* ctx, int32_t prefix_bits, int32_t d0_lo, int32_t d0_hi);
+/* Level-0 bucket totals (k-mer instances per leading-D0-bits bucket, HOST, *n_level0 = 2^D0 entries) of the last
+ * apgk_partition* call on this context -- also after one that failed with APGK_E_RANGE -- and the number of
+ * instances one round may hold under the device-memory budget; what the ranks need to agree on the ranges. */
+int apgk_level0_totals(apgk_ctx* ctx, uint64_t* totals_out, uint32_t cap, uint32_t* n_level0, uint64_t* round_capacity);
 /* Result of apgk_partition, all DEVICE pointers owned by the library: bucket sizes
  * (uint64[n_buckets]), the elements grouped by bucket (elem_bytes each: 4, or 8 * W). */
 int apgk_partition_info(apgk_ctx* ctx, const uint64_t** d_bucket_sizes, uint64_t* n_buckets, void** d_elems,

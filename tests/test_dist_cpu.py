@@ -135,3 +135,24 @@ def test_balanced_splitters():
         assert b[0] == 0 and b[-1] == 4096 and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
         per = [int(t[b[r]:b[r + 1]].sum()) for r in range(world)]
         assert sum(per) == int(t.sum()) and max(per) - min(per) <= 2 * 1000
+
+
+def test_plan_rounds_host_logic():
+    """k-mer-space rounds of the sharded form: consecutive level-0 bucket ranges within the capacity, covering
+    every bucket once, a bucket above the capacity alone in its range; deterministic."""
+    from allpathslg_b200.dist import plan_rounds
+
+    rng = np.random.default_rng(3)
+    for cap in (1, 50, 1000, 10 ** 9):
+        tot = rng.integers(0, 400, size=257)
+        tot[100] = 5000
+        r = plan_rounds(tot, cap)
+        assert r[0][0] == 0 and r[-1][1] == len(tot)
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        for lo, hi in r:
+            assert hi > lo
+            if int(tot[lo:hi].sum()) > cap:   # only a single bucket above the capacity (after empty ones) may exceed it
+                assert int((tot[lo:hi] > 0).sum()) == 1 and tot[hi - 1] > 0
+        assert r == plan_rounds(tot.tolist(), cap)
+    assert plan_rounds([0, 0, 0], 10) == [(0, 3)]
+    assert plan_rounds([], 10) == [(0, 0)]

@@ -537,6 +537,80 @@ def test_partition_first_shards_emulated_ranks(oracle, K, world, n_reads, exchan
         kc.close()
 
 
+@pytest.mark.parametrize("K,world,n_reads", [(25, 3, 30_000), (48, 2, 12_000), (20, 2, 20_000)])
+def test_partition_first_rounds_emulated_ranks(oracle, K, world, n_reads):
+    """K-mer-space rounds of the partition-first form, emulated on one GPU: the level-0 bucket space is cut into
+    the same ranges on every "rank" (dist.plan_rounds on the per-bucket maximum), every round is one
+    apgk_partition_range -> exchange -> apgk_count_pieces, and a round's table and spectrum are harvested before
+    the next round.  Tables concatenated in (round, rank) order must be the oracle's sorted table."""
+    import torch
+
+    from allpathslg_b200 import KmerCounter
+    from allpathslg_b200.dist import balanced_splitters, plan_rounds
+
+    L = 100
+    sp = oracle.synth_params(200_000, L)
+    p, o = oracle.synth_reads(sp, 0, n_reads)
+    ek, ec, en = oracle.count(p, o, K)
+    share = [(n_reads * r) // world for r in range(world + 1)]
+    kcs = []
+    for r in range(world):
+        kc = KmerCounter(K)
+        n = share[r + 1] - share[r]
+        pr, _ = oracle.synth_reads(sp, share[r], n)
+        kc.add_reads_uniform(pr, n, L)
+        kcs.append(kc)
+    P = kcs[0].choose_prefix_bits(max(kc.window_upper() for kc in kcs))
+    tots = []
+    for kc in kcs:
+        kc.partition(P)                      # fits here; also leaves the level-0 totals behind
+        t, cap = kc.level0_totals()
+        assert cap > 0 and int(t.sum()) == kc.partition_info()[4]
+        tots.append(t)
+    rounds = plan_rounds(np.max(np.stack(tots), axis=0), max(1, en // (3 * world)))
+    assert len(rounds) >= 3 and rounds[0][0] == 0 and rounds[-1][1] == len(tots[0])
+    got_k, got_c = [], []
+    total_spec = np.zeros(1, dtype=np.uint64)
+    n_seen = 0
+    for lo0, hi0 in rounds:
+        sizes, elems, eb = [], [], None
+        for kc in kcs:
+            kc.partition_range(P, lo0, hi0)
+            sp_, nb, ep, eb, ne = kc.partition_info()
+            sz = torch.as_tensor(_CudaView(sp_, nb, "<i8"), device="cuda").cpu().numpy()
+            dt = "<i4" if eb == 4 else "<i8"
+            words = 1 if eb == 4 else eb // 8
+            e = torch.as_tensor(_CudaView(ep, max(ne, 1) * words, dt), device="cuda")[: ne * words].cpu().numpy() if ne else \
+                np.zeros(0, dtype=np.int32 if eb == 4 else np.int64)
+            assert int(sz.sum()) == ne
+            sizes.append(sz); elems.append(e)
+        all_sizes = np.stack(sizes)
+        bounds = balanced_splitters(all_sizes.sum(0), world)
+        words = 1 if eb == 4 else eb // 8
+        cum = np.concatenate([np.zeros((world, 1), np.int64), np.cumsum(all_sizes, axis=1)], axis=1)
+        d_sizes = torch.from_numpy(all_sizes.astype(np.int32)).cuda().contiguous()
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            parts = [elems[s][cum[s, lo] * words: cum[s, hi] * words] for s in range(world)]
+            seg_off = np.concatenate([[0], np.cumsum([len(x) // words for x in parts])[:-1]]).astype(np.uint64)
+            recv = torch.from_numpy(np.concatenate(parts) if sum(len(x) for x in parts) else np.zeros(1, parts[0].dtype)).cuda()
+            kcs[r].count_pieces(recv.data_ptr(), world, d_sizes.data_ptr(), seg_off, lo, hi)
+            gk, gc = kcs[r].counts()
+            got_k.append(gk); got_c.append(gc)
+            n_seen += kcs[r].totals()[0]
+            s = kcs[r].spectrum()
+            if len(s) > len(total_spec):
+                total_spec = np.concatenate([total_spec, np.zeros(len(s) - len(total_spec), np.uint64)])
+            total_spec[: len(s)] += s
+    gk = np.concatenate(got_k); gc = np.concatenate(got_c)
+    assert n_seen == en
+    assert len(gk) == len(ek) and (gk == ek).all() and (gc.astype(np.uint64) == ec).all()
+    es = oracle.spectrum(ec)
+    assert len(total_spec) == len(es) and (total_spec == es).all()
+    for kc in kcs:
+        kc.close()
+
+
 class _CudaView:
     def __init__(self, ptr, n, typestr):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
