@@ -192,7 +192,8 @@ int apgk_window_upper(const apgk_ctx* ctx, uint64_t* upper);
  * and pass the result to apgk_partition so that all of them use the same geometry. */
 int apgk_choose_prefix_bits(apgk_ctx* ctx, uint64_t upper, int32_t* prefix_bits);
 /* Levels 0+1 over the read store with 2^prefix_bits buckets (0 = choose).  APGK_E_RANGE when the
- * k-mers would need more than one k-mer-space round on this device. */
+ * k-mers would need more than one k-mer-space round on this device: run the rounds with
+ * apgk_level0_totals + apgk_partition_range then. */
 int apgk_partition(apgk_ctx* ctx, int32_t prefix_bits);
 /* K-mer-space rounds of the sharded form (a rank whose k-mers do not fit one round): the same two levels
  * restricted to the level-0 buckets [d0_lo, d0_hi) -- the leading D0 bits of the canonical k-mer, D0 as
