@@ -325,7 +325,20 @@ def _sharded_count_rounds(kc, rank, world, P, dev, group, timings, on_round, wan
         if on_round is not None:
             on_round(kc, i, len(rounds))
         dist.barrier(group=group)   # the peers are done reading this round's partition buffers
-    # global sums: the dense part in one all-reduce with the totals, the (rare) frequencies beyond it gathered
+    out, ni_g, nd_g = merge_sparse_spectra(spec, ni, nd, world, dev, group)
+    if timings is not None:
+        timings["path"] = "partition-first/rounds/" + path
+        timings["n_rounds"] = len(rounds)
+        timings["prefix_bits"] = int(P)
+        timings["level0_rounds"] = [tuple(r) for r in rounds]
+        timings["bucket_ranges"] = ranges
+    return out, ni_g, nd_g
+
+
+def merge_sparse_spectra(spec, ni, nd, world, dev, group=None):
+    """Sum per-rank sparse spectra {frequency: n_kmers} (disjoint k-mer sets, so plain sums) and the totals over
+    the ranks: frequencies below 65536 and the totals in one all-reduce, the (rare) larger ones gathered.
+    -> (dense uint64 spectrum up to the largest frequency, n_instances, n_distinct).  Works on gloo and nccl."""
     DENSE = 65536
     dense = np.zeros(DENSE + 2, dtype=np.int64)
     far = {}
@@ -333,7 +346,7 @@ def _sharded_count_rounds(kc, rank, world, P, dev, group, timings, on_round, wan
         if x < DENSE:
             dense[x] = y
         else:
-            far[x] = y
+            far[int(x)] = int(y)
     dense[DENSE], dense[DENSE + 1] = ni, nd
     td = torch.from_numpy(dense).to(dev)
     dist.all_reduce(td, op=dist.ReduceOp.SUM, group=group)
@@ -350,12 +363,6 @@ def _sharded_count_rounds(kc, rank, world, P, dev, group, timings, on_round, wan
     out[: min(top + 1, DENSE)] = dense[: min(top + 1, DENSE)].astype(np.uint64)
     for x, y in far.items():
         out[x] = y
-    if timings is not None:
-        timings["path"] = "partition-first/rounds/" + path
-        timings["n_rounds"] = len(rounds)
-        timings["prefix_bits"] = int(P)
-        timings["level0_rounds"] = [tuple(r) for r in rounds]
-        timings["bucket_ranges"] = ranges
     return out, int(dense[DENSE]), int(dense[DENSE + 1])
 
 

@@ -156,3 +156,32 @@ def test_plan_rounds_host_logic():
         assert r == plan_rounds(tot.tolist(), cap)
     assert plan_rounds([0, 0, 0], 10) == [(0, 3)]
     assert plan_rounds([], 10) == [(0, 0)]
+
+
+def _merge_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from allpathslg_b200.dist import merge_sparse_spectra
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = [{1: 5, 70000: 1}, {1: 7, 2: 3, 70000: 2, 80000: 1}, {}][rank]
+    spec, ni, nd = merge_sparse_spectra(mine, 100 * (rank + 1), 10 * (rank + 1), world, torch.device("cpu"))
+    np.save(os.path.join(out_dir, "m%d.npy" % rank), np.concatenate([spec, [ni, nd]]).astype(np.uint64))
+    dist.destroy_process_group()
+
+
+def test_rounds_spectrum_merge_gloo(tmp_path):
+    """The reduction that ends the sharded form's k-mer-space rounds: per-rank sparse spectra (frequencies beyond the
+    dense 65536 included, one rank with nothing at all) and the totals, summed over three gloo ranks."""
+    world = 3
+    mp.spawn(_merge_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), "m%d.npy" % r)) for r in range(world)]
+    for o in outs:
+        assert (o == outs[0]).all()
+    spec, ni, nd = outs[0][:-2], int(outs[0][-2]), int(outs[0][-1])
+    assert len(spec) == 80001 and spec[1] == 12 and spec[2] == 3 and spec[70000] == 3 and spec[80000] == 1
+    assert int(spec.sum()) == 19 and (ni, nd) == (600, 60)
