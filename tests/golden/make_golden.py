@@ -49,6 +49,9 @@ OCC_HAND = [
     # GATTACA: GATT->AATC(rc) ATTA(fw) TTAC->GTAA(rc) TACA(fw); TGTAATC: TGTA->TACA(rc) GTAA(fw) TAAT->ATTA(rc) AATC(fw)
     dict(reads=["GATTACA", "TGTAATC"], K=4, kmers=[13, 60, 176, 196],
          occ=[[[0, -1], [1, 4]], [[0, 2], [1, -3]], [[0, -3], [1, 2]], [[0, 4], [1, -1]]]),
+    # even K, palindromes count as forward: ACGTACGT K=4 -> ACGT(+1, pal) CGTA(+2) GTAC(+3, pal) TACG->CGTA(-4) ACGT(+5)
+    # ACGT=0b00011011=27  CGTA=0b01101100=108  GTAC=0b10110001=177
+    dict(reads=["ACGTACGT"], K=4, kmers=[27, 108, 177], occ=[[[0, 1], [0, 5]], [[0, 2], [0, -4]], [[0, 3]]]),
     # a read shorter than K still owns read id 0
     dict(reads=["AC", "ACG"], K=3, kmers=[6], occ=[[[1, 1]]]),
     # reads without bases keep their ids; TT is AA read backwards
