@@ -176,6 +176,38 @@ def workload_config(n_gpus):
             "l2_policy": "inputs (1.5 GB packed reads, 36 GB keys) exceed the 126 MB L2; no flush needed"}
 
 
+def measure_lookups(kc, torch, total_bases):
+    """k-mer frequency of every window of the reads (FindErrors table lookups), bulk form, device output."""
+    out = torch.empty(total_bases, dtype=torch.int32, device="cuda")
+    kc.read_freqs_device(out.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lms = kc.read_freqs_device(out.data_ptr())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n_valid = int(kc.totals()[0])  # one lookup per window that lies inside a read = per k-mer instance
+    del out
+    torch.cuda.empty_cache()
+    return {"what": "k-mer frequency of every window of the reads (FindErrors table lookups), bulk form, device output",
+            "ms": round(dt * 1e3, 2), "value": round(n_valid / dt / 1e9, 3), "unit": "G lookups/s",
+            "stage_ms": {k_: round(v, 2) for k_, v in lms.items()}, "n_lookups": n_valid,
+            "direct_form": "per-window table search (APGK_FREQ_DIRECT=1): see profiles/r01_occ.txt"}
+
+
+def measure_records(kc, torch):
+    """(read id, signed position) of every k-mer instance grouped by k-mer: second sweep over the reads."""
+    kc.build_occurrences()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    info = kc.build_occurrences()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"what": "(read id, signed position) of every k-mer instance grouped by k-mer: bucket scatter + per-bucket placement + per-run sort",
+            "ms": round(dt * 1e3, 2), "value": round(info["n_occ"] / dt / 1e9, 3), "unit": "G records/s",
+            "stage_ms": {k_: round(v, 2) for k_, v in info["ms"].items()}, "n_big_runs": info["n_big_runs"],
+            "bytes_out": int(info["n_occ"]) * 8}
+
+
 def run_ours(args):
     import torch
 
@@ -294,45 +326,20 @@ def run_ours(args):
     # exact size-independent invariant: sum f * spectrum[f] == instances
     inv_ok = int((spec * np.arange(len(spec), dtype=np.uint64)).sum()) == n_inst_total
 
-    # ---------------- frequency-table lookups (what error correction asks): the count of the k-mer at every base of
-    # the store into a device buffer, N=1 only; reported beside the headline
-    lookups = None
+    # ---------------- side measurements (N=1 only, after the timed regions; a failure here must never cost the
+    # headline line): the frequency of every window of the reads into a device buffer (what error correction
+    # asks), then the occurrence records (SortKmers / KmerParcels payload)
+    lookups = records = None
     if world == 1 and os.environ.get("APGK_BENCH_LOOKUPS", "1") != "0":
-      try:
-        out = torch.empty(total_bases, dtype=torch.int32, device="cuda")
-        kc.read_freqs_device(out.data_ptr())
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        lms = kc.read_freqs_device(out.data_ptr())
-        torch.cuda.synchronize()
-        dt_l = time.perf_counter() - t0
-        n_valid = int(kc.totals()[0])  # one lookup per window that lies inside a read = per k-mer instance
-        lookups = {"what": "k-mer frequency of every window of the reads (FindErrors table lookups), bulk form, device output",
-                   "ms": round(dt_l * 1e3, 2), "value": round(n_valid / dt_l / 1e9, 3), "unit": "G lookups/s",
-                   "stage_ms": {k_: round(v, 2) for k_, v in lms.items()}, "n_lookups": n_valid,
-                   "direct_form": "per-window table search (APGK_FREQ_DIRECT=1): see profiles/r01_occ.txt"}
-        del out
-        torch.cuda.empty_cache()
-      except Exception as e:  # a side measurement must never cost the headline line
-        lookups = {"error": str(e)[:200]}
-
-    # ---------------- occurrence records (SortKmers / KmerParcels payload): second sweep over the reads, N=1 only.
-    # Not part of the headline step; reported beside it.
-    records = None
+        try:
+            lookups = measure_lookups(kc, torch, total_bases)
+        except Exception as e:
+            lookups = {"error": str(e)[:200]}
     if world == 1 and os.environ.get("APGK_BENCH_RECORDS", "1") != "0":
-      try:
-        kc.build_occurrences()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        info = kc.build_occurrences()
-        torch.cuda.synchronize()
-        dt_r = time.perf_counter() - t0
-        records = {"what": "(read id, signed position) of every k-mer instance grouped by k-mer: table lookup sweep + per-run sort",
-                   "ms": round(dt_r * 1e3, 2), "value": round(info["n_occ"] / dt_r / 1e9, 3), "unit": "G records/s",
-                   "stage_ms": {k_: round(v, 2) for k_, v in info["ms"].items()}, "n_big_runs": info["n_big_runs"],
-                   "bytes_out": int(info["n_occ"]) * 8}
-      except Exception as e:
-        records = {"error": str(e)[:200]}
+        try:
+            records = measure_records(kc, torch)
+        except Exception as e:
+            records = {"error": str(e)[:200]}
 
     if rank != 0:
         if dist is not None:
