@@ -18,7 +18,8 @@ MAX_K = 96
 
 class Config(C.Structure):
     _fields_ = [("K", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("prefix_bits", C.c_int32),
-                ("reserve_bases", C.c_uint64), ("max_round_keys", C.c_uint64)]
+                ("reserve_bases", C.c_uint64), ("max_round_keys", C.c_uint64),
+                ("max_inner_keys", C.c_uint64)]
 
 
 class SynthParams(C.Structure):

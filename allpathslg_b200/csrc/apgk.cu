@@ -6,13 +6,16 @@
 //   local     k_local (+ k_big for oversize buckets)           B      -> temp records in A/B + spectrum
 //   table     scan of per-bucket record counts -> k_compact    temp   -> sorted (k-mer, count) table + index
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <map>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/apgk.h"
@@ -70,6 +73,7 @@ struct apgk_ctx {
   // ---- read store
   DevBuf bases, starts, staging, off_dev;
   uint64_t total_bases = 0, n_reads = 0;
+  uint64_t n_windows = 0;            // exact k-mer instances of the store: sum over reads of max(0, L - K + 1)
   // ---- streamed ingest (APGK_ASYNC_INGEST): copies in flight on copy_stream, one event per slice
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_main = nullptr;
@@ -77,6 +81,13 @@ struct apgk_ctx {
   std::vector<uint64_t> slice_end;   // bases resident once slice i has landed
   size_t n_slices = 0;               // pending slices (0 = nothing in flight)
   // ---- pipeline buffers
+  DevBuf tot0_dev, res;              // level-0 bucket totals; the step's result block (RES_*)
+  unsigned long long* res_host = nullptr;   // pinned mirror of `res`
+  HostPlan hp0;                      // level-0 plan: a function of the input size, kept from step to step
+  uint64_t hp0_elems = ~0ull; uint32_t hp0_tile = 0;
+  std::map<std::pair<const void*, size_t>, int> kattr;   // (kernel, dynamic smem) -> occupancy, attribute set
+  bool table_pending = false;        // single-round step: the table's size is read at the final synchronisation
+  void* tmp_keys_last = nullptr;     // where the last count_buckets left its per-bucket records
   DevBuf A, B, T, chunksum, chunksum0, plan0, out_off_local, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
       scratch, stacks, spec_dense, spec_ovf, misc, deferred;
   // ---- results
@@ -114,9 +125,12 @@ struct apgk_ctx {
   std::vector<uint64_t> owner_counts;
   HostPlan owner_plan;
   DevBuf owner_plan_dev;
-  // ---- instrumentation
-  cudaEvent_t ev[APGK_N_STAGES][2]{};
-  bool ev_used[APGK_N_STAGES]{};
+  // ---- instrumentation: one (start, end) event pair per stage interval of the current step, taken from a
+  // pool and read back at the step's final synchronisation (a stage may run many times per step)
+  struct StageIv { int stage; cudaEvent_t e0, e1; bool ended; };
+  std::vector<StageIv> ivs;
+  size_t n_ivs = 0;
+  int open_iv[APGK_N_STAGES]{};
   float stage_ms[APGK_N_STAGES]{};
   uint64_t launches = 0;
 };
@@ -145,27 +159,44 @@ namespace {
 static const bool kSyncDebug = getenv("APGK_SYNC_DEBUG") != nullptr;  // sync after every launch to localise faults
 #define LAUNCHED() do { c->launches++; CU(cudaGetLastError()); if (kSyncDebug) CU(cudaStreamSynchronize(c->stream)); } while (0)
 
-// A stage may run once per round: its previous interval is folded into stage_ms before the events are reused.
-void stage_flush(apgk_ctx* c, int s) {
-  if (!c->ev_used[s]) return;
-  float ms = 0;
-  if (cudaEventSynchronize(c->ev[s][1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev[s][0], c->ev[s][1]) == cudaSuccess)
-    c->stage_ms[s] += ms;
-  c->ev_used[s] = false;
-}
+// Stage intervals are recorded without ever waiting on the device mid-step; stages_collect() folds them into
+// stage_ms once the step's stream has been synchronised.
 static const bool kTrace = getenv("APGK_TRACE") != nullptr;  // host wall clock at every stage boundary, to stderr
 static double trace_now() {
   timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
+void stages_reset(apgk_ctx* c) {
+  c->n_ivs = 0;
+  for (int s = 0; s < APGK_N_STAGES; s++) { c->stage_ms[s] = 0; c->open_iv[s] = -1; }
+}
 void stage_begin(apgk_ctx* c, int s) {
-  stage_flush(c, s);
+  if (c->n_ivs == c->ivs.size()) {
+    apgk_ctx::StageIv iv{s, nullptr, nullptr, false};
+    if (cudaEventCreate(&iv.e0) != cudaSuccess || cudaEventCreate(&iv.e1) != cudaSuccess) return;
+    c->ivs.push_back(iv);
+  }
+  apgk_ctx::StageIv& iv = c->ivs[c->n_ivs];
+  iv.stage = s; iv.ended = false;
+  c->open_iv[s] = (int)c->n_ivs++;
   if (kTrace) fprintf(stderr, "[apgk %.2f] begin %s\n", trace_now(), kStageNames[s]);
-  cudaEventRecord(c->ev[s][0], c->stream); c->ev_used[s] = true;
+  cudaEventRecord(iv.e0, c->stream);
 }
 void stage_end(apgk_ctx* c, int s) {
-  cudaEventRecord(c->ev[s][1], c->stream);
+  const int i = c->open_iv[s];
+  if (i < 0) return;
+  cudaEventRecord(c->ivs[i].e1, c->stream);
+  c->ivs[i].ended = true;
+  c->open_iv[s] = -1;
   if (kTrace) fprintf(stderr, "[apgk %.2f] end   %s\n", trace_now(), kStageNames[s]);
+}
+// after the stream has been synchronised
+void stages_collect(apgk_ctx* c) {
+  for (size_t i = 0; i < c->n_ivs; i++) {
+    float ms = 0;
+    if (c->ivs[i].ended && cudaEventElapsedTime(&ms, c->ivs[i].e0, c->ivs[i].e1) == cudaSuccess) c->stage_ms[c->ivs[i].stage] += ms;
+  }
+  c->n_ivs = 0;
 }
 
 int words_for(int K) { return (2 * K + 63) / 64; }
@@ -216,22 +247,6 @@ void build_plan(HostPlan& hp, const std::vector<uint64_t>& seg_sizes, uint32_t t
   }
   hp.lp.bins = bins; hp.lp.n_segments = S; hp.lp.chunk_tiles = ct;
   hp.lp.n_tiles = hp.seg_tile0[S]; hp.lp.n_chunks = hp.seg_chunk0[S]; hp.lp.tile_elems = tile_elems;
-}
-
-// copy the plan arrays to the device (ctx->plan) and patch the pointers
-int upload_plan(apgk_ctx* c, HostPlan& hp) {
-  const size_t S1 = hp.seg_tile0.size();
-  const size_t bytes = S1 * (4 + 4 + 8) + 64;
-  CU(c->plan.ensure(bytes));
-  unsigned char* d = c->plan.as<unsigned char>();
-  CU(cudaMemcpyAsync(d, hp.seg_start.data(), S1 * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d + S1 * 8, hp.seg_tile0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d + S1 * 12, hp.seg_chunk0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));  // the host vectors may die before the copy otherwise
-  hp.lp.seg_start = (const uint64_t*)d;
-  hp.lp.seg_tile0 = (const uint32_t*)(d + S1 * 8);
-  hp.lp.seg_chunk0 = (const uint32_t*)(d + S1 * 12);
-  return APGK_OK;
 }
 
 // per-chunk digit counts (chunksum, written by the hist kernels) -> per-chunk exclusive prefixes,
@@ -367,14 +382,11 @@ enum RunMode { RUN_FULL = 0, RUN_PARTITION = 1 };
 template <int W, typename ElemB>
 int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode);
 template <int W, typename ElemB>
-int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N_all, uint64_t& n_prev);
+int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N_all, uint64_t& n_prev, Key<W>* tmp_keys, bool nosync);
 
-// upper bound of the k-mer instances a run over the read store will see
-uint64_t window_upper(const apgk_ctx* c) {
-  // reads shorter than K aside, a read of L bases yields L-K+1 windows
-  const uint64_t lost = c->n_reads * (uint64_t)(c->cfg.K - 1);
-  return c->total_bases > lost ? c->total_bases - lost : 1;
-}
+// k-mer instances a run over the read store sees: exact, accumulated at ingest (a read of L bases yields
+// max(0, L-K+1) windows), so the host sizes buffers and grids without waiting for the level-0 histogram
+uint64_t window_upper(const apgk_ctx* c) { return c->n_windows; }
 
 // Geometry of a run over `upper` instances (forced_P > 0 overrides the choice: ranks of a sharded run
 // must agree on it).  Returns true when level 1 stores 32-bit remainders.
@@ -383,6 +395,7 @@ bool select_geometry(apgk_ctx* c, uint64_t upper, int forced_P) {
   // decide element type of the level-1 buffer first (it fixes LOCAL_MAX, which fixes P)
   int lm_u32 = LM_U32;
   if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) lm_u32 = atoi(e); }
+  if (upper == 0) upper = 1;
   if (forced_P > 0) {
     make_geom(c, std::max(2, std::min(24, forced_P)));
     return W == 1 && c->geom.REM <= 32;
@@ -402,11 +415,26 @@ bool select_geometry(apgk_ctx* c, uint64_t upper, int forced_P) {
   return u32;
 }
 
+template <int W> int compact_table(apgk_ctx* c, uint64_t total);
+
+// The result block: a few words the kernels of a step leave for the host, fetched with ONE copy at the
+// step's final synchronisation (RES_* index c->res, 16 x u64 on the device, mirrored in pinned host memory).
+enum { RES_RANGE_N = 0, RES_SUM_TOT0 = 1, RES_FLAGS = 2, RES_DISTINCT = 3, RES_TABLE_OVF = 4, RES_WORDS = 16 };
+
+int fetch_results(apgk_ctx* c) {
+  CU(cudaMemcpyAsync(c->res_host, c->res.p, RES_WORDS * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return APGK_OK;
+}
+
 template <int W>
 int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode = RUN_FULL, int forced_P = 0) {
   invalidate_results(c);
-  for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
+  stages_reset(c);
   select_geometry<W>(c, dev_keys ? n_keys : window_upper(c), forced_P);
+  if (!c->res_host) CU(cudaHostAlloc((void**)&c->res_host, RES_WORDS * 8, cudaHostAllocDefault));
+  CU(c->res.ensure(RES_WORDS * 8));
+  CU(cudaMemsetAsync(c->res.p, 0, RES_WORDS * 8, c->stream));
   stage_begin(c, ST_TOTAL);
   int rc;
   if constexpr (W == 1) {
@@ -415,13 +443,33 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mo
   } else {
     rc = run_levels<W, Key<W>>(c, dev_keys, n_keys, mode);
   }
-  if (rc) return rc;
+  if (rc) { cudaStreamSynchronize(c->stream); c->n_ivs = 0; c->table_pending = false; return rc; }
   stage_end(c, ST_TOTAL);
   c->n_deferred = 0;
   if (mode == RUN_FULL && c->deferred.p && c->n_instances)
     CU(cudaMemcpyAsync(&c->n_deferred, c->deferred.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  for (int s = 0; s < APGK_N_STAGES; s++) stage_flush(c, s);
+  { int r2 = fetch_results(c); if (r2) return r2; }   // the step's one synchronisation
+  if (c->res_host[RES_FLAGS] & 1ull) FAIL(APGK_E_RANGE, "a level-0 bucket holds 2^32 or more k-mers");
+  if (c->res_host[RES_SUM_TOT0] && c->res_host[RES_SUM_TOT0] != c->n_instances)
+    FAIL(APGK_E_STATE, "internal: level-0 histogram counts %llu k-mers, the read store holds %llu windows",
+         (unsigned long long)c->res_host[RES_SUM_TOT0], (unsigned long long)c->n_instances);
+  if (mode == RUN_FULL && c->table_pending) {
+    // single-round fast path: the table was compacted optimistically into the buffers of the previous step
+    c->table_pending = false;
+    const uint64_t total = c->res_host[RES_DISTINCT];
+    if (c->res_host[RES_TABLE_OVF]) {   // it did not fit: grow and compact again (the temp records are still in place)
+      rc = APGK_E_ARG;
+      switch (c->W) {
+        case 1: rc = compact_table<1>(c, total); break;
+        case 2: rc = compact_table<2>(c, total); break;
+        case 3: rc = compact_table<3>(c, total); break;
+      }
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    c->n_distinct = total;
+  }
+  stages_collect(c);
   if (mode == RUN_FULL) c->finished = true;
   else c->part_ready = true;
   return APGK_OK;
@@ -451,57 +499,53 @@ int ensure_preserve(apgk_ctx* c, DevBuf& b, size_t bytes, size_t keep_bytes) {
   return APGK_OK;
 }
 
-template <int W, typename ElemB>
-int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode) {
-  const KeyGeom g = c->geom;
-  const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
-  int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : (use_local4(W) ? LM_KEY4 : Geo<W>::LM_KEY);
-  int l3_nt = L3_NT;
-  if (std::is_same<ElemB, uint32_t>::value) {  // tuning knobs
-    if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) local_max = atoi(e); }
-    if (const char* e = getenv("APGK_L3_NT")) { if (atoi(e) == 256 || atoi(e) == 512) l3_nt = atoi(e); }
+// dynamic shared memory opt-in and occupancy of a kernel: asked once per (kernel, shared bytes), not per step
+template <typename K>
+int kernel_setup(apgk_ctx* c, K kernel, int nt, size_t smem, int* occ_out) {
+  const auto key = std::make_pair((const void*)kernel, smem);
+  auto it = c->kattr.find(key);
+  if (it == c->kattr.end()) {
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nt, smem));
+    it = c->kattr.emplace(key, std::max(occ, 1)).first;
   }
-  const bool use_l3 = std::is_same<ElemB, uint32_t>::value && g.REM >= 1 && g.REM <= 31;
-  const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
-  c->elem_bytes = sizeof(ElemB);
-  c->local_max = (uint32_t)local_max;
-  c->nb1 = (uint32_t)bins0 * (uint32_t)bins1;
-  c->n_rounds = 0; c->n_big = 0; c->n_distinct = 0;
-  CU(c->spec_dense.ensure((size_t)SPEC_DENSE * 8));
-  CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
-  CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
-  CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
+  if (occ_out) *occ_out = it->second;
+  return APGK_OK;
+}
 
-  // ================= level 0: one histogram pass over everything (all rounds share it)
-  DigitSpec ds0{DIGIT_BITS, g.TB - g.D0, g.D0, g.pad, 0};
-  DigitFn<DIGIT_BITS> dg0 = make_digit_fn<DIGIT_BITS>(ds0);
-  HostPlan hp0;
+// chunk length (in tiles) of a pass whose segments hold about avg_tiles tiles each: a scatter CTA walks one
+// chunk; ~4+ chunks per segment keep the CTAs balanced (the fullest canonical prefixes hold ~2x the average)
+int chunk_tiles_for(uint64_t avg_tiles) {
+  int ct = (int)std::min<uint64_t>((2 * avg_tiles + 3) / 4, 128);
+  ct = std::max(8, ct);
+  if (const char* e = getenv("APGK_CT")) { if (atoi(e) > 0) ct = atoi(e); }  // tuning knob
+  return ct;
+}
+
+// ---- level 0, histogram: reads (or a key array) -> chunksum0, level-0 bucket totals tot0_dev.  The plan
+// depends on the input size alone and is kept from step to step.
+template <int W>
+int level0_hist(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, DigitFn<DIGIT_BITS>& dg0) {
+  const KeyGeom g = c->geom;
+  const int bins0 = 1 << g.D0;
   const uint32_t tile0 = dev_keys ? Geo<W>::TILE1 : (uint32_t)Geo<W>::NT0 * POS_PER_THREAD;
-  {
-    std::vector<uint64_t> one{dev_keys ? n_keys : c->total_bases};
+  const uint64_t n_elems = dev_keys ? n_keys : c->total_bases;
+  HostPlan& hp0 = c->hp0;
+  if (c->hp0_elems != n_elems || c->hp0_tile != tile0 || hp0.lp.bins != bins0 || !c->plan0.p) {
+    std::vector<uint64_t> one{n_elems};
     build_plan(hp0, one, tile0, bins0);
-  }
-  if (hp0.lp.n_tiles == 0) {  // nothing to count
-    c->n_instances = 0;
-    c->tot0_host.assign((size_t)bins0, 0);
-    c->have_table = want_table != 0;
-    if (mode == RUN_PARTITION) {
-      CU(c->segtot.ensure((size_t)c->nb1 * 8));
-      CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
-    }
-    return APGK_OK;
-  }
-  {  // the level-0 plan must outlive the level-1 uploads of every round: it gets its own device copy
     const size_t S1 = hp0.seg_tile0.size();
     CU(c->plan0.ensure(S1 * 16 + 64));
     unsigned char* d = c->plan0.as<unsigned char>();
+    // (pageable host memory: cudaMemcpyAsync returns once the bytes are staged, and hp0 lives in the context)
     CU(cudaMemcpyAsync(d, hp0.seg_start.data(), S1 * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d + S1 * 8, hp0.seg_tile0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d + S1 * 12, hp0.seg_chunk0.data(), S1 * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     hp0.lp.seg_start = (const uint64_t*)d;
     hp0.lp.seg_tile0 = (const uint32_t*)(d + S1 * 8);
     hp0.lp.seg_chunk0 = (const uint32_t*)(d + S1 * 12);
+    c->hp0_elems = n_elems; c->hp0_tile = tile0;
   }
   CU(c->chunksum0.ensure((size_t)hp0.lp.n_chunks * bins0 * 4));
   stage_begin(c, ST_HIST0);
@@ -538,24 +582,162 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
   LAUNCHED();
   stage_end(c, ST_HIST0);
   stage_begin(c, ST_SCAN0);
-  CU(c->segtot.ensure((size_t)bins0 * 8));
+  CU(c->tot0_dev.ensure((size_t)bins0 * 8));
   CU(c->bstart32.ensure((size_t)bins0 * 4));
-  k_segscan<COL_NT><<<1, COL_NT, 0, c->stream>>>(hp0.lp, c->chunksum0.as<uint32_t>(), c->segtot.as<unsigned long long>(),
+  k_segscan<COL_NT><<<1, COL_NT, 0, c->stream>>>(hp0.lp, c->chunksum0.as<uint32_t>(), c->tot0_dev.as<unsigned long long>(),
                                                  c->bstart32.as<uint32_t>(), nullptr, 0);
   LAUNCHED();
   stage_end(c, ST_SCAN0);
-  std::vector<uint64_t> tot0(bins0);
-  CU(cudaMemcpyAsync(tot0.data(), c->segtot.p, (size_t)bins0 * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  uint64_t N = 0;
-  for (int d = 0; d < bins0; d++) {
-    if (tot0[d] >= (1ull << 32)) FAIL(APGK_E_RANGE, "level-0 bucket %d holds %llu k-mers (>= 2^32)", d, (unsigned long long)tot0[d]);
-    N += tot0[d];
+  return APGK_OK;
+}
+
+// ---- level 0, scatter of the level-0 buckets [lo, hi) (all of them: no filtering) -> A, bucketed by D0 bits
+template <int W>
+int level0_scatter(apgk_ctx* c, const Key<W>* dev_keys, DigitFn<DIGIT_BITS> dg0, int lo, int hi, uint64_t n_round) {
+  const KeyGeom g = c->geom;
+  const int bins0 = 1 << g.D0;
+  const bool filter = lo > 0 || hi < bins0;
+  const HostPlan& hp0 = c->hp0;
+  const uint32_t tile0 = hp0.lp.tile_elems;
+  CU(c->A.ensure(std::max<size_t>(n_round, 1) * sizeof(Key<W>)));
+  CU(c->bstart64.ensure(((size_t)bins0 + 1) * 8));
+  stage_begin(c, ST_SCAN0);
+  // starts of the round's level-0 buckets in A; also the histogram's grand total and the 2^32 check -> result block
+  k_plan_range<<<1, PLAN_NT, 0, c->stream>>>(c->tot0_dev.as<unsigned long long>(), bins0, lo, hi, 1u, 1u,
+                                            c->bstart64.as<unsigned long long>(), nullptr, nullptr, c->res.as<unsigned long long>());
+  LAUNCHED();
+  stage_end(c, ST_SCAN0);
+  dg0.flo = (uint32_t)lo; dg0.fwidth = (uint32_t)(hi - lo);
+  stage_begin(c, ST_SCATTER0);
+  const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
+  if (dev_keys) {
+    auto launch = [&](auto kern) -> int {
+      { int rc = kernel_setup(c, kern, Geo<W>::NT1, sm, nullptr); if (rc) return rc; }
+      kern<<<hp0.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(dev_keys, hp0.lp, dg0, c->chunksum0.as<uint32_t>(),
+                                                            c->bstart64.as<uint64_t>(), 0, 0, c->A.as<Key<W>>());
+      return APGK_OK;
+    };
+    int rc = filter ? launch(k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS, true>)
+                    : launch(k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS, false>);
+    if (rc) return rc;
+  } else {
+    auto launch = [&](auto kern) -> int {
+      { int rc = kernel_setup(c, kern, Geo<W>::NTS, sm, nullptr); if (rc) return rc; }
+      kern<<<hp0.lp.n_chunks, Geo<W>::NTS, sm, c->stream>>>(read_store(c), dg0, hp0.lp, c->chunksum0.as<uint32_t>(),
+                                                            c->bstart64.as<uint64_t>(), c->A.as<Key<W>>());
+      return APGK_OK;
+    };
+    int rc = filter ? launch(k_scatter_reads<W, Geo<W>::NTS, DIGIT_BITS, true, Geo<W>::NPOS>)
+                    : launch(k_scatter_reads<W, Geo<W>::NTS, DIGIT_BITS, false, Geo<W>::NPOS>);
+    if (rc) return rc;
   }
+  LAUNCHED();
+  stage_end(c, ST_SCATTER0);
+  return APGK_OK;
+}
+
+// ---- level 1 over the level-0 buckets (segments) [s_lo, s_hi), whose n_range keys start at a_src:
+// -> B (n_range elements bucketed by D0+D1 bits, relative to the range), bucket sizes segtot, offsets bofs.
+// The plan (tiles / chunks of every segment) is made on the device from tot0_dev; the host only bounds the grid.
+// d2 > 0 also leaves the sizes of the 2^d2 sub-buckets of every bucket in sub_sizes (sharded exchange).
+template <int W, typename ElemB>
+int level1(apgk_ctx* c, int s_lo, int s_hi, uint64_t n_range, const Key<W>* a_src, int d2) {
+  const KeyGeom g = c->geom;
+  const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
+  const uint32_t tile = Geo<W>::TILE1;
+  const int n_seg_in = std::max(1, s_hi - s_lo);
+  const int ct = chunk_tiles_for(n_range / tile / (uint64_t)n_seg_in);
+  const uint64_t tiles_bound = n_range / tile + (uint64_t)n_seg_in;
+  const uint32_t chunks_bound = (uint32_t)(tiles_bound / (uint64_t)ct + (uint64_t)n_seg_in + 1);
+  const size_t S1 = (size_t)bins0 + 1;
+  CU(c->plan.ensure(S1 * 16 + 64));
+  unsigned char* d = c->plan.as<unsigned char>();
+  LevelPlan lp{};
+  lp.bins = bins1; lp.n_segments = bins0; lp.chunk_tiles = ct; lp.tile_elems = tile;
+  lp.n_tiles = (uint32_t)tiles_bound; lp.n_chunks = chunks_bound;
+  lp.seg_start = (const uint64_t*)d;
+  lp.seg_tile0 = (const uint32_t*)(d + S1 * 8);
+  lp.seg_chunk0 = (const uint32_t*)(d + S1 * 12);
+  DigitSpec ds1{DIGIT_BITS, g.TB - g.D0 - g.D1, g.D1, g.pad, 0};
+  const DigitFn<DIGIT_BITS> dg1 = make_digit_fn<DIGIT_BITS>(ds1);
+  DigitSpec dsw{DIGIT_BITS, g.TB - g.D0 - g.D1 - d2, g.D1 + d2, g.pad, 0};
+  const DigitFn<DIGIT_BITS> dgw = make_digit_fn<DIGIT_BITS>(dsw);
+  stage_begin(c, ST_SCAN1);
+  k_plan_range<<<1, PLAN_NT, 0, c->stream>>>(c->tot0_dev.as<unsigned long long>(), bins0, s_lo, s_hi, tile, (uint32_t)ct,
+                                            (unsigned long long*)d, (uint32_t*)(d + S1 * 8), (uint32_t*)(d + S1 * 12), nullptr);
+  LAUNCHED();
+  stage_end(c, ST_SCAN1);
+  CU(c->chunksum.ensure((size_t)chunks_bound * bins1 * 4));
+  CU(c->segtot.ensure((size_t)c->nb1 * 8));
+  CU(c->bstart32.ensure((size_t)c->nb1 * 4));
+  CU(c->bofs.ensure(((size_t)c->nb1 + 1) * 8));
+  if (d2 > 0) {
+    CU(c->sub_sizes.ensure(((size_t)c->nb1 << d2) * 4 + 16));
+    CU(cudaMemsetAsync(c->sub_sizes.p, 0, ((size_t)c->nb1 << d2) * 4, c->stream));
+  }
+  stage_begin(c, ST_HIST1);
+  {
+    auto kern = k_hist_keys<Key<W>, Geo<W>::NT1, DIGIT_BITS>;
+    const size_t smh = ((size_t)bins1 << d2) * 4;
+    { int rc = kernel_setup(c, kern, Geo<W>::NT1, smh, nullptr); if (rc) return rc; }
+    kern<<<chunks_bound, Geo<W>::NT1, smh, c->stream>>>(a_src, lp, dg1, c->chunksum.as<uint32_t>(), dgw, d2,
+                                                        d2 > 0 ? c->sub_sizes.as<uint32_t>() : nullptr);
+    LAUNCHED();
+  }
+  stage_end(c, ST_HIST1);
+  stage_begin(c, ST_SCAN1);
+  k_segscan<COL_NT><<<bins0, COL_NT, 0, c->stream>>>(lp, c->chunksum.as<uint32_t>(), c->segtot.as<unsigned long long>(),
+                                                     c->bstart32.as<uint32_t>(), c->bofs.as<unsigned long long>(), 1);
+  LAUNCHED();
+  stage_end(c, ST_SCAN1);
+  CU(c->B.ensure(std::max<size_t>(n_range, 1) * sizeof(ElemB) + 16));
+  stage_begin(c, ST_SCATTER1);
+  {
+    auto kern = ScatterSel<ElemB, W>::kernel();
+    const size_t sm = scatter_smem_bytes<Key<W>>(tile, bins1);
+    { int rc = kernel_setup(c, kern, Geo<W>::NT1, sm, nullptr); if (rc) return rc; }
+    kern<<<chunks_bound, Geo<W>::NT1, sm, c->stream>>>(a_src, lp, dg1, c->chunksum.as<uint32_t>(), nullptr, g.pad, g.REM,
+                                                       c->B.as<ElemB>());
+    LAUNCHED();
+  }
+  stage_end(c, ST_SCATTER1);
+  return APGK_OK;
+}
+
+// device memory the temp buffers of a run may take: what is free now plus what the context already holds for them
+int temp_budget(apgk_ctx* c, size_t* budget) {
+  size_t fr = 0, tot = 0;
+  CU(cudaMemGetInfo(&fr, &tot));
+  const size_t held = c->A.cap + c->B.cap + c->T.cap;  // reusable
+  *budget = (size_t)((double)(fr + held) * 0.60);       // temp buffers ~60 % of it; the result table gets the rest
+  return APGK_OK;
+}
+
+template <int W, typename ElemB>
+int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mode) {
+  const KeyGeom g = c->geom;
+  const int bins0 = 1 << g.D0, bins1 = 1 << g.D1;
+  int local_max = std::is_same<ElemB, uint32_t>::value ? LM_U32 : (use_local4(W) ? LM_KEY4 : Geo<W>::LM_KEY);
+  if (std::is_same<ElemB, uint32_t>::value) {  // tuning knob
+    if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) local_max = atoi(e); }
+  }
+  const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
+  c->elem_bytes = sizeof(ElemB);
+  c->local_max = (uint32_t)local_max;
+  c->nb1 = (uint32_t)bins0 * (uint32_t)bins1;
+  c->n_rounds = 0; c->n_big = 0; c->n_distinct = 0;
+  c->table_pending = false;
+  CU(c->spec_dense.ensure((size_t)SPEC_DENSE * 8));
+  CU(cudaMemsetAsync(c->spec_dense.p, 0, (size_t)SPEC_DENSE * 8, c->stream));
+  CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
+  CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
+  const uint64_t N = dev_keys ? n_keys : c->n_windows;   // exact, known before any kernel runs
   c->n_instances = N;
-  c->tot0_host = tot0;
-  if (N == 0) {
+  c->tot0_host.assign((size_t)bins0, 0);
+  if (N == 0) {  // nothing to count
+    { int rc = wait_ingest(c); if (rc) return rc; }
     c->have_table = want_table != 0;
+    c->part_n = 0;
     if (mode == RUN_PARTITION) {
       CU(c->segtot.ensure((size_t)c->nb1 * 8));
       CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
@@ -563,57 +745,98 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
     return APGK_OK;
   }
 
-  // ================= rounds over k-mer space (SortKmers "passes" / KmerParcels "parcels"): consecutive
-  // level-0 buckets whose keys, with their level-1 copy and temp counts, fit the device memory budget
-  const size_t bytes_per_key = sizeof(Key<W>) + sizeof(ElemB) + (want_table ? 4 : 0);
-  uint64_t cap_keys = c->cfg.max_round_keys;
-  if (const char* e = getenv("APGK_ROUND_KEYS")) { if (atoll(e) > 0) cap_keys = (uint64_t)atoll(e); }
-  if (!cap_keys) {
-    size_t fr = 0, tot = 0;
-    CU(cudaMemGetInfo(&fr, &tot));
-    const size_t held = c->A.cap + c->B.cap + c->T.cap;  // reusable
-    // temp buffers may take ~60 % of what is available; the result table gets the rest
-    cap_keys = (uint64_t)((double)(fr + held) * 0.60 / (double)bytes_per_key);
+  // ================= level 0: one histogram pass over everything (all rounds share it)
+  DigitSpec ds0{DIGIT_BITS, g.TB - g.D0, g.D0, g.pad, 0};
+  DigitFn<DIGIT_BITS> dg0 = make_digit_fn<DIGIT_BITS>(ds0);
+  { int rc = level0_hist<W>(c, dev_keys, n_keys, dg0); if (rc) return rc; }
+
+  // ================= rounds over k-mer space (SortKmers "passes" / KmerParcels "parcels").  Two levels:
+  //   outer rounds  consecutive level-0 buckets whose full keys (A) fit: one (filtered) level-0 scatter each
+  //   inner rounds  sub-ranges of an outer round whose level-1 copy + temp counts (B, T) fit: level 1 + counting
+  // so a memory-tight run re-extracts the reads once per OUTER round only.  The common case -- everything
+  // fits at once -- needs nothing from the device to be planned: no host round trip.
+  const size_t eA = sizeof(Key<W>), eB = sizeof(ElemB) + (want_table ? 4 : 0);
+  uint64_t cap_outer = c->cfg.max_round_keys, cap_inner = c->cfg.max_inner_keys;
+  if (const char* e = getenv("APGK_ROUND_KEYS")) { if (atoll(e) > 0) cap_outer = (uint64_t)atoll(e); }
+  if (const char* e = getenv("APGK_INNER_KEYS")) { if (atoll(e) > 0) cap_inner = (uint64_t)atoll(e); }
+  bool single;
+  if (cap_outer) {
+    if (!cap_inner) cap_inner = cap_outer;
+    single = N <= cap_outer && N <= cap_inner;
+    c->last_cap_keys = std::min(cap_outer, cap_inner);
+  } else {
+    single = N * (eA + eB) <= c->A.cap + c->B.cap + c->T.cap && N * eA <= c->A.cap && N * sizeof(ElemB) <= c->B.cap;
+    if (!single || mode == RUN_PARTITION) {
+      size_t budget = 0;
+      { int rc = temp_budget(c, &budget); if (rc) return rc; }
+      c->last_cap_keys = (uint64_t)(budget / (eA + eB));
+      single = N <= c->last_cap_keys;
+      if (!single) {
+        // A holds an outer round, B + T a quarter of it (unless the caller fixed the inner size)
+        const uint64_t ci = cap_inner;
+        cap_outer = ci ? (budget > ci * eB ? (budget - ci * eB) / eA : 1) : (uint64_t)((double)budget / ((double)eA + (double)eB / 4.0));
+        cap_inner = ci ? ci : std::max<uint64_t>(1, cap_outer / 4);
+        cap_outer = std::max<uint64_t>(cap_outer, 1);
+      }
+    }
   }
-  c->last_cap_keys = cap_keys;
-  std::vector<std::pair<int, int>> rounds;  // [lo, hi) level-0 buckets
   const bool forced_range = mode == RUN_PARTITION && c->force_d0_lo >= 0;
+  struct Round { int lo, hi; uint64_t n; std::vector<std::array<uint64_t, 3>> inner; };  // inner: {s_lo, s_hi, n}
+  std::vector<Round> rounds;
+  std::vector<uint64_t>& tot0 = c->tot0_host;
+  if (!single || mode == RUN_PARTITION) {
+    // the plan needs the level-0 totals on the host: the one mid-step round trip of the memory-tight path
+    CU(cudaMemcpyAsync(tot0.data(), c->tot0_dev.p, (size_t)bins0 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint64_t sum = 0;
+    for (int d = 0; d < bins0; d++) {
+      if (tot0[d] >= (1ull << 32)) FAIL(APGK_E_RANGE, "level-0 bucket %d holds %llu k-mers (>= 2^32)", d, (unsigned long long)tot0[d]);
+      sum += tot0[d];
+    }
+    if (sum != N) FAIL(APGK_E_STATE, "internal: level-0 histogram counts %llu k-mers, expected %llu", (unsigned long long)sum, (unsigned long long)N);
+  }
   if (forced_range) {   // the caller runs the rounds (sharded counting: all ranks use the same ranges)
-    rounds.push_back({std::min(c->force_d0_lo, bins0), std::min(std::max(c->force_d0_hi, c->force_d0_lo), bins0)});
+    Round r;
+    r.lo = std::min(c->force_d0_lo, bins0); r.hi = std::min(std::max(c->force_d0_hi, c->force_d0_lo), bins0);
+    r.n = 0;
+    for (int d = r.lo; d < r.hi; d++) r.n += tot0[d];
+    r.inner.push_back({(uint64_t)r.lo, (uint64_t)r.hi, r.n});
+    rounds.push_back(r);
+  } else if (single) {
+    Round r{0, bins0, N, {}};
+    r.inner.push_back({0, (uint64_t)bins0, N});
+    rounds.push_back(r);
   } else {
     int lo = 0; uint64_t acc = 0;
+    auto close_outer = [&](int hi) {
+      Round r{lo, hi, acc, {}};
+      int ilo = lo; uint64_t iacc = 0;
+      for (int d = lo; d < hi; d++) {
+        if (iacc && iacc + tot0[d] > cap_inner) { r.inner.push_back({(uint64_t)ilo, (uint64_t)d, iacc}); ilo = d; iacc = 0; }
+        iacc += tot0[d];
+      }
+      r.inner.push_back({(uint64_t)ilo, (uint64_t)hi, iacc});
+      rounds.push_back(r);
+    };
     for (int d = 0; d < bins0; d++) {
-      if (acc && acc + tot0[d] > cap_keys) { rounds.push_back({lo, d}); lo = d; acc = 0; }
+      if (acc && acc + tot0[d] > cap_outer) { close_outer(d); lo = d; acc = 0; }
       acc += tot0[d];
     }
-    rounds.push_back({lo, bins0});
+    close_outer(bins0);
   }
-  c->n_rounds = (uint32_t)rounds.size();
-  if (mode == RUN_PARTITION && rounds.size() > 1 && !forced_range)
-    FAIL(APGK_E_RANGE, "apgk_partition: %zu k-mer-space rounds would be needed; the sharded exchange takes one", rounds.size());
+  for (const Round& r : rounds) c->n_rounds += (uint32_t)r.inner.size();
+  if (mode == RUN_PARTITION && !forced_range && !single)
+    FAIL(APGK_E_RANGE, "apgk_partition: %u k-mer-space rounds would be needed; the sharded exchange takes one", c->n_rounds);
 
   CU(c->spec_ovf.ensure(((size_t)N / SPEC_DENSE + 16) * 8));
   CU(cudaMemsetAsync(c->spec_ovf.p, 0, 8, c->stream));
-  CU(c->bofs.ensure(((size_t)c->nb1 + 1) * 8));
   CU(c->nd.ensure(((size_t)c->nb1 + 1) * 4));
   CU(c->out_off_local.ensure(((size_t)c->nb1 + 1) * 8));
   CU(c->stats.ensure(64));
-  CU(c->bstart64.ensure(((size_t)bins0 + 1) * 8));
-  DigitSpec ds1{DIGIT_BITS, g.TB - g.D0 - g.D1, g.D1, g.pad, 0};
-  const DigitFn<DIGIT_BITS> dg1 = make_digit_fn<DIGIT_BITS>(ds1);
   uint64_t n_prev = 0;  // records already in the result table
 
-  for (size_t r = 0; r < rounds.size(); r++) {
-    const int lo = rounds[r].first, hi = rounds[r].second;
-    const bool filter = rounds.size() > 1 || (forced_range && (lo > 0 || hi < bins0));
-    std::vector<uint64_t> tot_r(bins0, 0), bstart_r(bins0 + 1, 0);
-    uint64_t Nr = 0;
-    for (int d = 0; d < bins0; d++) {
-      bstart_r[d] = Nr;
-      if (d >= lo && d < hi) { tot_r[d] = tot0[d]; Nr += tot0[d]; }
-    }
-    bstart_r[bins0] = Nr;
-    if (Nr == 0) {
+  for (const Round& r : rounds) {
+    if (r.n == 0) {
       if (mode == RUN_PARTITION) {   // nothing in this range: an empty partition
         CU(c->segtot.ensure((size_t)c->nb1 * 8));
         CU(cudaMemsetAsync(c->segtot.p, 0, (size_t)c->nb1 * 8, c->stream));
@@ -622,80 +845,45 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
       }
       continue;
     }
-    CU(cudaMemcpyAsync(c->bstart64.p, bstart_r.data(), ((size_t)bins0 + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(c->A.ensure(std::max<size_t>(Nr, 1) * sizeof(Key<W>)));
-    dg0.flo = (uint32_t)lo; dg0.fwidth = (uint32_t)(hi - lo);
-
-    // ---- level-0 scatter of this round's buckets
-    stage_begin(c, ST_SCATTER0);
-    {
-      const size_t sm = scatter_smem_bytes<Key<W>>(tile0, bins0);
-      if (dev_keys) {
-        auto launch = [&](auto kern) -> int {
-          { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-          kern<<<hp0.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(dev_keys, hp0.lp, dg0, c->chunksum0.as<uint32_t>(),
-                                                                c->bstart64.as<uint64_t>(), 0, 0, c->A.as<Key<W>>());
-          return APGK_OK;
-        };
-        int rc = filter ? launch(k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS, true>)
-                        : launch(k_scatter_keys<Key<W>, Key<W>, Geo<W>::NT1, DIGIT_BITS, false>);
-        if (rc) return rc;
-      } else {
-        auto launch = [&](auto kern) -> int {
-          { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-          kern<<<hp0.lp.n_chunks, Geo<W>::NTS, sm, c->stream>>>(read_store(c), dg0, hp0.lp, c->chunksum0.as<uint32_t>(),
-                                                                c->bstart64.as<uint64_t>(), c->A.as<Key<W>>());
-          return APGK_OK;
-        };
-        int rc = filter ? launch(k_scatter_reads<W, Geo<W>::NTS, DIGIT_BITS, true, Geo<W>::NPOS>)
-                        : launch(k_scatter_reads<W, Geo<W>::NTS, DIGIT_BITS, false, Geo<W>::NPOS>);
-        if (rc) return rc;
-      }
-      LAUNCHED();
+    { int rc = level0_scatter<W>(c, dev_keys, dg0, r.lo, r.hi, r.n); if (rc) return rc; }
+    uint64_t off_a = 0;   // keys of the outer round before the current inner range
+    for (const auto& in : r.inner) {
+      const uint64_t n_in = in[2];
+      if (n_in == 0) continue;
+      Key<W>* a_src = c->A.as<Key<W>>() + off_a;
+      { int rc = level1<W, ElemB>(c, (int)in[0], (int)in[1], n_in, a_src, 0); if (rc) return rc; }
+      if (mode == RUN_PARTITION) { c->part_n = n_in; return APGK_OK; }
+      c->count_src = c->B.p; c->bucket_lo = c->bucket_hi = 0;
+      // the temp records of the range's buckets go over the range's own level-0 keys: dead once level 1 has run
+      { int rc = count_buckets<W, ElemB>(c, n_in, N, n_prev, a_src, single); if (rc) return rc; }
+      off_a += n_in;
     }
-    stage_end(c, ST_SCATTER0);
-
-    // ---- level 1
-    HostPlan hp1;
-    build_plan(hp1, tot_r, Geo<W>::TILE1, bins1);
-    { int rc = upload_plan(c, hp1); if (rc) return rc; }
-    CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
-    CU(c->chunksum.ensure((size_t)std::max<uint32_t>(hp1.lp.n_chunks, 1) * bins1 * 4));
-    stage_begin(c, ST_HIST1);
-    k_hist_keys<Key<W>, Geo<W>::NT1, DIGIT_BITS><<<hp1.lp.n_chunks, Geo<W>::NT1, bins1 * 4, c->stream>>>(
-        c->A.as<Key<W>>(), hp1.lp, dg1, c->chunksum.as<uint32_t>());
-    LAUNCHED();
-    stage_end(c, ST_HIST1);
-    stage_begin(c, ST_SCAN1);
-    { int rc = column_scan(c, hp1, 1, c->bofs.as<unsigned long long>()); if (rc) return rc; }
-    stage_end(c, ST_SCAN1);
-    CU(c->B.ensure(std::max<size_t>(Nr, 1) * sizeof(ElemB) + 16));
-    stage_begin(c, ST_SCATTER1);
-    {
-      auto kern = ScatterSel<ElemB, W>::kernel();
-      const size_t sm = scatter_smem_bytes<Key<W>>(Geo<W>::TILE1, bins1);
-      { int rc = set_smem(c, kern, sm); if (rc) return rc; }
-      kern<<<hp1.lp.n_chunks, Geo<W>::NT1, sm, c->stream>>>(c->A.as<Key<W>>(), hp1.lp, dg1, c->chunksum.as<uint32_t>(),
-                                                            nullptr, g.pad, g.REM, c->B.as<ElemB>());
-      LAUNCHED();
-    }
-    stage_end(c, ST_SCATTER1);
-
-    if (mode == RUN_PARTITION) { c->part_n = Nr; return APGK_OK; }
-    c->count_src = c->B.p; c->bucket_lo = c->bucket_hi = 0;
-    { int rc = count_buckets<W, ElemB>(c, Nr, N, n_prev); if (rc) return rc; }
   }
-  c->n_distinct = n_prev;
+  if (!single) c->n_distinct = n_prev;
   c->have_table = want_table != 0;
   return APGK_OK;
 }
 
+// final table of a single-round step whose record count is on the host: (re)size the result buffers, compact
+template <int W>
+int compact_table(apgk_ctx* c, uint64_t total) {
+  CU(c->out_keys.ensure(std::max<size_t>(total + (total >> 5), 1) * sizeof(Key<W>)));
+  CU(c->out_cnt.ensure(std::max<size_t>(total + (total >> 5), 1) * 4));
+  k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(c->tmp_keys_last ? (const Key<W>*)c->tmp_keys_last : c->A.as<Key<W>>(), c->T.as<uint32_t>(),
+                                                   c->bofs.as<unsigned long long>(), c->out_off_local.as<unsigned long long>(), c->nb1,
+                                                   c->out_keys.as<Key<W>>(), c->out_cnt.as<uint32_t>(), nullptr, 0ull, nullptr);
+  LAUNCHED();
+  return APGK_OK;
+}
+
 // ---------------------------------------------------------------- per-bucket sort + count, table append
-// Input: c->B holds Nr elements grouped by the nb1 buckets (offsets c->bofs, sizes c->segtot).  Appends the
-// distinct k-mers of these buckets to the result table at n_prev (buckets ascend in k-mer order).
+// Input: c->count_src holds Nr elements grouped by the nb1 buckets (offsets c->bofs, sizes c->segtot).  Appends the
+// distinct k-mers of these buckets to the result table at n_prev (buckets ascend in k-mer order).  tmp_keys:
+// Nr keys of scratch for the per-bucket records.  nosync (single-round steps, n_prev == 0): nothing is read
+// back here -- the table is compacted into the result buffers as they are and the caller checks the result
+// block (RES_DISTINCT, RES_TABLE_OVF) at the step's final synchronisation.
 template <int W, typename ElemB>
-int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
+int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev, Key<W>* tmp_keys, bool nosync) {
   const KeyGeom g = c->geom;
   const int local_max = (int)c->local_max;
   int l3_nt = L3_NT;
@@ -705,24 +893,26 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
   const bool use_l3 = std::is_same<ElemB, uint32_t>::value && g.REM >= 1 && g.REM <= 31;
   const bool use_l4 = !std::is_same<ElemB, uint32_t>::value && use_local4(W) && g.pad == 0 && g.REM >= 1;
   const int want_table = (c->cfg.flags & APGK_WANT_COUNTS) ? 1 : 0;
-  // bucket classification (oversize list)
+  // bucket classification (oversize list): the range-splitting kernels take every bucket size
   const uint32_t big_cap = (uint32_t)(Nr / local_max + 16);
-  CU(c->big_list.ensure((size_t)big_cap * 4));
-  CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
-  k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1,
-                                                         (use_l3 || use_l4) ? 0xFFFFFFFFu : (uint32_t)local_max,
-                                                         c->big_list.as<uint32_t>(), big_cap,
-                                                         c->stats.as<unsigned long long>());
-  LAUNCHED();
+  uint64_t n_big = 0;
   unsigned long long stats[2] = {0, 0};
-  CU(cudaMemcpyAsync(stats, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  const uint64_t n_big = stats[0];
-  c->n_big += n_big;
+  if (!(use_l3 || use_l4)) {
+    CU(c->big_list.ensure((size_t)big_cap * 4));
+    CU(cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
+    k_classify<<<(c->nb1 + 255) / 256, 256, 0, c->stream>>>(c->segtot.as<unsigned long long>(), c->nb1, (uint32_t)local_max,
+                                                           c->big_list.as<uint32_t>(), big_cap, c->stats.as<unsigned long long>());
+    LAUNCHED();
+    CU(cudaMemcpyAsync(stats, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    n_big = stats[0];
+    c->n_big += n_big;
+  }
   {
     EmitCtx<W> ec;
     ec.want_table = want_table; ec.rem_bits = g.REM; ec.pad = g.pad;
-    ec.tmp_keys = c->A.as<Key<W>>();
+    ec.tmp_keys = tmp_keys;
+    c->tmp_keys_last = tmp_keys;
     if (want_table) CU(c->T.ensure(std::max<size_t>(Nr, 1) * 4));
     ec.tmp_cnt = c->T.as<uint32_t>();
     ec.spec_dense = c->spec_dense.as<unsigned long long>();
@@ -741,9 +931,8 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       if constexpr (std::is_same<ElemB, uint32_t>::value) {
         auto launch3 = [&](auto kern3, int nt) -> int {
           const size_t sm3 = Local3Smem::bytes(local_max);
-          { int rc = set_smem(c, kern3, sm3); if (rc) return rc; }
           int occ3 = 1;
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kern3, nt, sm3));
+          { int rc = kernel_setup(c, kern3, nt, sm3, &occ3); if (rc) return rc; }
           const uint32_t grid3 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ3, 1)));
           kern3<<<grid3, nt, sm3, c->stream>>>((const uint32_t*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>());
           return APGK_OK;
@@ -757,9 +946,8 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       if constexpr (!std::is_same<ElemB, uint32_t>::value) {
         auto kern4 = k_local4<512, W>;
         const size_t sm4 = Local4Smem::bytes(local_max, W);
-        { int rc = set_smem(c, kern4, sm4); if (rc) return rc; }
         int occ4 = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, kern4, 512, sm4));
+        { int rc = kernel_setup(c, kern4, 512, sm4, &occ4); if (rc) return rc; }
         const uint32_t grid4 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ4, 1)));
         kern4<<<grid4, 512, sm4, c->stream>>>((const Key<W>*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>());
         LAUNCHED();
@@ -768,9 +956,8 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       // general element types: warp-table kernel; buckets it cannot take land on the deferred list ...
       auto kern2 = k_local2<ElemB, W>;
       const size_t sm2 = Local2Smem<ElemB>::bytes(local_max);
-      { int rc = set_smem(c, kern2, sm2); if (rc) return rc; }
       int occ2 = 1;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, L2_NT, sm2));
+      { int rc = kernel_setup(c, kern2, L2_NT, sm2, &occ2); if (rc) return rc; }
       const uint32_t grid2 = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ2, 1)));
       kern2<<<grid2, L2_NT, sm2, c->stream>>>((const ElemB*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>(),
                                               c->deferred.as<uint32_t>(), c->nb1);
@@ -778,9 +965,8 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       // ... which the barrier-heavy general kernel then walks (normally empty)
       auto kern = k_local<ElemB, W>;
       const size_t sm = LocalSmem<ElemB>::bytes(local_max);
-      { int rc = set_smem(c, kern, sm); if (rc) return rc; }
       int occ = 1;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
+      { int rc = kernel_setup(c, kern, LOCAL_NT, sm, &occ); if (rc) return rc; }
       const uint32_t grid = std::min<uint32_t>(c->nb1, (uint32_t)(c->n_sm * std::max(occ, 1)));
       kern<<<grid, LOCAL_NT, sm, c->stream>>>((const ElemB*)c->count_src, bt, g.REM, ec, c->nd.as<uint32_t>(),
                                               c->deferred.as<uint32_t>(), c->nb1);
@@ -791,9 +977,8 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       if (n_big > big_cap) FAIL(APGK_E_RANGE, "internal: oversize bucket list overflow");
       auto kern = k_big<ElemB, W>;
       const size_t sm = LocalSmem<ElemB>::bytes(local_max);
-      { int rc = set_smem(c, kern, sm); if (rc) return rc; }
       int occ = 1;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LOCAL_NT, sm));
+      { int rc = kernel_setup(c, kern, LOCAL_NT, sm, &occ); if (rc) return rc; }
       const uint32_t grid = (uint32_t)std::min<uint64_t>(n_big, (uint64_t)c->n_sm * std::max(occ, 1));
       CU(c->scratch.ensure((size_t)stats[1] * sizeof(ElemB) + 16));
       CU(c->stacks.ensure((size_t)grid * BIG_STACK * 16));
@@ -818,30 +1003,45 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev) {
       const uint64_t n = c->nb1;
       const uint32_t nblocks = (uint32_t)((n + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
       CU(c->blocksum.ensure(((size_t)nblocks + 1) * 8));
+      unsigned long long* res = c->res.as<unsigned long long>();
       k_scan_blocksum<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>());
       LAUNCHED();
-      k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks);
+      k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks, res ? res + RES_DISTINCT : nullptr);
       LAUNCHED();
       k_scan_apply<<<nblocks, SCAN_NT, 0, c->stream>>>(c->nd.as<uint32_t>(), n, c->blocksum.as<unsigned long long>(),
                                                        c->out_off_local.as<unsigned long long>());
       LAUNCHED();
-      unsigned long long total = 0;
-      CU(cudaMemcpyAsync(&total, c->blocksum.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
       // global prefix index = sum over rounds of the local prefixes (buckets outside a round add 0 / its total)
       k_accumulate_u64<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(c->out_off.as<unsigned long long>(),
                                                                               c->out_off_local.as<unsigned long long>(), n + 1);
       LAUNCHED();
-      if (want_table) {
-        { int rc = ensure_preserve(c, c->out_keys, std::max<size_t>(n_prev + total, 1) * sizeof(Key<W>), n_prev * sizeof(Key<W>)); if (rc) return rc; }
-        { int rc = ensure_preserve(c, c->out_cnt, std::max<size_t>(n_prev + total, 1) * 4, n_prev * 4); if (rc) return rc; }
-        k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(c->A.as<Key<W>>(), c->T.as<uint32_t>(),
-                                                         c->bofs.as<unsigned long long>(),
-                                                         c->out_off_local.as<unsigned long long>(), c->nb1,
-                                                         c->out_keys.as<Key<W>>() + n_prev, c->out_cnt.as<uint32_t>() + n_prev);
-        LAUNCHED();
+      const bool optimistic = nosync && n_prev == 0 && (!want_table || (c->out_keys.cap && c->out_cnt.cap));
+      if (optimistic) {
+        if (want_table) {
+          const unsigned long long cap = std::min<unsigned long long>(c->out_keys.cap / sizeof(Key<W>), c->out_cnt.cap / 4);
+          k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(tmp_keys, c->T.as<uint32_t>(), c->bofs.as<unsigned long long>(),
+                                                           c->out_off_local.as<unsigned long long>(), c->nb1, c->out_keys.as<Key<W>>(),
+                                                           c->out_cnt.as<uint32_t>(), res + RES_DISTINCT, cap, res + RES_TABLE_OVF);
+          LAUNCHED();
+        }
+        c->table_pending = true;   // finish_impl reads RES_DISTINCT / RES_TABLE_OVF at the step's synchronisation
+      } else {
+        unsigned long long total = 0;
+        CU(cudaMemcpyAsync(&total, c->blocksum.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (want_table) {
+          const size_t want = n_prev + total + (nosync ? (total >> 5) : 0);   // a little slack: the next step reuses the buffers
+          { int rc = ensure_preserve(c, c->out_keys, std::max<size_t>(want, 1) * sizeof(Key<W>), n_prev * sizeof(Key<W>)); if (rc) return rc; }
+          { int rc = ensure_preserve(c, c->out_cnt, std::max<size_t>(want, 1) * 4, n_prev * 4); if (rc) return rc; }
+          k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(tmp_keys, c->T.as<uint32_t>(), c->bofs.as<unsigned long long>(),
+                                                           c->out_off_local.as<unsigned long long>(), c->nb1,
+                                                           c->out_keys.as<Key<W>>() + n_prev, c->out_cnt.as<uint32_t>() + n_prev,
+                                                           nullptr, 0ull, nullptr);
+          LAUNCHED();
+        }
+        n_prev += total;
+        if (nosync) c->n_distinct = n_prev;
       }
-      n_prev += total;
     }
     stage_end(c, ST_TABLE);
     }
@@ -937,7 +1137,7 @@ int scan_u32(apgk_ctx* c, const uint32_t* in, uint64_t n, unsigned long long* ou
   CU(c->blocksum.ensure(((size_t)nblocks + 1) * 8));
   k_scan_blocksum<<<nblocks, SCAN_NT, 0, c->stream>>>(in, n, c->blocksum.as<unsigned long long>());
   LAUNCHED();
-  k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks);
+  k_scan_top<<<1, SCAN_NT, 0, c->stream>>>(c->blocksum.as<unsigned long long>(), nblocks, nullptr);
   LAUNCHED();
   k_scan_apply<<<nblocks, SCAN_NT, 0, c->stream>>>(in, n, c->blocksum.as<unsigned long long>(), out);
   LAUNCHED();
@@ -1191,7 +1391,7 @@ int count_pieces_typed(apgk_ctx* c, const void* const* bases_host, bool peer, ui
   // split bits: every merged bucket is cut into 2^d2 sub-buckets by the leading remainder bits
   d2 = effective_split_bits(c, d2);
   const uint32_t nbf = nb << d2;
-  for (int s = 0; s < APGK_N_STAGES; s++) { c->ev_used[s] = false; c->stage_ms[s] = 0; }
+  stages_reset(c);
   stage_begin(c, ST_TOTAL);
   stage_begin(c, ST_OWNER);
   CU(c->segtot.ensure((size_t)nbf * 8));
@@ -1255,14 +1455,15 @@ int count_pieces_typed(apgk_ctx* c, const void* const* bases_host, bool peer, ui
   CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)nbf + 1) * 8, c->stream));
   c->count_src = dst.p;
   c->bucket_lo = lo << d2; c->bucket_hi = hi << d2;
-  if (Nr) { int rc = count_buckets<W, ElemB>(c, Nr, Nr, n_prev); if (rc) return rc; }
+  CU(c->res.ensure(RES_WORDS * 8));
+  if (Nr) { int rc = count_buckets<W, ElemB>(c, Nr, Nr, n_prev, c->A.as<Key<W>>(), false); if (rc) return rc; }
   c->n_distinct = n_prev;
   c->have_table = (c->cfg.flags & APGK_WANT_COUNTS) != 0;
   stage_end(c, ST_TOTAL);
   c->n_deferred = 0;
   if (c->deferred.p && Nr) CU(cudaMemcpyAsync(&c->n_deferred, c->deferred.p, 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  for (int s = 0; s < APGK_N_STAGES; s++) stage_flush(c, s);
+  stages_collect(c);
   c->part_ready = false;
   c->spec_loaded = false;
   c->finished = true;
@@ -1406,7 +1607,7 @@ int apgk_create(const apgk_config* cfg, apgk_ctx** out) {
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete c; return APGK_E_CUDA; }
   c->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return APGK_E_CUDA; }
-  for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventCreate(&c->ev[s][0]); cudaEventCreate(&c->ev[s][1]); }
+  stages_reset(c);
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { apgk_destroy(c); return APGK_E_CUDA; }
   cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
   if (cfg->reserve_bases && ensure_store(c, cfg->reserve_bases) != APGK_OK) {
@@ -1421,7 +1622,7 @@ void apgk_destroy(apgk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* all[] = {&c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum, &c->chunksum0, &c->plan0, &c->out_off_local,
+  DevBuf* all[] = {&c->tot0_dev, &c->res, &c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum, &c->chunksum0, &c->plan0, &c->out_off_local,
                    &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
                    &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc, &c->deferred,
                    &c->out_keys, &c->out_cnt, &c->owner_plan_dev, &c->piece_off, &c->piece_tmp, &c->piece_ptrs, &c->C2, &c->sub_sizes,
@@ -1429,7 +1630,8 @@ void apgk_destroy(apgk_ctx* c) {
                    &c->occ_tmp};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->occ_ev) if (e) cudaEventDestroy(e);
-  for (int s = 0; s < APGK_N_STAGES; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
+  for (auto& iv : c->ivs) { cudaEventDestroy(iv.e0); cudaEventDestroy(iv.e1); }
+  if (c->res_host) cudaFreeHost(c->res_host);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   for (cudaEvent_t e : c->slice_ev) cudaEventDestroy(e);
   if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -1447,7 +1649,7 @@ int apgk_reset(apgk_ctx* c) {
     CU(cudaMemsetAsync(c->bases.p, 0, std::min(c->bases.cap, (size_t)((c->total_bases + 31) / 32) * 8 + 256), c->stream));
     CU(cudaMemsetAsync(c->starts.p, 0, std::min(c->starts.cap, (size_t)((c->total_bases + 31) / 32) * 4 + 256), c->stream));
   }
-  c->total_bases = 0; c->n_reads = 0;
+  c->total_bases = 0; c->n_reads = 0; c->n_windows = 0;
   c->empty_nb.clear();
   invalidate_results(c);
   return APGK_OK;
@@ -1472,8 +1674,11 @@ int apgk_add_reads(apgk_ctx* c, const uint8_t* packed, const uint64_t* off, uint
     LAUNCHED();
   }
   CU(cudaStreamSynchronize(c->stream));  // inputs are only borrowed for the duration of the call
-  for (uint64_t r = 0; r < n_reads; r++)   // reads without bases own no start bit: remember where they sit (occurrence read ids)
-    if (off[r + 1] == off[r]) c->empty_nb.push_back(c->n_reads + r - c->empty_nb.size());
+  for (uint64_t r = 0; r < n_reads; r++) {  // reads without bases own no start bit: remember where they sit (occurrence read ids)
+    const uint64_t len = off[r + 1] - off[r];
+    if (len == 0) c->empty_nb.push_back(c->n_reads + r - c->empty_nb.size());
+    if (len >= (uint64_t)c->cfg.K) c->n_windows += len - (uint64_t)c->cfg.K + 1;
+  }
   c->total_bases += nb; c->n_reads += n_reads;
   invalidate_results(c);
   return APGK_OK;
@@ -1514,6 +1719,7 @@ int apgk_add_reads_uniform(apgk_ctx* c, const uint8_t* packed, uint64_t first_ba
                                                                                    c->starts.as<uint32_t>());
     LAUNCHED();
     c->total_bases += nb; c->n_reads += n_reads;
+    if (read_len >= (uint32_t)c->cfg.K) c->n_windows += n_reads * (uint64_t)(read_len - (uint32_t)c->cfg.K + 1);
     invalidate_results(c);
     c->n_slices = n_sl;
     return APGK_OK;
@@ -1526,6 +1732,7 @@ int apgk_add_reads_uniform(apgk_ctx* c, const uint8_t* packed, uint64_t first_ba
   LAUNCHED();
   CU(cudaStreamSynchronize(c->stream));
   c->total_bases += nb; c->n_reads += n_reads;
+  if (read_len >= (uint32_t)c->cfg.K) c->n_windows += n_reads * (uint64_t)(read_len - (uint32_t)c->cfg.K + 1);
   invalidate_results(c);
   return APGK_OK;
 }
@@ -1549,6 +1756,7 @@ int apgk_synth_reads(apgk_ctx* c, const apgk_synth_params* p, uint64_t r0, uint6
   LAUNCHED();
   CU(cudaStreamSynchronize(c->stream));
   c->total_bases += nb; c->n_reads += n_reads;
+  if (p->read_len >= (uint32_t)c->cfg.K) c->n_windows += n_reads * (uint64_t)(p->read_len - (uint32_t)c->cfg.K + 1);
   invalidate_results(c);
   return APGK_OK;
 }

@@ -551,14 +551,21 @@ struct ElemCvt<uint32_t, Key<1>> {  // keep only the REM low bits of the virtual
 // elements a thread holds in registers per tile
 template <typename Elem> struct TileItems { static constexpr int N = sizeof(Elem) <= 8 ? 16 : (sizeof(Elem) <= 16 ? 8 : 5); };
 
+// With d2 > 0 the histogram is taken over the WIDE digit dgw = (level digit << d2) | next d2 key bits: the chunk
+// row is its fold over the low d2 bits, and the wide counts are added to sub[(segment * bins << d2) + wide digit]
+// -- the sub-bucket sizes the sharded exchange needs (table.cuh k_gather_split), for one more shared-memory
+// reduction per chunk instead of a second pass over the partition buffer.
 template <typename Elem, int NT, int MODE>
 __global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, LevelPlan lp, DigitFn<MODE> dg,
-                                                  uint32_t* __restrict__ chunksum) {
+                                                  uint32_t* __restrict__ chunksum, DigitFn<MODE> dgw = DigitFn<MODE>{}, int d2 = 0,
+                                                  uint32_t* __restrict__ sub = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* hist = (uint32_t*)smem_raw;
   const int bins = lp.bins;
-  for (int i = threadIdx.x; i < bins; i += NT) hist[i] = 0;
+  const int hbins = bins << d2;
+  for (int i = threadIdx.x; i < hbins; i += NT) hist[i] = 0;
   __syncthreads();
+  if (blockIdx.x >= lp.seg_chunk0[lp.n_segments]) return;  // the grid is a host-side bound of the device-made plan
   int s; uint32_t t0, t1;
   chunk_tiles(lp, blockIdx.x, s, t0, t1);
   const uint64_t seg_lo = lp.seg_start[s], seg_hi = lp.seg_start[s + 1];
@@ -577,12 +584,25 @@ __global__ void __launch_bounds__(NT) k_hist_keys(const Elem* __restrict__ src, 
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint64_t i = base + (uint64_t)u * NT + threadIdx.x;
-      if (i < e1) reds_add(hist_a + 4 * dg(r[u]), 1u);
+      if (i < e1) reds_add(hist_a + 4 * (d2 ? dgw(r[u]) : dg(r[u])), 1u);
     }
   }
   __syncthreads();
   uint32_t* row = chunksum + (size_t)blockIdx.x * bins;
-  for (int i = threadIdx.x; i < bins; i += NT) row[i] = hist[i];
+  if (d2 == 0) {
+    for (int i = threadIdx.x; i < bins; i += NT) row[i] = hist[i];
+  } else {
+    uint32_t* gsub = sub + ((size_t)s * bins << d2);
+    for (int i = threadIdx.x; i < bins; i += NT) {
+      uint32_t t = 0;
+      for (int j = 0; j < (1 << d2); j++) {
+        const uint32_t v = hist[(i << d2) | j];
+        if (v) atomicAdd(&gsub[(i << d2) | j], v);
+        t += v;
+      }
+      row[i] = t;
+    }
+  }
 }
 
 // Software-pipelined over tiles: the loads and the ranking atomics of tile t+1 are issued in the same
@@ -599,6 +619,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
   ElemIn* stage; uint32_t* cnt2; unsigned long long* G; unsigned long long* Gabs; uint32_t* scratch;
   const int bins = lp.bins;
   scatter_smem_carve<ElemIn>(smem_raw, lp.tile_elems, bins, stage, cnt2, G, Gabs, scratch);
+  if (blockIdx.x >= lp.seg_chunk0[lp.n_segments]) return;  // the grid is a host-side bound of the device-made plan
   int s; uint32_t t0, t1;
   chunk_tiles(lp, blockIdx.x, s, t0, t1);
   const uint64_t seg_lo = lp.seg_start[s], seg_hi = lp.seg_start[s + 1];
@@ -694,6 +715,83 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_scatter_keys(const 
 #endif
     if (more) rank_tile(cnt_next_a);
   }
+}
+
+// ---------------------------------------------------------------- plans made on the device
+// Exclusive scan of one 64-bit value per thread over the block (NT multiple of 32); total via scratch[32].
+template <int NT>
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* scratch /* 33 */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long t = lane < NT / 32 ? scratch[lane] : 0ull, it = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, it, o);
+      if (lane >= o) it += u;
+    }
+    scratch[lane] = it - t;
+    if (lane == 31) scratch[32] = it;
+  }
+  __syncthreads();
+  return incl - v + scratch[wid];
+}
+
+// What the host used to do between the two levels, with the level-0 totals it had to fetch first: the plan of
+// a pass over the segments [s_lo, s_hi) of `tot` (segments outside the range count as empty), made by ONE CTA.
+//   seg_start[s]  element offset of segment s relative to the start of segment s_lo   [n_seg + 1]
+//   seg_tile0[s]  / seg_chunk0[s]   first tile / chunk of segment s                      [n_seg + 1]  (may be null)
+// info[0] = elements in the range, info[1] = sum of ALL n_seg totals, info[2] |= 1 if a segment holds 2^32 or more.
+constexpr int PLAN_NT = 1024;
+__global__ void __launch_bounds__(PLAN_NT) k_plan_range(const unsigned long long* __restrict__ tot, int n_seg, int s_lo, int s_hi,
+                                                         uint32_t tile_elems, uint32_t chunk_tiles,
+                                                         unsigned long long* __restrict__ seg_start, uint32_t* __restrict__ seg_tile0,
+                                                         uint32_t* __restrict__ seg_chunk0, unsigned long long* __restrict__ info) {
+  __shared__ unsigned long long scratch[34];
+  __shared__ unsigned long long carry[4];
+  if (threadIdx.x == 0) { carry[0] = carry[1] = carry[2] = carry[3] = 0; }
+  __syncthreads();
+  unsigned int bad = 0;
+  for (int s0 = 0; s0 < n_seg; s0 += PLAN_NT) {
+    const int s = s0 + (int)threadIdx.x;
+    const unsigned long long all = s < n_seg ? tot[s] : 0ull;
+    const unsigned long long n = (s >= s_lo && s < s_hi) ? all : 0ull;
+    if (all >= (1ull << 32)) bad = 1;
+    const unsigned long long tiles = (n + tile_elems - 1) / tile_elems;
+    const unsigned long long chunks = (tiles + chunk_tiles - 1) / chunk_tiles;
+    const unsigned long long e_n = block_excl_scan_u64<PLAN_NT>(n, scratch);
+    const unsigned long long t_n = scratch[32];
+    const unsigned long long e_t = block_excl_scan_u64<PLAN_NT>(tiles, scratch);
+    const unsigned long long t_t = scratch[32];
+    const unsigned long long e_c = block_excl_scan_u64<PLAN_NT>(chunks, scratch);
+    const unsigned long long t_c = scratch[32];
+    const unsigned long long e_a = block_excl_scan_u64<PLAN_NT>(all, scratch);
+    const unsigned long long t_a = scratch[32];
+    (void)e_a;
+    if (s < n_seg) {
+      seg_start[s] = carry[0] + e_n;
+      if (seg_tile0) seg_tile0[s] = (uint32_t)(carry[1] + e_t);
+      if (seg_chunk0) seg_chunk0[s] = (uint32_t)(carry[2] + e_c);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { carry[0] += t_n; carry[1] += t_t; carry[2] += t_c; carry[3] += t_a; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    seg_start[n_seg] = carry[0];
+    if (seg_tile0) seg_tile0[n_seg] = (uint32_t)carry[1];
+    if (seg_chunk0) seg_chunk0[n_seg] = (uint32_t)carry[2];
+    if (info) { info[0] = carry[0]; info[1] = carry[3]; }
+  }
+  if (bad && info) atomicOr(&info[2], 1ull);
 }
 
 // ---------------------------------------------------------------- column scan over tiles

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_blocksum(const uint32_t* __res
   if (threadIdx.x == 0) blocksum[blockIdx.x] = scratch[32];
 }
 // single block: exclusive scan of blocksum[nblocks] in place; total -> blocksum[nblocks]
-__global__ void __launch_bounds__(SCAN_NT) k_scan_top(unsigned long long* blocksum, uint32_t nblocks) {
+__global__ void __launch_bounds__(SCAN_NT) k_scan_top(unsigned long long* blocksum, uint32_t nblocks,
+                                                      unsigned long long* __restrict__ total_out /* may be null */) {
   __shared__ unsigned long long part[SCAN_NT];
   const uint32_t per = (nblocks + SCAN_NT - 1) / SCAN_NT;
   const uint32_t b0 = threadIdx.x * per;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_top(unsigned long long* blocks
     unsigned long long run = 0;
     for (int i = 0; i < SCAN_NT; i++) { unsigned long long v = part[i]; part[i] = run; run += v; }
     blocksum[nblocks] = run;
+    if (total_out) *total_out = run;
   }
   __syncthreads();
   unsigned long long run = part[threadIdx.x];
@@ -258,11 +260,18 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* const* __restri
 
 // ---------------------------------------------------------------- compaction: temp records -> final table
 // One warp per bucket.  Temp keys / counts live at element offset bofs[b] of the temp buffers.
+// Guarded form (total != null): the host launched this without knowing the record count; when *total exceeds
+// the buffers' capacity nothing is written and *overflow is raised (the host grows the buffers and runs it again).
 template <int W>
 __global__ void k_compact(const Key<W>* __restrict__ tmp_keys, const uint32_t* __restrict__ tmp_cnt,
                           const unsigned long long* __restrict__ bofs,
                           const unsigned long long* __restrict__ out_off, uint32_t nb, Key<W>* __restrict__ out_keys,
-                          uint32_t* __restrict__ out_cnt) {
+                          uint32_t* __restrict__ out_cnt, const unsigned long long* __restrict__ total,
+                          unsigned long long capacity, unsigned long long* __restrict__ overflow) {
+  if (total && *total > capacity) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1ull;
+    return;
+  }
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t b = warp; b < nb; b += nwarps) {

@@ -45,13 +45,14 @@ class KmerCounter:
     """One engine context on one GPU."""
 
     def __init__(self, K, device=0, want_counts=True, prefix_bits=0, reserve_bases=0, max_round_keys=0,
-                 async_ingest=False):
+                 async_ingest=False, max_inner_keys=0):
         self._L = _lib.lib()
         self.K = int(K)
         self.W = words_per_kmer(self.K)
         cfg = Config(K=self.K, device=device,
                      flags=WANT_SPECTRUM | (WANT_COUNTS if want_counts else 0) | (ASYNC_INGEST if async_ingest else 0),
-                     prefix_bits=prefix_bits, reserve_bases=reserve_bases, max_round_keys=max_round_keys)
+                     prefix_bits=prefix_bits, reserve_bases=reserve_bases, max_round_keys=max_round_keys,
+                     max_inner_keys=max_inner_keys)
         h = C.c_void_p()
         rc = self._L.apgk_create(C.byref(cfg), C.byref(h))
         if rc != 0:

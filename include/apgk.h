@@ -75,6 +75,11 @@ typedef struct {
   uint64_t reserve_bases; /* 0 or a hint: pre-size the device read store for this many bases */
   uint64_t max_round_keys; /* 0 = auto (from free device memory); else the most k-mer instances one
                               k-mer-space round may hold -- more rounds, less memory */
+  uint64_t max_inner_keys; /* 0 = auto.  Rounds have two levels: an OUTER round extracts the k-mers of a range
+                              of leading-bit buckets once (8*W bytes per instance), its INNER rounds run the
+                              second partition level and the counting over sub-ranges (4 or 8*W, + 4 bytes per
+                              instance).  max_round_keys bounds the outer rounds, this field the inner ones
+                              (default: max_round_keys when that is set) */
 } apgk_config;
 
 /* Parameters of the synthetic read generator; identical in the oracle. */

@@ -206,6 +206,58 @@ static int cmp_q(const void* a, const void* b) { return cmp_w((const uint64_t*)a
 
 void oracle_free(void* p) { free(p); }
 
+/* Steps 3-4 of the algorithm above: keys[] grouped by bucket (bstart[nb+1], bucket = top bbits bits) are sorted
+ * bucket by bucket and run-length counted.  Outputs malloc'd: sorted distinct k-mers, their counts. */
+static int sort_count_buckets(uint64_t* keys, const uint64_t* bstart, uint32_t nb, int K, int W, int bbits, int T,
+                              uint64_t** kmers_out, uint64_t** counts_out, uint64_t* n_distinct_out) {
+  uint64_t N = bstart[nb];
+  uint64_t* nd = (uint64_t*)calloc(nb + 1, 8);
+  uint64_t* cnts = (uint64_t*)malloc((N ? N : 1) * 8); /* counts at the bucket's instance offset, compacted later */
+  if (!nd || !cnts) return -2;
+  int lowbits = 2 * K - bbits;
+  g_cmpW = W;
+#pragma omp parallel num_threads(T)
+  {
+    uint64_t* tmp = NULL; uint64_t tmpcap = 0;
+#pragma omp for schedule(dynamic, 8)
+    for (int64_t b = 0; b < (int64_t)nb; b++) {
+      uint64_t lo = bstart[b], n = bstart[b + 1] - lo;
+      if (!n) continue;
+      uint64_t* a = keys + lo * W;
+      if (W == 1) {
+        if (n > tmpcap) { free(tmp); tmpcap = n + n / 4; tmp = (uint64_t*)malloc(tmpcap * 8); }
+        radix_sort_u64(a, tmp, n, lowbits);
+      } else {
+        qsort(a, n, (size_t)W * 8, cmp_q);
+      }
+      uint64_t d = 0;
+      for (uint64_t i = 0; i < n;) {
+        uint64_t j = i + 1;
+        while (j < n && cmp_w(a + i * W, a + j * W, W) == 0) j++;
+        if (d != i) memmove(a + d * W, a + i * W, (size_t)W * 8);
+        cnts[lo + d] = j - i;
+        d++; i = j;
+      }
+      nd[b] = d;
+    }
+    free(tmp);
+  }
+  uint64_t D = 0;
+  for (uint32_t b = 0; b < nb; b++) D += nd[b];
+  uint64_t* ok = (uint64_t*)malloc((D ? D : 1) * W * 8);
+  uint64_t* oc = (uint64_t*)malloc((D ? D : 1) * 8);
+  if (!ok || !oc) return -2;
+  uint64_t o = 0;
+  for (uint32_t b = 0; b < nb; b++) {
+    memcpy(ok + o * W, keys + bstart[b] * W, nd[b] * W * 8);
+    memcpy(oc + o, cnts + bstart[b], nd[b] * 8);
+    o += nd[b];
+  }
+  free(cnts); free(nd);
+  *kmers_out = ok; *counts_out = oc; *n_distinct_out = D;
+  return 0;
+}
+
 /* Count canonical k-mers.  Returns 0 on success.  Outputs are malloc'd:
  *   kmers  : n_distinct * W words, sorted ascending;  counts : n_distinct uint64.
  * n_instances_out (optional) = sum over reads of max(0, L-K+1). */
@@ -269,50 +321,166 @@ int oracle_count(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, i
     roll_reads(packed, off, slice[t], slice[t + 1], K, W, emit_scatter, &c);
   }
   free(cnt); free(slice);
-  /* sort each bucket, run-length count in place; nd[b] = distinct in bucket */
-  uint64_t* nd = (uint64_t*)calloc(nb + 1, 8);
-  uint64_t* cnts = (uint64_t*)malloc((N ? N : 1) * 8); /* counts at the bucket's instance offset, compacted later */
-  int lowbits = 2 * K - bbits;
-  g_cmpW = W;
+  int rc = sort_count_buckets(keys, bstart, nb, K, W, bbits, T, kmers_out, counts_out, n_distinct_out);
+  free(keys); free(bstart);
+  return rc;
+}
+
+/* ------------------------------------------------------------------ sampled-partition oracle
+ * SURVEY.md section 8(c) "human-scale check" (ii): the full k-mer set of a large read set cannot be held on the
+ * host, so the oracle scans ALL reads but keeps only the canonical k-mer instances whose leading `pbits` bits
+ * name a selected partition (sel[p] != 0, p < 2^pbits); those partitions are then counted exactly and compared
+ * with the device's table for the same key ranges.
+ *
+ * oracle_sample_prefix: the selected instances, unsorted (malloc'd, n * W words).  Reads are off[] delimited, or
+ * uniform (off == NULL: n_reads reads of read_len bases back to back).  n_windows_out = ALL windows seen. */
+int oracle_sample_prefix(const uint8_t* packed, const uint64_t* off, uint64_t n_reads, uint32_t read_len, int K, int pbits,
+                         const uint8_t* sel, int n_threads, uint64_t** keys_out, uint64_t* n_out, uint64_t* n_windows_out) {
+  if (K < 1 || K > 32 * MAXW || pbits < 0 || pbits > 16 || pbits > 2 * K) return -1;
+  int W = (2 * K + 63) / 64;
+#ifdef _OPENMP
+  if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+  n_threads = 1;
+#endif
+  int T = n_threads;
+  int topbits = 2 * K - 64 * (W - 1);
+  uint64_t topmask = topbits == 64 ? ~0ull : ((1ull << topbits) - 1);
+  int topshift = topbits - 2;
+  uint64_t* cnt = (uint64_t*)calloc((size_t)T + 1, 8);
+  uint64_t* win = (uint64_t*)calloc((size_t)T + 1, 8);
+  uint64_t** bufs = (uint64_t**)calloc((size_t)T, sizeof(uint64_t*));
+  if (!cnt || !win || !bufs) return -2;
+  int failed = 0;
 #pragma omp parallel num_threads(T)
   {
-    uint64_t* tmp = NULL; uint64_t tmpcap = 0;
-#pragma omp for schedule(dynamic, 8)
-    for (int64_t b = 0; b < (int64_t)nb; b++) {
-      uint64_t lo = bstart[b], n = bstart[b + 1] - lo;
-      if (!n) continue;
-      uint64_t* a = keys + lo * W;
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    uint64_t r_lo = n_reads / T * t + (n_reads % T < (uint64_t)t ? n_reads % T : (uint64_t)t);
+    uint64_t r_hi = n_reads / T * (t + 1) + (n_reads % T < (uint64_t)(t + 1) ? n_reads % T : (uint64_t)(t + 1));
+    uint64_t n = 0, nw = 0, cap = 1u << 16;
+    uint64_t* out = (uint64_t*)malloc(cap * (size_t)W * 8);   /* grows: the thread's selected instances */
+    int bad = out == NULL;
+    for (uint64_t r = r_lo; r < r_hi && !bad; r++) {
+      uint64_t b0 = off ? off[r] : r * (uint64_t)read_len, b1 = off ? off[r + 1] : b0 + read_len;
+      if (b1 - b0 < (uint64_t)K) continue;
+      if (n + (b1 - b0) > cap) {   /* room for every window of this read */
+        cap = 2 * cap + (b1 - b0);
+        uint64_t* nb = (uint64_t*)realloc(out, cap * (size_t)W * 8);
+        if (!nb) { bad = 1; break; }
+        out = nb;
+      }
       if (W == 1) {
-        if (n > tmpcap) { free(tmp); tmpcap = n + n / 4; tmp = (uint64_t*)malloc(tmpcap * 8); }
-        radix_sort_u64(a, tmp, n, lowbits);
+        uint64_t fw = 0, rc = 0, filled = 0;
+        for (uint64_t q = b0; q < b1; q++) {
+          uint32_t b = get_base(packed, q);
+          fw = ((fw << 2) | b) & topmask;
+          rc = (rc >> 2) | ((uint64_t)(3u - b) << topshift);
+          if (++filled >= (uint64_t)K) {
+            uint64_t c = fw < rc ? fw : rc;
+            nw++;
+            out[n] = c;
+            n += sel[pbits ? (uint32_t)(c >> (topbits - pbits)) : 0] != 0;
+          }
+        }
       } else {
-        qsort(a, n, (size_t)W * 8, cmp_q);
+        uint64_t fw[MAXW] = {0, 0, 0, 0}, rc[MAXW] = {0, 0, 0, 0};
+        uint64_t filled = 0;
+        for (uint64_t q = b0; q < b1; q++) {
+          uint32_t b = get_base(packed, q);
+          roll_fw(fw, W, topmask, b);
+          roll_rc(rc, W, topshift, b);
+          if (++filled >= (uint64_t)K) {
+            const uint64_t* c = cmp_w(fw, rc, W) <= 0 ? fw : rc;
+            nw++;
+            if (sel[bucket_of(c, K, W, pbits)]) {
+              for (int i = 0; i < W; i++) out[n * W + i] = c[i];
+              n++;
+            }
+          }
+        }
       }
-      uint64_t d = 0;
-      for (uint64_t i = 0; i < n;) {
-        uint64_t j = i + 1;
-        while (j < n && cmp_w(a + i * W, a + j * W, W) == 0) j++;
-        if (d != i) memmove(a + d * W, a + i * W, (size_t)W * 8);
-        cnts[lo + d] = j - i;
-        d++; i = j;
-      }
-      nd[b] = d;
     }
-    free(tmp);
+    if (bad) {
+#pragma omp atomic write
+      failed = 1;
+    }
+    cnt[t + 1] = n; win[t] = nw; bufs[t] = out;
   }
-  uint64_t D = 0;
-  for (uint32_t b = 0; b < nb; b++) D += nd[b];
-  uint64_t* ok = (uint64_t*)malloc((D ? D : 1) * W * 8);
-  uint64_t* oc = (uint64_t*)malloc((D ? D : 1) * 8);
-  uint64_t o = 0;
-  for (uint32_t b = 0; b < nb; b++) {
-    memcpy(ok + o * W, keys + bstart[b] * W, nd[b] * W * 8);
-    memcpy(oc + o, cnts + bstart[b], nd[b] * 8);
-    o += nd[b];
+  for (int t = 0; t < T; t++) cnt[t + 1] += cnt[t];   /* cnt[t] = first output slot of thread t */
+  uint64_t* keys = failed ? NULL : (uint64_t*)malloc((cnt[T] ? cnt[T] : 1) * (size_t)W * 8);
+  uint64_t nw = 0;
+  for (int t = 0; t < T; t++) {
+    if (keys && bufs[t]) memcpy(keys + cnt[t] * W, bufs[t], (cnt[t + 1] - cnt[t]) * (size_t)W * 8);
+    free(bufs[t]);
+    nw += win[t];
   }
-  free(keys); free(cnts); free(nd); free(bstart);
-  *kmers_out = ok; *counts_out = oc; *n_distinct_out = D;
+  uint64_t n_all = cnt[T];
+  free(cnt); free(win); free(bufs);
+  if (!keys) return -2;
+  *keys_out = keys; *n_out = n_all;
+  if (n_windows_out) *n_windows_out = nw;
   return 0;
+}
+
+/* oracle_count_keys: sort + count n canonical k-mer instances (W words each, any order; the array is consumed:
+ * reordered in place is not promised, it is copied).  Outputs as oracle_count. */
+int oracle_count_keys(const uint64_t* keys_in, uint64_t n, int K, int n_threads, uint64_t** kmers_out, uint64_t** counts_out,
+                      uint64_t* n_distinct_out) {
+  if (K < 1 || K > 32 * MAXW) return -1;
+  int W = (2 * K + 63) / 64;
+  int bbits = 2 * K < 16 ? 2 * K : 16;
+  uint32_t nb = 1u << bbits;
+#ifdef _OPENMP
+  if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+  n_threads = 1;
+#endif
+  int T = n_threads;
+  uint64_t* cnt = (uint64_t*)calloc((size_t)T * nb, 8);
+  uint64_t* bstart = (uint64_t*)malloc(((size_t)nb + 1) * 8);
+  uint64_t* keys = (uint64_t*)malloc((n ? n : 1) * (size_t)W * 8);
+  if (!cnt || !bstart || !keys) return -2;
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    uint64_t lo = n / T * t + (n % T < (uint64_t)t ? n % T : (uint64_t)t);
+    uint64_t hi = n / T * (t + 1) + (n % T < (uint64_t)(t + 1) ? n % T : (uint64_t)(t + 1));
+    uint64_t* c = cnt + (size_t)t * nb;
+    for (uint64_t i = lo; i < hi; i++) c[bucket_of(keys_in + i * W, K, W, bbits)]++;
+  }
+  uint64_t run = 0;
+  for (uint32_t b = 0; b < nb; b++) {
+    bstart[b] = run;
+    for (int t = 0; t < T; t++) { uint64_t v = cnt[(size_t)t * nb + b]; cnt[(size_t)t * nb + b] = run; run += v; }
+  }
+  bstart[nb] = run;
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    uint64_t lo = n / T * t + (n % T < (uint64_t)t ? n % T : (uint64_t)t);
+    uint64_t hi = n / T * (t + 1) + (n % T < (uint64_t)(t + 1) ? n % T : (uint64_t)(t + 1));
+    uint64_t* c = cnt + (size_t)t * nb;
+    for (uint64_t i = lo; i < hi; i++) {
+      uint64_t pos = c[bucket_of(keys_in + i * W, K, W, bbits)]++;
+      for (int j = 0; j < W; j++) keys[pos * W + j] = keys_in[i * W + j];
+    }
+  }
+  free(cnt);
+  int rc = sort_count_buckets(keys, bstart, nb, K, W, bbits, T, kmers_out, counts_out, n_distinct_out);
+  free(keys); free(bstart);
+  return rc;
 }
 
 /* spectrum[f] = #distinct k-mers with count f; dense, length max_f + 1 (index 0 unused = 0). */

@@ -63,6 +63,11 @@ def lib():
         L.oracle_occurrences.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_occurrences.restype = C.c_int
+        L.oracle_sample_prefix.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_int, C.POINTER(u64p), u64p, u64p]
+        L.oracle_sample_prefix.restype = C.c_int
+        L.oracle_count_keys.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(u64p), C.POINTER(u64p), u64p]
+        L.oracle_count_keys.restype = C.c_int
         _lib = L
     return _lib
 
@@ -108,6 +113,56 @@ def count(packed, off, K, n_threads=0):
     L.oracle_free(kp)
     L.oracle_free(cp)
     return kmers, counts, ni.value
+
+
+def sample_prefix(packed, off, K, pbits, parts, n_reads=None, read_len=0, n_threads=0):
+    """Sampled-partition oracle, step 1 (SURVEY.md section 8c "human-scale check" ii): the canonical k-mer INSTANCES
+    of all reads whose leading `pbits` bits are one of `parts`.  packed: uint8 array or an integer address; off:
+    uint64[n+1] or None for uniform reads (n_reads x read_len).  -> (keys uint64[n, W] unsorted, n_windows_seen)."""
+    L = lib()
+    if isinstance(packed, np.ndarray):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        paddr = packed.ctypes.data
+    else:
+        paddr = int(packed)
+    oaddr = None
+    if off is not None:
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n_reads = len(off) - 1
+        oaddr = off.ctypes.data
+    sel = np.zeros(1 << pbits, dtype=np.uint8)
+    sel[np.asarray(list(parts), dtype=np.int64)] = 1
+    kp = C.POINTER(C.c_uint64)()
+    n = C.c_uint64()
+    nw = C.c_uint64()
+    rc = L.oracle_sample_prefix(paddr, oaddr, n_reads, read_len, K, pbits, sel.ctypes.data, n_threads,
+                                C.byref(kp), C.byref(n), C.byref(nw))
+    if rc != 0:
+        raise RuntimeError("oracle_sample_prefix failed rc=%d" % rc)
+    W = n_words(K)
+    keys = np.ctypeslib.as_array(kp, shape=(max(n.value, 1) * W,))[: n.value * W].copy().reshape(n.value, W)
+    L.oracle_free(kp)
+    return keys, nw.value
+
+
+def count_keys(keys, K, n_threads=0):
+    """Sampled-partition oracle, step 2: sort + count canonical k-mer instances (uint64[n, W], any order).
+    -> (kmers uint64[d, W] sorted, counts uint64[d])."""
+    L = lib()
+    W = n_words(K)
+    keys = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1, W)
+    kp = C.POINTER(C.c_uint64)()
+    cp = C.POINTER(C.c_uint64)()
+    nd = C.c_uint64()
+    rc = L.oracle_count_keys(keys.ctypes.data, len(keys), K, n_threads, C.byref(kp), C.byref(cp), C.byref(nd))
+    if rc != 0:
+        raise RuntimeError("oracle_count_keys failed rc=%d" % rc)
+    n = nd.value
+    kmers = np.ctypeslib.as_array(kp, shape=(max(n, 1) * W,))[: n * W].copy().reshape(n, W)
+    counts = np.ctypeslib.as_array(cp, shape=(max(n, 1),))[:n].copy()
+    L.oracle_free(kp)
+    L.oracle_free(cp)
+    return kmers, counts
 
 
 def spectrum(counts):

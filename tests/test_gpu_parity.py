@@ -90,6 +90,7 @@ def test_ragged_reads(oracle, K, prefix_bits):
     p, o = oracle.pack_strings(reads)
     kc = _run(p, o, K, prefix_bits=prefix_bits)
     ek, ec = _assert_equal_to_oracle(oracle, kc, p, o, K)
+    assert kc.window_upper() == kc.totals()[0]   # the instance count kept at ingest is exact, short reads included
     # frequency-table lookups: present k-mers (both strands), absent k-mers
     if len(ek):
         idx = np.random.RandomState(K).randint(0, len(ek), size=min(len(ek), 500))
@@ -178,11 +179,13 @@ def test_kmer_space_rounds(oracle, K):
     sp = oracle.synth_params(400_000, 150)
     p, o = oracle.synth_reads(sp, 0, 20_000)
     ek, ec, en = oracle.count(p, o, K)
-    for budget in (en // 5 + 1, en // 2 + 1):
-        kc = KmerCounter(K, max_round_keys=budget)
+    # (outer budget, inner budget): one level of rounds, then outer rounds (one filtered extraction each) cut
+    # into inner rounds (second partition level + counting over sub-ranges of the extracted keys)
+    for budget, inner in ((en // 5 + 1, 0), (en // 2 + 1, 0), (en // 2 + 1, en // 7 + 1), (en + 1, en // 4 + 1)):
+        kc = KmerCounter(K, max_round_keys=budget, max_inner_keys=inner)
         kc.add_reads_uniform(p, 20_000, 150)
         kc.finish()
-        assert kc.geometry()["n_rounds"] >= 2
+        assert kc.geometry()["n_rounds"] >= (2 if not inner else 4)
         _assert_equal_to_oracle(oracle, kc, p, o, K)
         idx = np.random.RandomState(K).randint(0, len(ek), size=2000)
         assert (kc.lookup(ek[idx], canonicalise=False).astype(np.uint64) == ec[idx]).all()

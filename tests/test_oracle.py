@@ -140,3 +140,30 @@ def test_occurrences_a_matches_b(oracle, K):
             w = reads[r][abs(q) - 1:abs(q) - 1 + K]
             assert len(w) == K and B.kmer_to_int(B.canonical_str(w)) == kv
             assert (q > 0) == (B.canonical_str(w) == w)
+
+
+@pytest.mark.parametrize("K", [2, 5, 20, 25, 32, 33, 48, 64, 96])
+def test_sampled_partition_oracle_matches_full_count(oracle, K):
+    """The sampled-partition oracle used at sizes the host cannot hold (human-scale check ii):
+    scanning all reads and keeping the k-mers of a few leading-bit partitions, then counting them, must give
+    exactly the full oracle's records of those partitions -- ragged reads (off[]) and uniform reads (no off[])."""
+    rnd = random.Random(300 + K)
+    reads = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([0, 1, K - 1, K, K + 1, K + 9, 140]))) for _ in range(200)]
+    reads += ["A" * (K + 25), "ACGT" * 40, "T" * (K + 3), ""]
+    p, o = oracle.pack_strings(reads)
+    ek, ec, en = oracle.count(p, o, K)
+    W = ek.shape[1]
+    pb = min(8, 2 * K)
+    top = 2 * K - 64 * (W - 1)
+    parts = sorted({0, 3 % (1 << pb), (1 << pb) - 1, 77 % (1 << pb)})
+    keys, nw = oracle.sample_prefix(p, o, K, pb, parts)
+    assert nw == en
+    sk, sc = oracle.count_keys(keys, K)
+    m = np.isin((ek[:, 0] >> np.uint64(top - pb)).astype(np.int64), parts)
+    assert (sk == ek[m]).all() and (sc == ec[m]).all() and int(sc.sum()) == len(keys)
+    sp = oracle.synth_params(100_000, 100)
+    pu, ou = oracle.synth_reads(sp, 0, 5_000)
+    ku, nu = oracle.sample_prefix(pu, None, K, pb, parts, n_reads=5_000, read_len=100)
+    kr, nr = oracle.sample_prefix(pu, ou, K, pb, parts)
+    assert nu == nr and (oracle.count_keys(ku, K)[0] == oracle.count_keys(kr, K)[0]).all()
+    assert (oracle.count_keys(ku, K)[1] == oracle.count_keys(kr, K)[1]).all()
