@@ -1992,6 +1992,24 @@ int apgk_counts_copy(apgk_ctx* c, uint64_t first, uint64_t n, uint64_t* kmers_ou
   return APGK_OK;
 }
 
+int apgk_prefix_range(apgk_ctx* c, int32_t prefix_bits, uint64_t prefix, uint64_t* first, uint64_t* n) {
+  if (!c || !first || !n) return APGK_E_ARG;
+  if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");
+  const int P = c->geom.D0 + c->geom.D1;
+  if (prefix_bits < 0 || prefix_bits > P || c->geom.pad != 0 || (prefix >> prefix_bits) != 0)
+    FAIL(APGK_E_ARG, "apgk_prefix_range: prefix_bits must be 0..%d (the table's index bits) and the prefix below 2^prefix_bits", P);
+  *first = 0; *n = 0;
+  if (!c->n_distinct) return APGK_OK;
+  CU(cudaSetDevice(c->device));
+  unsigned long long lo = 0, hi = 0;
+  const unsigned long long* idx = c->out_off.as<unsigned long long>();
+  CU(cudaMemcpyAsync(&lo, idx + (prefix << (P - prefix_bits)), 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&hi, idx + ((prefix + 1) << (P - prefix_bits)), 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *first = lo; *n = hi - lo;
+  return APGK_OK;
+}
+
 int apgk_lookup(apgk_ctx* c, const uint64_t* kmers, uint64_t n, int canonicalise, uint32_t* counts_out) {
   if (!c || (!kmers && n) || (!counts_out && n)) return APGK_E_ARG;
   if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");

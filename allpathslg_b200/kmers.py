@@ -151,6 +151,12 @@ class KmerCounter:
         self._ck(self._L.apgk_counts_copy(self._h, first, n, k.ctypes.data, c.ctypes.data))
         return k[:n], c[:n]
 
+    def prefix_range(self, prefix_bits, prefix):
+        """(first, n): the table records whose k-mers start with the `prefix_bits`-bit value `prefix`."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.apgk_prefix_range(self._h, prefix_bits, prefix, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def counts_device(self):
         a, b = C.c_void_p(), C.c_void_p()
         n = C.c_uint64()

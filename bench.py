@@ -43,17 +43,32 @@ READ_LEN = 100
 READS_PER_GPU = int(os.environ.get("APGK_BENCH_READS", 60_000_000))
 GENOME_PER_GPU = int(os.environ.get("APGK_BENCH_GENOME", 100_000_000))
 CPU_SAMPLE_READS = int(os.environ.get("APGK_BENCH_CPU_READS", 10_000_000))
+# the CPU arm's sample keeps the workload's coverage (60x): 10 M reads of a 16.7 Mb genome, the same at every N
+CPU_SAMPLE_GENOME = max(READ_LEN, GENOME_PER_GPU * CPU_SAMPLE_READS // READS_PER_GPU)
+PARITY_PBITS, PARITY_PARTS = 8, (5, 77, 130, 201)   # sampled-partition oracle check: 4 of 256 leading-bit partitions
 B_ALG_K25 = 136.0  # 8 * (2*7 + 3) bytes per instance for the 7-pass LSD model
 
 
-def ncu_traffic(stage):
-    """DRAM bytes per launch of a stage's kernel from the committed full-size ncu capture
-    (profiles/r01_traffic.json: same workload as the N=1 bench), or None."""
+def traffic_file():
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        if os.path.exists(os.path.join(ROOT, "profiles", name)):
+            return name
+    return None
+
+
+def ncu_traffic(stage=None):
+    """DRAM bytes per launch of a stage's kernel from the committed full-size ncu capture (profiles/rNN_traffic.json:
+    same workload as the N=1 bench), or None.  stage=None: the sum over the step's kernels that were captured."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            k = json.load(f)["kernels"][stage]
-        t = (k["dram_read_GB"] + k["dram_write_GB"]) * 1e9
-        return t if t == t else None
+        with open(os.path.join(ROOT, "profiles", traffic_file())) as f:
+            ks = json.load(f)["kernels"]
+        if stage is not None:
+            ks = {stage: ks[stage]}
+        t = 0.0
+        for k in ks.values():
+            if k.get("dram_read_GB") is not None and k.get("dram_write_GB") is not None:
+                t += (k["dram_read_GB"] + k["dram_write_GB"]) * 1e9
+        return t if t > 0 else None
     except Exception:
         return None
 
@@ -123,7 +138,8 @@ class ClockSampler:
 
 
 def cpu_baseline(reads, genome_len, threads=0):
-    """Oracle port timed on the host cores over the first `reads` reads of the workload."""
+    """Oracle port timed on the host cores over `reads` reads of a `genome_len` genome (same generator, same
+    coverage as the workload)."""
     from oracle import oracle_a as A
 
     A.build()
@@ -144,15 +160,14 @@ def run_reference(args):
     if rank != 0:
         return 0
     n_gpus = args.gpus
-    genome = GENOME_PER_GPU * n_gpus
     times, n_inst, cores = [], 0, 1
     for i in range(args.warmup + args.steps):
-        n_inst, dt, cores = cpu_baseline(CPU_SAMPLE_READS, genome)
+        n_inst, dt, cores = cpu_baseline(CPU_SAMPLE_READS, CPU_SAMPLE_GENOME)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     val = n_inst / (ms * 1e-3) / 1e9
-    sample = "first %d reads (%d k-mer instances) of the workload per step" % (CPU_SAMPLE_READS, n_inst)
+    sample = cpu_sample_text(n_inst) + ", per step"
     line = {
         "impl": "reference", "metric": "k-mer spectrum throughput (K=25), k-mer instances counted per second",
         "value": val, "unit": "Gk-mers/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
@@ -166,8 +181,14 @@ def run_reference(args):
     return 0
 
 
+def cpu_sample_text(n_inst):
+    return ("%d reads of a %.1f Mb genome (%dx, the workload's coverage and generator; %d k-mer instances)"
+            % (CPU_SAMPLE_READS, CPU_SAMPLE_GENOME / 1e6, CPU_SAMPLE_READS * READ_LEN // max(CPU_SAMPLE_GENOME, 1), n_inst))
+
+
 def workload_config(n_gpus):
-    return {"workload": "synthetic %d Mb genome, %d M x %d bp reads (%dx) per GPU, K=%d spectrum + counts"
+    return {"workload": "synthetic %d Mb genome, %d M x %d bp reads (%dx) per GPU, K=%d: spectrum to the host + sorted "
+                        "(k-mer, count) table resident on the device (what the frequency-table lookups read)"
                         % (GENOME_PER_GPU // 1_000_000, READS_PER_GPU // 1_000_000, READ_LEN,
                            READS_PER_GPU * READ_LEN // GENOME_PER_GPU, K),
             "K": K, "reads_per_gpu": READS_PER_GPU, "read_len": READ_LEN, "genome_len": GENOME_PER_GPU * n_gpus,
@@ -206,6 +227,30 @@ def measure_records(kc, torch):
             "ms": round(dt * 1e3, 2), "value": round(info["n_occ"] / dt / 1e9, 3), "unit": "G records/s",
             "stage_ms": {k_: round(v, 2) for k_, v in info["ms"].items()}, "n_big_runs": info["n_big_runs"],
             "bytes_out": int(info["n_occ"]) * 8}
+
+
+def sampled_parity(kc, host, n_reads):
+    """oracle over ALL reads restricted to a few leading-bit partitions vs the table."""
+    from oracle import oracle_a as A
+
+    t0 = time.perf_counter()
+    keys, n_win = A.sample_prefix(host.data_ptr(), None, K, PARITY_PBITS, PARITY_PARTS, n_reads=n_reads, read_len=READ_LEN,
+                                  n_threads=os.cpu_count() or 1)
+    ok_, oc_ = A.count_keys(keys, K, n_threads=os.cpu_count() or 1)
+    top = 2 * K
+    pre = (ok_[:, 0] >> np.uint64(top - PARITY_PBITS)).astype(np.int64)
+    ok = n_win == kc.totals()[0]
+    n_rec = 0
+    for part in PARITY_PARTS:
+        first, n = kc.prefix_range(PARITY_PBITS, part)
+        gk, gc = kc.counts(first, n)
+        m = pre == part
+        ok = ok and len(gk) == int(m.sum()) and bool((gk == ok_[m]).all()) and bool((gc.astype(np.uint64) == oc_[m]).all())
+        n_rec += n
+    return {"what": "CPU oracle over all reads restricted to %d of %d leading-bit partitions vs the device table, record by record"
+                    % (len(PARITY_PARTS), 1 << PARITY_PBITS),
+            "ok": bool(ok), "records_compared": int(n_rec), "instances_in_sample": int(len(keys)),
+            "windows_scanned": int(n_win), "seconds": round(time.perf_counter() - t0, 2)}
 
 
 def run_ours(args):
@@ -313,7 +358,7 @@ def run_ours(args):
     step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     for _ in range(e2e_steps):
         spec = step_e2e()
     barrier()
@@ -341,6 +386,15 @@ def run_ours(args):
         except Exception as e:
             records = {"error": str(e)[:200]}
 
+    # ---------------- sampled-partition parity of THIS workload (N=1): the CPU oracle scans all the reads, keeps the
+    # k-mers of 4 of 256 leading-bit partitions, counts them and is compared record by record with the device table
+    parity = None
+    if world == 1 and os.environ.get("APGK_BENCH_PARITY", "1") != "0":
+        try:
+            parity = sampled_parity(kc, host, READS_PER_GPU)
+        except Exception as e:
+            parity = {"error": str(e)[:200]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -366,19 +420,34 @@ def run_ours(args):
     per_stage = {s: {"ms": round(stage_ms.get(s, 0.0), 3),
                      "alg_GBps": round(alg_bytes[s] / (stage_ms[s] * 1e-3) / 1e9, 1) if stage_ms.get(s, 0) > 0 else None}
                  for s in alg_bytes}
+    for s_ in ("scan0", "scan1", "big", "owner"):   # small stages without a byte model: time only
+        if stage_ms.get(s_, 0.0) > 0:
+            per_stage[s_] = {"ms": round(stage_ms[s_], 3), "alg_GBps": None}
     pipeline_ms = stage_ms.get("total", ms_step)
+    stage_sum = sum(v for k_, v in stage_ms.items() if k_ != "total")
+    step_traffic = ncu_traffic() if (n_gpus == 1 and READS_PER_GPU == 60_000_000) else None
     # measured DRAM bytes of that kernel: one ncu --set full capture of the N=1 workload, committed under profiles/
     traffic = ncu_traffic(dom) if (n_gpus == 1 and READS_PER_GPU == 60_000_000) else None
     roofline = {"bound": "hbm", "kernel": kern_names[dom], "achieved": round(achieved, 1), "peak": peak,
                 "peak_source": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                "traffic_source": "profiles/r01_traffic.json (ncu, separate run)" if traffic else None,
+                "traffic_source": ("profiles/%s (ncu, separate run)" % traffic_file()) if traffic else None,
                 "algorithmic_bytes": int(alg_bytes[dom]),
                 "stages": per_stage,
+                # the whole step's DRAM traffic as ncu measured it (sum over its kernels) over the step's device time:
+                # what the pipeline really draws from HBM -- the figure to read as "fraction of peak"
+                "pipeline_actual": ({"dram_bytes_per_step": int(step_traffic),
+                                     "GBps": round(step_traffic / (pipeline_ms * 1e-3) / 1e9, 1),
+                                     "frac_of_peak": round(step_traffic / (pipeline_ms * 1e-3) / 1e9 / peak, 4),
+                                     "source": "profiles/%s" % traffic_file()} if step_traffic else None),
+                "device_idle_ms_per_step": round(pipeline_ms - stage_sum, 3) if world == 1 else None,
+                # SURVEY.md section 8(d)'s contract figure: a 7-pass LSD sort would move 136 B per instance; this MSD + hash
+                # pipeline moves ~40.  "lsd_model_ratio" says how fast a model-conforming sort would have to stream to keep
+                # up -- it is NOT an achieved bandwidth and can exceed 1
                 "pipeline_model": {"B_alg_bytes_per_kmer": B_ALG_K25,
                                    "lsd_model_equivalent_GBps": round(n_local * B_ALG_K25 / (pipeline_ms * 1e-3) / 1e9, 1),
-                                   "frac_of_peak": round(n_local * B_ALG_K25 / (pipeline_ms * 1e-3) / 1e9 / peak, 4)}}
+                                   "lsd_model_ratio": round(n_local * B_ALG_K25 / (pipeline_ms * 1e-3) / 1e9 / peak, 4)}}
 
-    cb_inst, cb_dt, cores = cpu_baseline(CPU_SAMPLE_READS, genome)
+    cb_inst, cb_dt, cores = cpu_baseline(CPU_SAMPLE_READS, CPU_SAMPLE_GENOME)
     line = {
         "metric": "k-mer spectrum throughput (K=25), k-mer instances counted per second",
         "value": round(value, 3), "unit": "Gk-mers/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
@@ -389,13 +458,13 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(n_gpus),
         "e2e": {"value": round(e2e_val, 3), "unit": "Gk-mers/s", "h2d_bytes_per_step": int(nbytes) * n_gpus,
-                "d2h_bytes_per_step": int(spec_bytes) * n_gpus, "steps": e2e_steps},
+                "d2h_bytes_per_step": int(spec_bytes) * n_gpus, "steps": e2e_steps,
+                "d2h": "the spectrum; the sorted (k-mer, count) table stays on the device, where the lookups read it"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": {"value": round(cb_inst / cb_dt / 1e9, 4), "unit": "Gk-mers/s", "cores": cores, "kind": "port",
-                         "sample": "first %d reads (%d k-mer instances) of the workload, oracle port "
-                                   "(not the reference's code: parity unpinned)" % (CPU_SAMPLE_READS, cb_inst)},
+                         "sample": cpu_sample_text(cb_inst) + ", oracle port (not the reference's code: parity unpinned)"},
         "geometry": geo, "shard_ms": dict({k_: round(v / args.steps, 2) for k_, v in shard_acc.items()}, **{k_: (list(v) if isinstance(v, tuple) else v) for k_, v in shard_info.items()}) if shard_acc else None,
-        "records": records, "lookups": lookups,
+        "records": records, "lookups": lookups, "parity_sample": parity,
         "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }

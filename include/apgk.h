@@ -127,6 +127,11 @@ int apgk_counts_device(apgk_ctx* ctx, const uint64_t** d_kmers, const uint32_t**
 /* Copy records [first, first+n) of the table to host buffers (either may be NULL). */
 int apgk_counts_copy(apgk_ctx* ctx, uint64_t first, uint64_t n, uint64_t* kmers_out, uint32_t* counts_out);
 
+/* Records [*first, *first + *n) of the sorted table are exactly the k-mers whose leading prefix_bits bits equal
+ * `prefix` (one parcel of k-mer space; read off the table's prefix index).  prefix_bits <= D0 + D1 of
+ * apgk_geometry.  On a shard context only the k-mers the shard owns are there. */
+int apgk_prefix_range(apgk_ctx* ctx, int32_t prefix_bits, uint64_t prefix, uint64_t* first, uint64_t* n);
+
 /* ---- frequency-table queries (need APGK_WANT_COUNTS and a finished context) */
 /* counts_out[i] = count of query k-mer i (W words each, host), 0 if absent.  Queries are
  * canonicalised first when canonicalise != 0. */

@@ -159,7 +159,11 @@ def test_sampled_partition_oracle_matches_full_count(oracle, K):
     keys, nw = oracle.sample_prefix(p, o, K, pb, parts)
     assert nw == en
     sk, sc = oracle.count_keys(keys, K)
-    m = np.isin((ek[:, 0] >> np.uint64(top - pb)).astype(np.int64), parts)
+    if pb <= top:
+        pre = (ek[:, 0] >> np.uint64(top - pb)).astype(np.int64)
+    else:  # the prefix reaches into word 1
+        pre = ((ek[:, 0] << np.uint64(pb - top)) | (ek[:, 1] >> np.uint64(64 - (pb - top)))).astype(np.int64)
+    m = np.isin(pre, parts)
     assert (sk == ek[m]).all() and (sc == ec[m]).all() and int(sc.sum()) == len(keys)
     sp = oracle.synth_params(100_000, 100)
     pu, ou = oracle.synth_reads(sp, 0, 5_000)
