@@ -135,44 +135,59 @@ __global__ void __launch_bounds__(NT) k_sub_hist(const Elem* __restrict__ elems,
   }
 }
 
-// One CTA per owned bucket (grid-stride).  Source s's pieces start at src_base[s] + seg_off[s]: either
-// segments of one receive buffer (after an NCCL all-to-all) or the senders' own partition buffers mapped
-// over NVLink peer memory -- then this kernel IS the exchange, the loads cross NVLink and no receive
-// buffer exists.  A merged bucket holds n_src times the instances the sender's
-// geometry aimed at, so the gather also SPLITS it by the next d2 remainder bits into 2^d2 sub-buckets
-// (two passes over the pieces, the second served by L2): count, then place with warp-aggregated
-// cursors.  Order inside a sub-bucket is arbitrary -- the counting kernels do not depend on it.
-// Writes the fine bucket table (sizes, offsets) for buckets (b << d2) | j.
+// What the gather reads and writes.  Source s's pieces start at src_base[s] + seg_off[s]: either segments of
+// one receive buffer (after an NCCL all-to-all) or the senders' own partition buffers mapped over NVLink peer
+// memory -- then the kernel IS the exchange, the loads cross NVLink and no receive buffer exists.
+template <typename Elem>
+struct GatherArgs {
+  const Elem* const* src_base;            // [n_src] base of every source's elements
+  const unsigned long long* seg_off;      // [n_src] element offset added to src_base[s] (null: 0)
+  const unsigned long long* piece_off;    // [n_src][nb + 1] offset of bucket b's piece in source s
+  const uint32_t* sizes_all;              // [n_src][nb] piece sizes
+  const unsigned long long* bofs_coarse;  // [nb] offset of merged bucket b in the shard, plus coarse_base
+  unsigned long long coarse_base;
+  uint32_t n_src, nb, lo, hi;             // owned buckets [lo, hi)
+  int d2, digit_pos;                      // split every merged bucket by the d2 bits at digit_pos
+  Elem* out;                              // the bucket-major shard
+  unsigned long long* bsize_fine;         // [nb << d2] sizes / offsets of the fine buckets (b << d2) | j
+  unsigned long long* bofs_fine;
+  const uint32_t* sub_sizes;              // [n_src][(hi - lo) << d2] senders' sub-bucket counts of this range, or null
+  const uint32_t* const* sub_ptrs;        // [n_src] the senders' own full count arrays [nb << d2] (peer memory), or null
+};
+
+// One WARP per owned bucket (grid-stride).  A merged bucket holds n_src times the instances the sender's
+// geometry aimed at, so the gather also SPLITS it by the next d2 remainder bits into 2^d2 sub-buckets.
+// With the senders' sub-bucket counts at hand the pieces are read ONCE (peer memory is not cached in the
+// reader's L2); without them a first pass over the pieces counts.  Order inside a sub-bucket is arbitrary --
+// the counting kernels do not depend on it.  Writes the fine bucket table (sizes, offsets).
 template <typename Elem, int NT>
-__global__ void __launch_bounds__(NT) k_gather_split(const Elem* const* __restrict__ src_base, const unsigned long long* __restrict__ seg_off,
-                                                     const unsigned long long* __restrict__ piece_off /* [n_src][nb+1] */,
-                                                     const uint32_t* __restrict__ sizes_all,
-                                                     const unsigned long long* __restrict__ bofs_coarse, uint32_t n_src, uint32_t nb,
-                                                     uint32_t lo, uint32_t hi, int d2, int digit_pos, Elem* __restrict__ out,
-                                                     unsigned long long* __restrict__ bsize_fine,
-                                                     unsigned long long* __restrict__ bofs_fine,
-                                                     const uint32_t* __restrict__ sub_sizes /* [n_src][(hi-lo) << d2] or null */) {
-  // One WARP per owned bucket: lane j keeps the count and then the write cursor of sub-bucket j in a
-  // register, positions come from ballots -- no shared memory, no barriers, no atomics, and the eight
-  // warps of a CTA keep eight buckets' loads (local HBM or NVLink) in flight.
+__global__ void __launch_bounds__(NT) k_gather_split(const GatherArgs<Elem> ga) {
+  // lane j keeps the count and then the write cursor of sub-bucket j in a register, positions come from
+  // ballots -- no shared memory, no barriers, no atomics, and the eight warps of a CTA keep eight buckets'
+  // loads (local HBM or NVLink) in flight.
   constexpr int U = 4;                 // elements per lane and step
+  const int d2 = ga.d2, digit_pos = ga.digit_pos;
+  const uint32_t n_src = ga.n_src, nb = ga.nb, lo = ga.lo, hi = ga.hi;
   const uint32_t nbins = 1u << d2, mask = nbins - 1u;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * NT + threadIdx.x) >> 5, nwarps = (gridDim.x * NT) >> 5;
+  Elem* __restrict__ out = ga.out;
   for (uint32_t b = lo + warp; b < hi; b += nwarps) {
-    // ---- sub-bucket sizes: from the senders' own counts when they came along (then the pieces are
-    // read once), else by a first pass over the pieces
+    // ---- sub-bucket sizes
     uint32_t mine = 0;                 // lane j: size of sub-bucket j
     if (d2 == 0) {
-      for (uint32_t s = 0; s < n_src; s++) mine += sizes_all[(size_t)s * nb + b];  // only lane 0's copy is used
-    } else if (sub_sizes) {
+      for (uint32_t s = 0; s < n_src; s++) mine += ga.sizes_all[(size_t)s * nb + b];  // only lane 0's copy is used
+    } else if (ga.sub_ptrs) {
+      if (lane < nbins)
+        for (uint32_t s = 0; s < n_src; s++) mine += ga.sub_ptrs[s][((size_t)b << d2) + lane];
+    } else if (ga.sub_sizes) {
       const size_t row = (size_t)(hi - lo) << d2;
       if (lane < nbins)
-        for (uint32_t s = 0; s < n_src; s++) mine += sub_sizes[(size_t)s * row + (((size_t)(b - lo)) << d2) + lane];
+        for (uint32_t s = 0; s < n_src; s++) mine += ga.sub_sizes[(size_t)s * row + (((size_t)(b - lo)) << d2) + lane];
     } else {
       for (uint32_t s = 0; s < n_src; s++) {
-        const uint32_t n = sizes_all[(size_t)s * nb + b];
-        const Elem* src = src_base[s] + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
+        const uint32_t n = ga.sizes_all[(size_t)s * nb + b];
+        const Elem* src = ga.src_base[s] + (ga.seg_off ? ga.seg_off[s] : 0ull) + ga.piece_off[(size_t)s * (nb + 1) + b];
         for (uint32_t i0 = 0; i0 < n; i0 += 32 * U) {
           uint32_t d[U];
 #pragma unroll
@@ -198,17 +213,17 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* const* __restri
       if ((int)lane >= o) incl += v;
     }
     uint32_t cur = incl - mine;        // lane j: next free slot of sub-bucket j
-    const unsigned long long base_b = bofs_coarse[b];
+    const unsigned long long base_b = ga.bofs_coarse[b] - ga.coarse_base;
     if (lane < nbins) {
       const size_t f = ((size_t)b << d2) | lane;
-      bsize_fine[f] = mine;
-      bofs_fine[f] = base_b + cur;
+      ga.bsize_fine[f] = mine;
+      ga.bofs_fine[f] = base_b + cur;
     }
     // ---- place.  32-bit elements are fetched 16 bytes per lane (512 bytes per warp instruction: NVLink
     // and HBM both like long requests); a scalar step first brings the piece to 16-byte alignment.
     for (uint32_t s = 0; s < n_src; s++) {
-      const uint32_t n = sizes_all[(size_t)s * nb + b];
-      const Elem* src = src_base[s] + seg_off[s] + piece_off[(size_t)s * (nb + 1) + b];
+      const uint32_t n = ga.sizes_all[(size_t)s * nb + b];
+      const Elem* src = ga.src_base[s] + (ga.seg_off ? ga.seg_off[s] : 0ull) + ga.piece_off[(size_t)s * (nb + 1) + b];
       uint32_t head = 0;
       if constexpr (sizeof(Elem) == 4) {
         head = (uint32_t)((16u - ((uint32_t)(uintptr_t)src & 15u)) & 15u) >> 2;
@@ -256,6 +271,66 @@ __global__ void __launch_bounds__(NT) k_gather_split(const Elem* const* __restri
       }
     }
   }
+}
+
+// ---------------------------------------------------------------- sharded counting: the plan of an exchange, on the device
+// u64 bucket sizes of this rank's partition -> u32 (what travels in the all-gather); flag |= 1 if one does not fit
+__global__ void k_sizes32(const unsigned long long* __restrict__ in, uint32_t nb, uint32_t* __restrict__ out,
+                          unsigned long long* __restrict__ flag) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const unsigned long long v = in[b];
+  if (v >= (1ull << 31)) { atomicOr(flag, 1ull); out[b] = 0; }
+  else out[b] = (uint32_t)v;
+}
+// merged size of every bucket over the sources; flag |= 2 if one reaches 2^32
+__global__ void k_total_sizes(const uint32_t* __restrict__ sizes_all, uint32_t n_src, uint32_t nb, uint32_t* __restrict__ tot32,
+                              unsigned long long* __restrict__ flag) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  unsigned long long t = 0;
+  for (uint32_t s = 0; s < n_src; s++) t += sizes_all[(size_t)s * nb + b];
+  if (t >= (1ull << 32)) { atomicOr(flag, 2ull); t = 0; }
+  tot32[b] = (uint32_t)t;
+}
+// Balanced contiguous bucket ranges from the exclusive prefix E[nb + 1] of the merged sizes: range r ends after the
+// first bucket whose cumulative count exceeds total * (r + 1) / world (the rule of dist.balanced_splitters).
+// plan[0 .. world] = bounds, plan[world + 1 .. 2 world + 1] = E at the bounds.  One thread per bound.
+__global__ void k_splitters(const unsigned long long* __restrict__ E, uint32_t nb, uint32_t world, unsigned long long* __restrict__ plan) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > world) return;
+  const unsigned long long total = E[nb];
+  uint32_t bound;
+  if (r == 0) bound = 0;
+  else if (r == world) bound = nb;
+  else {
+    // multiply in 128 bits: total * r may exceed 2^64 only beyond 2^60 instances; plain division order keeps it exact enough
+    const unsigned long long target = (unsigned long long)(((unsigned __int128)total * r) / world);
+    // smallest b in [0, nb] with E[b + 1] > target  (E[nb + 1] := infinity)
+    uint32_t lo = 0, hi = nb;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (E[mid + 1] > target) hi = mid; else lo = mid + 1;
+    }
+    bound = lo;
+  }
+  plan[r] = bound;
+  plan[world + 1 + r] = E[bound];
+}
+// out[i] = sum over ranks of in[r][i]  (in-process form of the spectrum all-reduce)
+__global__ void k_sum_ranks(const unsigned long long* const* __restrict__ in, uint32_t n_ranks, uint64_t n, unsigned long long* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long t = 0;
+  for (uint32_t r = 0; r < n_ranks; r++) t += in[r][i];
+  out[i] = t;
+}
+__global__ void k_max_ranks(const unsigned long long* const* __restrict__ in, uint32_t n_ranks, uint64_t n, unsigned long long* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long t = 0;
+  for (uint32_t r = 0; r < n_ranks; r++) t = in[r][i] > t ? in[r][i] : t;
+  out[i] = t;
 }
 
 // ---------------------------------------------------------------- compaction: temp records -> final table
