@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libapgk.so")
 APGK_OK = 0
 E_ARG, E_CUDA, E_NOMEM, E_STATE, E_RANGE = -1, -2, -3, -4, -5
 WANT_SPECTRUM, WANT_COUNTS, ASYNC_INGEST = 1, 2, 4
-N_STAGES = 12
+N_STAGES = 14
 MAX_K = 96
 
 
@@ -20,6 +20,12 @@ class Config(C.Structure):
     _fields_ = [("K", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("prefix_bits", C.c_int32),
                 ("reserve_bases", C.c_uint64), ("max_round_keys", C.c_uint64),
                 ("max_inner_keys", C.c_uint64)]
+
+
+class GroupStats(C.Structure):
+    _fields_ = [("world", C.c_int32), ("n_rounds", C.c_int32), ("n_outer_rounds", C.c_int32), ("prefix_bits", C.c_int32),
+                ("split_bits", C.c_int32), ("peer_exchange", C.c_int32), ("shard_instances", C.c_uint64),
+                ("remote_bytes", C.c_uint64), ("gather_ms", C.c_float), ("step_ms", C.c_float)]
 
 
 class SynthParams(C.Structure):
@@ -74,6 +80,15 @@ SYMBOLS = {
     "apgk_partition_export": (C.c_int, [_vp, _vp]),
     "apgk_peer_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "apgk_peer_close": (C.c_int, [_vp, _vp]),
+    "apgk_group_unique_id": (C.c_int, [_vp]),
+    "apgk_group_join": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "apgk_group_local": (C.c_int, [C.POINTER(_vp), C.c_int32, C.POINTER(_vp)]),
+    "apgk_group_destroy": (None, [_vp]),
+    "apgk_group_last_error": (C.c_char_p, [_vp]),
+    "apgk_group_count": (C.c_int, [_vp]),
+    "apgk_group_totals": (C.c_int, [_vp, _u64p, _u64p]),
+    "apgk_group_spectrum_sparse": (C.c_int, [_vp, C.POINTER(_u64p), C.POINTER(_u64p), _u64p]),
+    "apgk_group_stats_get": (C.c_int, [_vp, C.POINTER(GroupStats)]),
     "apgk_spectrum_device": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
     "apgk_spectrum_reload": (C.c_int, [_vp]),
     "apgk_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),

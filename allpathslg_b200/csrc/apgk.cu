@@ -26,9 +26,11 @@ using namespace apgk;
 namespace {
 
 enum Stage { ST_HIST0, ST_SCAN0, ST_SCATTER0, ST_HIST1, ST_SCAN1, ST_SCATTER1, ST_LOCAL, ST_BIG, ST_TABLE, ST_SPECTRUM,
-             ST_OWNER, ST_TOTAL };
+             ST_OWNER, ST_TOTAL, ST_PLAN, ST_REDUCE };
+// owner = the gather of the sharded form; plan = its all-gather + splitters (includes waiting for slower ranks);
+// reduce = the spectrum all-reduce (ditto)
 const char* kStageNames[APGK_N_STAGES] = {"hist0", "scan0", "scatter0", "hist1", "scan1", "scatter1",
-                                          "local", "big", "table", "spectrum", "owner", "total"};
+                                          "local", "big", "table", "spectrum", "owner", "total", "plan", "reduce"};
 
 struct DevBuf {
   void* p = nullptr;
@@ -74,6 +76,7 @@ struct apgk_ctx {
   DevBuf bases, starts, staging, off_dev;
   uint64_t total_bases = 0, n_reads = 0;
   uint64_t n_windows = 0;            // exact k-mer instances of the store: sum over reads of max(0, L - K + 1)
+  uint64_t n_windows_run = 0;        // instances the current step's level-0 histogram must find (store, or a key array)
   // ---- streamed ingest (APGK_ASYNC_INGEST): copies in flight on copy_stream, one event per slice
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_main = nullptr;
@@ -116,7 +119,8 @@ struct apgk_ctx {
   uint64_t last_cap_keys = 0;               // k-mer instances one round may hold (memory budget of the last run)
   bool part_ready = false;
   uint64_t part_n = 0;       // elements in B, grouped by the nb1 buckets (sizes in segtot)
-  DevBuf piece_off, piece_tmp, piece_ptrs, C2, sub_sizes;
+  DevBuf piece_off, piece_tmp, piece_ptrs, C2, sub_sizes, TK;
+  uint64_t budget_bytes = 0, budget_for = 0;   // temp-buffer budget of the sharded form, and the store size it was asked for
   void* count_src = nullptr;
   uint32_t bucket_lo = 0, bucket_hi = 0;  // shard's bucket range for count_buckets (0,0 = all)  // elements count_buckets reads (B, or C2 on the peer-memory path)
   // ---- owner partition state
@@ -419,11 +423,37 @@ template <int W> int compact_table(apgk_ctx* c, uint64_t total);
 
 // The result block: a few words the kernels of a step leave for the host, fetched with ONE copy at the
 // step's final synchronisation (RES_* index c->res, 16 x u64 on the device, mirrored in pinned host memory).
-enum { RES_RANGE_N = 0, RES_SUM_TOT0 = 1, RES_FLAGS = 2, RES_DISTINCT = 3, RES_TABLE_OVF = 4, RES_WORDS = 16 };
+enum { RES_RANGE_N = 0, RES_SUM_TOT0 = 1, RES_FLAGS = 2, RES_DISTINCT = 3, RES_TABLE_OVF = 4, RES_XFLAGS = 5, RES_WORDS = 16 };
 
 int fetch_results(apgk_ctx* c) {
   CU(cudaMemcpyAsync(c->res_host, c->res.p, RES_WORDS * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return APGK_OK;
+}
+
+// The step's one synchronisation: fetch the result block, check what the kernels flagged, and settle the table
+// of a single-round step that was compacted optimistically into the buffers of the previous step.
+int step_epilogue(apgk_ctx* c, bool full) {
+  { int r2 = fetch_results(c); if (r2) return r2; }
+  if (c->res_host[RES_FLAGS] & 1ull) FAIL(APGK_E_RANGE, "a level-0 bucket holds 2^32 or more k-mers");
+  if (c->res_host[RES_SUM_TOT0] && c->res_host[RES_SUM_TOT0] != c->n_windows_run)
+    FAIL(APGK_E_STATE, "internal: level-0 histogram counts %llu k-mers, the input holds %llu",
+         (unsigned long long)c->res_host[RES_SUM_TOT0], (unsigned long long)c->n_windows_run);
+  if (full && c->table_pending) {
+    c->table_pending = false;
+    const uint64_t total = c->res_host[RES_DISTINCT];
+    if (c->res_host[RES_TABLE_OVF]) {   // it did not fit: grow and compact again (the temp records are still in place)
+      int rc = APGK_E_ARG;
+      switch (c->W) {
+        case 1: rc = compact_table<1>(c, total); break;
+        case 2: rc = compact_table<2>(c, total); break;
+        case 3: rc = compact_table<3>(c, total); break;
+      }
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    c->n_distinct = total;
+  }
   return APGK_OK;
 }
 
@@ -448,27 +478,7 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mo
   c->n_deferred = 0;
   if (mode == RUN_FULL && c->deferred.p && c->n_instances)
     CU(cudaMemcpyAsync(&c->n_deferred, c->deferred.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  { int r2 = fetch_results(c); if (r2) return r2; }   // the step's one synchronisation
-  if (c->res_host[RES_FLAGS] & 1ull) FAIL(APGK_E_RANGE, "a level-0 bucket holds 2^32 or more k-mers");
-  if (c->res_host[RES_SUM_TOT0] && c->res_host[RES_SUM_TOT0] != c->n_instances)
-    FAIL(APGK_E_STATE, "internal: level-0 histogram counts %llu k-mers, the read store holds %llu windows",
-         (unsigned long long)c->res_host[RES_SUM_TOT0], (unsigned long long)c->n_instances);
-  if (mode == RUN_FULL && c->table_pending) {
-    // single-round fast path: the table was compacted optimistically into the buffers of the previous step
-    c->table_pending = false;
-    const uint64_t total = c->res_host[RES_DISTINCT];
-    if (c->res_host[RES_TABLE_OVF]) {   // it did not fit: grow and compact again (the temp records are still in place)
-      rc = APGK_E_ARG;
-      switch (c->W) {
-        case 1: rc = compact_table<1>(c, total); break;
-        case 2: rc = compact_table<2>(c, total); break;
-        case 3: rc = compact_table<3>(c, total); break;
-      }
-      if (rc) return rc;
-      CU(cudaStreamSynchronize(c->stream));
-    }
-    c->n_distinct = total;
-  }
+  { int r2 = step_epilogue(c, mode == RUN_FULL); if (r2) return r2; }   // the step's one synchronisation
   stages_collect(c);
   if (mode == RUN_FULL) c->finished = true;
   else c->part_ready = true;
@@ -732,7 +742,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
   CU(c->out_off.ensure(((size_t)c->nb1 + 1) * 8));
   CU(cudaMemsetAsync(c->out_off.p, 0, ((size_t)c->nb1 + 1) * 8, c->stream));
   const uint64_t N = dev_keys ? n_keys : c->n_windows;   // exact, known before any kernel runs
-  c->n_instances = N;
+  c->n_instances = N; c->n_windows_run = N;
   c->tot0_host.assign((size_t)bins0, 0);
   if (N == 0) {  // nothing to count
     { int rc = wait_ingest(c); if (rc) return rc; }
@@ -1436,16 +1446,21 @@ int count_pieces_typed(apgk_ctx* c, const void* const* bases_host, bool peer, ui
   if (Nr && hi > lo) {
     const uint32_t grid = std::min<uint32_t>((hi - lo + 7) / 8, (uint32_t)c->n_sm * 8);  // one warp per bucket
     // digit = the d2 bits just below the prefix: remainder bits [REM - d2, REM)
-    k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(
-        (const ElemB* const*)c->piece_ptrs.p, c->bstart64.as<unsigned long long>(), c->piece_off.as<unsigned long long>(), d_sizes_all,
-        c->out_off_local.as<unsigned long long>(), n_src, nb, lo, hi, d2, c->geom.REM - d2, (ElemB*)dst.p,
-        c->segtot.as<unsigned long long>(), c->bofs.as<unsigned long long>(), d_sub);
+    GatherArgs<ElemB> ga{};
+    ga.src_base = (const ElemB* const*)c->piece_ptrs.p; ga.seg_off = c->bstart64.as<unsigned long long>();
+    ga.piece_off = c->piece_off.as<unsigned long long>(); ga.sizes_all = d_sizes_all;
+    ga.bofs_coarse = c->out_off_local.as<unsigned long long>(); ga.coarse_base = 0;
+    ga.n_src = n_src; ga.nb = nb; ga.lo = lo; ga.hi = hi; ga.d2 = d2; ga.digit_pos = c->geom.REM - d2;
+    ga.out = (ElemB*)dst.p; ga.bsize_fine = c->segtot.as<unsigned long long>(); ga.bofs_fine = c->bofs.as<unsigned long long>();
+    ga.sub_sizes = d_sub; ga.sub_ptrs = nullptr;
+    k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(ga);
     LAUNCHED();
   }
   stage_end(c, ST_OWNER);
   // from here on the context describes the finer geometry: P + d2 prefix bits
   c->geom.D1 += d2; c->geom.REM -= d2;
   c->nb1 = nbf;
+  c->part_ready = false;   // the partition's geometry is gone: a failed count cannot be retried on it
   c->n_instances = Nr;
   c->n_big = 0;
   uint64_t n_prev = 0;
@@ -1585,6 +1600,8 @@ static void host_extract(const uint8_t* packed, const uint64_t* off, uint64_t n_
 
 }  // namespace
 
+#include "group.cuh"
+
 // ================================================================= C ABI
 extern "C" {
 
@@ -1625,7 +1642,7 @@ void apgk_destroy(apgk_ctx* c) {
   DevBuf* all[] = {&c->tot0_dev, &c->res, &c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum, &c->chunksum0, &c->plan0, &c->out_off_local,
                    &c->segtot, &c->bstart32, &c->bofs, &c->plan, &c->bstart64, &c->nd, &c->out_off, &c->blocksum,
                    &c->big_list, &c->stats, &c->scratch, &c->stacks, &c->spec_dense, &c->spec_ovf, &c->misc, &c->deferred,
-                   &c->out_keys, &c->out_cnt, &c->owner_plan_dev, &c->piece_off, &c->piece_tmp, &c->piece_ptrs, &c->C2, &c->sub_sizes,
+                   &c->out_keys, &c->out_cnt, &c->owner_plan_dev, &c->piece_off, &c->piece_tmp, &c->piece_ptrs, &c->C2, &c->sub_sizes, &c->TK,
                    &c->occ, &c->occ_pos, &c->occ_off, &c->occ_cnt, &c->occ_bstart, &c->occ_bcur, &c->rank_cnt, &c->rank_dir, &c->empty_dev,
                    &c->occ_tmp};
   for (DevBuf* b : all) b->release();
@@ -2223,6 +2240,123 @@ int apgk_host_alloc(void** p, size_t bytes) {
   return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? APGK_OK : APGK_E_NOMEM;
 }
 int apgk_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? APGK_OK : APGK_E_CUDA; }
+
+
+// ---------------------------------------------------------------- groups
+int apgk_group_unique_id(uint8_t id_out[APGK_GROUP_ID_BYTES]) {
+  if (!id_out) return APGK_E_ARG;
+  static_assert(sizeof(ncclUniqueId) == APGK_GROUP_ID_BYTES, "unique id size");
+  if (!g_nccl.load().empty()) return APGK_E_CUDA;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return APGK_E_CUDA;
+  memcpy(id_out, &id, APGK_GROUP_ID_BYTES);
+  return APGK_OK;
+}
+
+static int group_init_rank(apgk_group* g, RankState& r, apgk_ctx* c) {
+  r.c = c;
+  GCU(cudaSetDevice(c->device));
+  GCU(cudaEventCreateWithFlags(&r.ev_a, cudaEventDisableTiming));
+  GCU(cudaEventCreateWithFlags(&r.ev_b, cudaEventDisableTiming));
+  return APGK_OK;
+}
+
+int apgk_group_join(apgk_ctx* ctx, const uint8_t id[APGK_GROUP_ID_BYTES], int32_t rank, int32_t world, apgk_group** out) {
+  if (!ctx || !id || !out || world < 1 || world > 1024 || rank < 0 || rank >= world) return APGK_E_ARG;
+  *out = nullptr;
+  apgk_ctx* c = ctx;
+  const std::string e = g_nccl.load();
+  if (!e.empty()) FAIL(APGK_E_CUDA, "%s", e.c_str());
+  apgk_group* g = new apgk_group();
+  g->world = world; g->n_local = 1; g->rank0 = rank; g->use_nccl = true;
+  g->rs.resize(1);
+  int rc = group_init_rank(g, g->rs[0], ctx);
+  if (rc == APGK_OK) {
+    ncclUniqueId nid;
+    memcpy(&nid, id, APGK_GROUP_ID_BYTES);
+    const ncclResult_t r = g_nccl.CommInitRank(&g->comm, world, nid, rank);
+    if (r != ncclSuccess) { g->err = std::string("ncclCommInitRank failed: ") + g_nccl.GetErrorString(r); rc = APGK_E_CUDA; }
+  }
+  if (rc) { c->err = g->err; apgk_group_destroy(g); return rc; }
+  *out = g;
+  return APGK_OK;
+}
+
+int apgk_group_local(apgk_ctx* const* ctxs, int32_t n, apgk_group** out) {
+  if (!ctxs || !out || n < 1 || n > 1024) return APGK_E_ARG;
+  *out = nullptr;
+  for (int i = 0; i < n; i++) if (!ctxs[i]) return APGK_E_ARG;
+  apgk_group* g = new apgk_group();
+  g->world = n; g->n_local = n; g->rank0 = 0; g->use_nccl = false;
+  g->rs.resize(n);
+  int rc = APGK_OK;
+  for (int i = 0; i < n && rc == APGK_OK; i++) rc = group_init_rank(g, g->rs[i], ctxs[i]);
+  // contexts on different devices read each other's partition buffers directly
+  for (int i = 0; i < n && rc == APGK_OK; i++)
+    for (int j = 0; j < n; j++) {
+      const int di = ctxs[i]->device, dj = ctxs[j]->device;
+      if (di == dj) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, di, dj);
+      if (!can) { g->err = "devices of a single-process group must be peer-accessible"; rc = APGK_E_CUDA; break; }
+      cudaSetDevice(di);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g->err = cudaGetErrorString(e); rc = APGK_E_CUDA; break; }
+      cudaGetLastError();
+    }
+  if (rc) { ctxs[0]->err = g->err; apgk_group_destroy(g); return rc; }
+  *out = g;
+  return APGK_OK;
+}
+
+void apgk_group_destroy(apgk_group* g) {
+  if (!g) return;
+  close_exports(g);
+  for (RankState& r : g->rs) {
+    if (!r.c) continue;
+    cudaSetDevice(r.c->device);
+    cudaStreamSynchronize(r.c->stream);
+    DevBuf* all[] = {&r.sizes32, &r.sizes_all, &r.tot32, &r.E_tot, &r.plan_dev, &r.ptrs_dev, &r.red_in, &r.red_out, &r.ovf_out,
+                     &r.ovf_all, &r.tot0_red, &r.meta_dev, &r.meta_all, &r.bar};
+    for (DevBuf* b : all) b->release();
+    if (r.host) cudaFreeHost(r.host);
+    if (r.ev_a) cudaEventDestroy(r.ev_a);
+    if (r.ev_b) cudaEventDestroy(r.ev_b);
+  }
+  if (g->comm) g_nccl.CommDestroy(g->comm);
+  delete g;
+}
+
+const char* apgk_group_last_error(const apgk_group* g) { return g ? g->err.c_str() : "null group"; }
+
+int apgk_group_count(apgk_group* g) {
+  if (!g) return APGK_E_ARG;
+  return group_count(g);
+}
+
+int apgk_group_totals(const apgk_group* g, uint64_t* n_instances, uint64_t* n_distinct) {
+  if (!g) return APGK_E_ARG;
+  if (!g->counted) return APGK_E_STATE;
+  if (n_instances) *n_instances = g->n_instances;
+  if (n_distinct) *n_distinct = g->n_distinct;
+  return APGK_OK;
+}
+
+int apgk_group_spectrum_sparse(apgk_group* g, const uint64_t** freq, const uint64_t** n_kmers, uint64_t* n) {
+  if (!g) return APGK_E_ARG;
+  if (!g->counted) GFAIL(APGK_E_STATE, "apgk_group_count has not run");
+  if (freq) *freq = g->sparse_f.data();
+  if (n_kmers) *n_kmers = g->sparse_n.data();
+  if (n) *n = g->sparse_f.size();
+  return APGK_OK;
+}
+
+int apgk_group_stats_get(const apgk_group* g, apgk_group_stats* out) {
+  if (!g || !out) return APGK_E_ARG;
+  if (!g->counted) return APGK_E_STATE;
+  *out = g->stats;
+  return APGK_OK;
+}
 
 // ---------------------------------------------------------------- host test hooks
 int apgk_debug_counters(apgk_ctx* c, uint64_t* out8, int reset) {

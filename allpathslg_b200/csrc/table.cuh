@@ -296,7 +296,9 @@ __global__ void k_total_sizes(const uint32_t* __restrict__ sizes_all, uint32_t n
 // Balanced contiguous bucket ranges from the exclusive prefix E[nb + 1] of the merged sizes: range r ends after the
 // first bucket whose cumulative count exceeds total * (r + 1) / world (the rule of dist.balanced_splitters).
 // plan[0 .. world] = bounds, plan[world + 1 .. 2 world + 1] = E at the bounds.  One thread per bound.
-__global__ void k_splitters(const unsigned long long* __restrict__ E, uint32_t nb, uint32_t world, unsigned long long* __restrict__ plan) {
+// plan[2 world + 2 ..] = own[] at the bounds (the calling rank's own prefix: how much of each range it holds itself).
+__global__ void k_splitters(const unsigned long long* __restrict__ E, uint32_t nb, uint32_t world,
+                            const unsigned long long* __restrict__ own, unsigned long long* __restrict__ plan) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > world) return;
   const unsigned long long total = E[nb];
@@ -316,6 +318,7 @@ __global__ void k_splitters(const unsigned long long* __restrict__ E, uint32_t n
   }
   plan[r] = bound;
   plan[world + 1 + r] = E[bound];
+  plan[2 * (world + 1) + r] = own[bound];
 }
 // out[i] = sum over ranks of in[r][i]  (in-process form of the spectrum all-reduce)
 __global__ void k_sum_ranks(const unsigned long long* const* __restrict__ in, uint32_t n_ranks, uint64_t n, unsigned long long* __restrict__ out) {

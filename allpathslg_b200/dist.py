@@ -1,30 +1,17 @@
 """Multi-GPU k-mer spectrum: one process per GPU, sharded by canonical k-mer.
 
-Partition-first form (`sharded_count`, the default).  Every rank runs levels 0 and 1 of the
-single-GPU pipeline on ITS reads (`apgk_partition`): the canonical k-mers end up grouped by their
-leading P bits, as 32-bit remainders when they fit.  The ranks all-gather the bucket histogram,
-cut the bucket space into `world` contiguous ranges of (nearly) equal instance counts
-(`balanced_splitters`), exchange whole ranges with one NCCL all-to-all over NVLink
-(`torch.distributed.all_to_all_single`), and each rank sorts + counts the ranges it owns
-(`apgk_count_pieces`).  The per-rank spectra -- disjoint sets of k-mers, so plain integer sums --
-are all-reduced.  A k-mer's owner depends on the canonical k-mer alone, so counts are final
-without a merge.
+`sharded_count` is a thin caller of the library's group API (include/apgk.h, csrc/group.cuh): every rank runs
+levels 0 and 1 of the single-GPU pipeline on ITS reads, the ranks all-gather the bucket histogram, cut the bucket
+space into `world` contiguous ranges of (nearly) equal instance counts, every rank gathers the ranges it owns
+straight from the peers' partition buffers over NVLink peer memory (the exchange is fused into the gather kernel)
+and sorts + counts them; the per-rank spectra -- disjoint sets of k-mers, so plain integer sums -- are all-reduced.
+A k-mer's owner depends on the canonical k-mer alone, so counts are final without a merge.
+When a rank's k-mers do not fit its device at once the library runs the same pipeline in k-mer-space rounds.
+torch.distributed is used for one thing only: handing rank 0's group id to the other ranks.
 
-K-mer-space rounds (`_sharded_count_rounds`): when a rank's k-mers do not fit the device in one go
-(`apgk_partition` answers APGK_E_RANGE), the ranks all-reduce their level-0 bucket totals, cut the
-level-0 bucket space into the same consecutive ranges everywhere (`plan_rounds`) and run the
-partition-first pipeline once per range (`apgk_partition_range`); a round's spectrum and totals are
-harvested before the next round reuses the buffers, so the context keeps the LAST round's shard table
-only (pass `on_round` to take every round's table).  Ranges ascend in k-mer order: the tables
-concatenated in (round, rank) order are the globally sorted table.
-
-Hash form (`sharded_count_hash`, the first implementation; APGK_SHARD_ROUNDS=0 selects it instead of the
-rounds): owner = hash(k-mer) % world
-(`apgk_owner_plan` / `apgk_owner_scatter`), exchange of full k-mers, then the whole pipeline again
-on the received keys (`apgk_finish_keys_device`).  It extracts and partitions every k-mer twice
-and sends 8 bytes per instance where the partition-first form sends 4.
-
-torch is used for device buffers, streams and the collectives only.
+The rest of this module is the HOST mirror of the exchange (numpy + gloo/nccl all_to_all), which the CPU test-suite
+runs at world size 2 and 3: the same ownership rule (`balanced_splitters`) and the same round planning
+(`plan_rounds`) as the device code, so the host logic of the N-rank path is covered without a GPU.
 """
 import os
 import time
@@ -75,264 +62,52 @@ def plan_rounds(level0_max, capacity):
     return rounds
 
 
-def sharded_count(kc, rank, world, group=None, timings=None, on_round=None):
-    """Run the sharded pipeline on this rank's KmerCounter `kc` (reads already in its store).
+def sharded_count(kc, rank, world, group=None, timings=None):
+    """Run the sharded pipeline on this rank's KmerCounter `kc` (reads already in its store): one call into the
+    library (apgk_group_count); torch.distributed only carries the 128-byte group id once.
 
     Returns (spectrum uint64 array summed over all ranks, n_instances_global, n_distinct_global).
-    The rank's own shard table stays queryable in `kc` (counts of the k-mers it owns); when the k-mers need
-    several k-mer-space rounds that is the last round's shard -- `on_round(kc, i, n_rounds)` is called after
-    every round for callers that want each round's table."""
-    from .kmers import ApgkError
+    The rank's own shard table stays queryable in `kc`: the counts of ALL the k-mers it owns, every k-mer-space
+    round appended."""
+    grp = _group_of(kc, rank, world, group)
+    grp.count()
+    ni, nd = grp.totals()
+    if timings is not None:
+        st = grp.stats()
+        ms = kc.stage_ms()
+        timings.update({k: float(v) for k, v in ms.items() if v})
+        timings["path"] = "partition-first/" + ("peer" if st["peer_exchange"] else "nccl") + ("" if st["n_rounds"] == 1 else "/rounds")
+        timings["n_rounds"] = st["n_rounds"]
+        timings["n_outer_rounds"] = st["n_outer_rounds"]
+        timings["prefix_bits"] = st["prefix_bits"]
+        timings["split_bits"] = st["split_bits"]
+        timings["shard_instances"] = st["shard_instances"]
+        timings["remote_bytes"] = st["remote_bytes"]
+        timings["gather_ms"] = st["gather_ms"]
+        timings["gather_remote_GBps"] = (st["remote_bytes"] / (st["gather_ms"] * 1e-3) / 1e9) if st["gather_ms"] > 0 else 0.0
+        timings["step_ms"] = st["step_ms"]
+    return grp.spectrum(), ni, nd
 
-    dev = torch.device("cuda", torch.cuda.current_device())
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-    e0.record()
-    wall = {}
-    t_last = [time.perf_counter()]
 
-    def lap(name):  # host wall clock of the synchronous phases (diagnostics in `timings`)
-        now = time.perf_counter()
-        wall[name] = wall.get(name, 0.0) + 1e3 * (now - t_last[0])
-        t_last[0] = now
+def _group_of(kc, rank, world, group=None):
+    """The library-side group of this counter (made once: rank 0's id is broadcast over torch.distributed)."""
+    from .kmers import KmerGroup
 
-    # ---- same geometry on every rank
-    up = torch.tensor([kc.window_upper()], dtype=torch.int64, device=dev)
-    dist.all_reduce(up, op=dist.ReduceOp.MAX, group=group)
-    P = kc.choose_prefix_bits(int(up.item()))
-    # ---- local partition (levels 0 + 1)
-    lap("w_geometry")
-    failed = 0
-    try:
-        kc.partition(P)
-    except ApgkError as e:
-        if e.code != -5:  # APGK_E_RANGE: more than one k-mer-space round needed here
-            raise
-        failed = 1
-    lap("w_partition")
-    sizes = None
-    want_peer = world > 1 and os.environ.get("APGK_SHARD_EXCHANGE", "peer") == "peer"
-    handle = np.zeros(64, dtype=np.uint8)
-    if not failed:
-        sizes_ptr, nb, elems_ptr, eb, n_elems = kc.partition_info()
-        sizes = _wrap(sizes_ptr, nb, "<i8", dev)
-        if want_peer:
-            handle = kc.partition_export()
-            d2, sub_ptr = kc.partition_subsizes(max(0, (world - 1).bit_length()))
-    lap("w_subsizes")
-    # one all-gather carries the bucket histogram, the "could not partition" flag and the IPC handle
-    nb_all = 1 << P
-    mine = torch.empty(nb_all + 9, dtype=torch.int64, device=dev)
-    mine[:nb_all] = sizes if sizes is not None else 0
-    mine[nb_all] = failed
-    mine[nb_all + 1:] = torch.from_numpy(handle.view(np.int64).copy()).to(dev)
-    gathered = torch.empty((world, nb_all + 9), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
-    all_sizes = gathered[:, :nb_all]
-    bounds_t = _splitters_tensor(all_sizes.sum(0), world)
-    cum = torch.zeros((world, nb_all + 1), dtype=torch.int64, device=dev)
-    torch.cumsum(all_sizes, 1, out=cum[:, 1:])
-    # everything the host needs in one transfer: flags, largest piece, bounds, cumulative counts at the bounds, handles
-    small = torch.cat([gathered[:, nb_all].max().reshape(1), all_sizes.max().reshape(1), bounds_t,
-                       cum[:, bounds_t].reshape(-1), gathered[:, nb_all + 1:].reshape(-1)]).cpu().numpy()
-    lap("w_plan")
-    if int(small[0]):
-        if os.environ.get("APGK_SHARD_ROUNDS", "1") == "0":
-            if timings is not None:
-                timings["path"] = "hash"
-            return sharded_count_hash(kc, rank, world, group, timings)
-        return _sharded_count_rounds(kc, rank, world, P, dev, group, timings, on_round, want_peer)
-    if int(small[1]) >= 2 ** 31:
-        raise RuntimeError("a bucket piece holds 2^31 or more k-mers")
-    bounds = [int(x) for x in small[2: 3 + world]]
-    at_bounds = small[3 + world: 3 + world + world * (world + 1)].reshape(world, world + 1)
-    handles = small[3 + world + world * (world + 1):].reshape(world, 8)
-    lo, hi = bounds[rank], bounds[rank + 1]
-    sizes_u32 = all_sizes.to(torch.int32).contiguous()
-    # ---- exchange fused into the gather: map the peers' partition buffers (CUDA IPC over NVLink)
-    peer_ptrs = None
-    if want_peer:
-        peer_ptrs = _open_peers(kc, rank, world, handles)
-        ok = torch.tensor([1 if peer_ptrs is not None else 0], dtype=torch.int64, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # every rank or none
-        if not int(ok.item()):
-            peer_ptrs = None
-    if peer_ptrs is not None:
-        e1.record()
-        e2.record()
-        torch.cuda.current_stream().synchronize()
-        n_recv = int((at_bounds[:, rank + 1] - at_bounds[:, rank]).sum())
-        # the senders' sub-bucket counts of my range (so that the pieces cross NVLink once)
-        sub = _wrap(sub_ptr, nb_all << d2, "<i4", dev)
-        sub_recv = torch.empty(world * ((hi - lo) << d2) + 1, dtype=torch.int32, device=dev)
-        dist.all_to_all_single(sub_recv[: world * ((hi - lo) << d2)], sub,
-                               output_split_sizes=[(hi - lo) << d2] * world,
-                               input_split_sizes=[(bounds[r + 1] - bounds[r]) << d2 for r in range(world)], group=group)
-        torch.cuda.current_stream().synchronize()
-        lap("w_peer_setup")
-        kc.count_pieces_peer(peer_ptrs, sizes_u32.data_ptr(), at_bounds[:, rank].astype(np.uint64), lo, hi,
-                             split_bits=d2, d_sub_sizes=sub_recv.data_ptr())
-        lap("w_count")
-        e3.record()
+    grp = getattr(kc, "_group", None)
+    if grp is not None and grp._h:
+        return grp
+    if world == 1:
+        grp = KmerGroup.local([kc])
     else:
-        # ---- NCCL all-to-all into a receive buffer, then gather
-        # per-destination send counts (my pieces) and per-source receive counts (their pieces of my range)
-        send_counts = (at_bounds[rank, 1:] - at_bounds[rank, :-1]).astype(np.int64)
-        recv_counts = (at_bounds[:, rank + 1] - at_bounds[:, rank]).astype(np.int64)
-        n_recv = int(recv_counts.sum())
-        words = 1 if eb == 4 else eb // 8
-        tstr, tdt = ("<i4", torch.int32) if eb == 4 else ("<i8", torch.int64)
-        send = _wrap(elems_ptr, max(n_elems, 1) * words, tstr, dev) if elems_ptr else torch.empty(1, dtype=tdt, device=dev)
-        need = max(n_recv, 1) * eb
-        buf = getattr(kc, "_recv_buf", None)
-        if buf is None or buf.numel() * 8 < need:
-            kc._recv_buf = None
-            del buf
-            torch.cuda.empty_cache()
-            buf = torch.empty(int(need * 1.02) // 8 + 1024, dtype=torch.int64, device=dev)
-            kc._recv_buf = buf
-        recv = buf.view(tdt)
-        e1.record()
-        dist.all_to_all_single(recv[: n_recv * words], send[: n_elems * words],
-                               output_split_sizes=[int(c) * words for c in recv_counts],
-                               input_split_sizes=[int(c) * words for c in send_counts], group=group)
-        e2.record()
-        torch.cuda.current_stream().synchronize()
-        del send
-        seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
-        lap("w_all_to_all")
-        kc.count_pieces(recv.data_ptr(), world, sizes_u32.data_ptr(), seg_off, lo, hi)
-        lap("w_count")
-        e3.record()
-    gather_ms = kc.stage_ms().get("owner", 0.0)
-    if on_round is not None:
-        on_round(kc, 0, 1)
-    out = _reduce_results(kc, dev, group)
-    lap("w_reduce")
-    if timings is not None:
-        torch.cuda.current_stream().synchronize()
-        timings.update(wall)
-        timings["gather_split_ms"] = gather_ms
-        timings["path"] = "partition-first" + ("/peer" if peer_ptrs is not None else "/nccl")
-        timings["partition_ms"] = e0.elapsed_time(e1)
-        timings["all_to_all_ms"] = e1.elapsed_time(e2)
-        timings["count_ms"] = e2.elapsed_time(e3)
-        timings["sent_elems"] = int(n_elems)
-        timings["recv_elems"] = n_recv
-        timings["elem_bytes"] = int(eb)
-        timings["bucket_range"] = (int(lo), int(hi))
-        timings["prefix_bits"] = int(P)
-    return out
-
-
-def _exchange_and_count(kc, rank, world, P, dev, group, want_peer):
-    """One partition-first exchange for the partition `kc` holds: all-gather of the bucket histograms, balanced
-    ranges, the owned range gathered from the peers' buffers (or through an all-to-all) and counted.
-    -> (bucket_lo, bucket_hi, path)."""
-    sizes_ptr, nb, elems_ptr, eb, n_elems = kc.partition_info()
-    sizes = _wrap(sizes_ptr, nb, "<i8", dev)
-    handle = np.zeros(64, dtype=np.uint8)
-    d2 = sub_ptr = None
-    if want_peer:
-        handle = kc.partition_export()
-        d2, sub_ptr = kc.partition_subsizes(max(0, (world - 1).bit_length()))
-    nb_all = 1 << P
-    mine = torch.empty(nb_all + 8, dtype=torch.int64, device=dev)
-    mine[:nb_all] = sizes
-    mine[nb_all:] = torch.from_numpy(handle.view(np.int64).copy()).to(dev)
-    gathered = torch.empty((world, nb_all + 8), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
-    all_sizes = gathered[:, :nb_all]
-    bounds_t = _splitters_tensor(all_sizes.sum(0), world)
-    cum = torch.zeros((world, nb_all + 1), dtype=torch.int64, device=dev)
-    torch.cumsum(all_sizes, 1, out=cum[:, 1:])
-    small = torch.cat([all_sizes.max().reshape(1), bounds_t, cum[:, bounds_t].reshape(-1),
-                       gathered[:, nb_all:].reshape(-1)]).cpu().numpy()
-    if int(small[0]) >= 2 ** 31:
-        raise RuntimeError("a bucket piece holds 2^31 or more k-mers")
-    bounds = [int(x) for x in small[1: 2 + world]]
-    at_bounds = small[2 + world: 2 + world + world * (world + 1)].reshape(world, world + 1)
-    handles = small[2 + world + world * (world + 1):].reshape(world, 8)
-    lo, hi = bounds[rank], bounds[rank + 1]
-    sizes_u32 = all_sizes.to(torch.int32).contiguous()
-    peer_ptrs = None
-    if want_peer:
-        peer_ptrs = _open_peers(kc, rank, world, handles)
-        ok = torch.tensor([1 if peer_ptrs is not None else 0], dtype=torch.int64, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if not int(ok.item()):
-            peer_ptrs = None
-    if peer_ptrs is not None:
-        sub = _wrap(sub_ptr, nb_all << d2, "<i4", dev)
-        sub_recv = torch.empty(world * ((hi - lo) << d2) + 1, dtype=torch.int32, device=dev)
-        dist.all_to_all_single(sub_recv[: world * ((hi - lo) << d2)], sub,
-                               output_split_sizes=[(hi - lo) << d2] * world,
-                               input_split_sizes=[(bounds[r + 1] - bounds[r]) << d2 for r in range(world)], group=group)
-        torch.cuda.current_stream().synchronize()
-        kc.count_pieces_peer(peer_ptrs, sizes_u32.data_ptr(), at_bounds[:, rank].astype(np.uint64), lo, hi,
-                             split_bits=d2, d_sub_sizes=sub_recv.data_ptr())
-        return lo, hi, "peer"
-    send_counts = (at_bounds[rank, 1:] - at_bounds[rank, :-1]).astype(np.int64)
-    recv_counts = (at_bounds[:, rank + 1] - at_bounds[:, rank]).astype(np.int64)
-    n_recv = int(recv_counts.sum())
-    words = 1 if eb == 4 else eb // 8
-    tstr, tdt = ("<i4", torch.int32) if eb == 4 else ("<i8", torch.int64)
-    send = _wrap(elems_ptr, max(n_elems, 1) * words, tstr, dev) if elems_ptr else torch.empty(1, dtype=tdt, device=dev)
-    need = max(n_recv, 1) * eb
-    buf = getattr(kc, "_recv_buf", None)
-    if buf is None or buf.numel() * 8 < need:
-        kc._recv_buf = None
-        del buf
-        torch.cuda.empty_cache()
-        buf = torch.empty(int(need * 1.02) // 8 + 1024, dtype=torch.int64, device=dev)
-        kc._recv_buf = buf
-    recv = buf.view(tdt)
-    dist.all_to_all_single(recv[: n_recv * words], send[: n_elems * words],
-                           output_split_sizes=[int(c) * words for c in recv_counts],
-                           input_split_sizes=[int(c) * words for c in send_counts], group=group)
-    torch.cuda.current_stream().synchronize()
-    del send
-    seg_off = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
-    kc.count_pieces(recv.data_ptr(), world, sizes_u32.data_ptr(), seg_off, lo, hi)
-    return lo, hi, "nccl"
-
-
-def _sharded_count_rounds(kc, rank, world, P, dev, group, timings, on_round, want_peer):
-    """The partition-first pipeline in k-mer-space rounds (see the module docstring)."""
-    tot0, cap = kc.level0_totals()
-    t = torch.from_numpy(np.concatenate([tot0.astype(np.int64), [-(cap if cap else 2 ** 62)]])).to(dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)   # per bucket: the largest share; smallest capacity (as -cap)
-    t = t.cpu().numpy()
-    cap_all = int(-t[-1])
-    forced = int(os.environ.get("APGK_SHARD_ROUND_KEYS", "0"))
-    # a round holds this rank's partition AND the shard it receives (about the same size): half the budget each
-    capacity = forced if forced > 0 else max(1, cap_all // 2)
-    rounds = plan_rounds(t[:-1], capacity)
-    spec = {}
-    ni = nd = 0
-    path = "?"
-    ranges = []
-    for i, (lo0, hi0) in enumerate(rounds):
-        kc.partition_range(P, lo0, hi0)
-        blo, bhi, path = _exchange_and_count(kc, rank, world, P, dev, group, want_peer)
-        ranges.append((blo, bhi))
-        a, b = kc.totals()
-        ni += a
-        nd += b
-        f, m = kc.spectrum_sparse()
-        for x, y in zip(f.tolist(), m.tolist()):
-            spec[x] = spec.get(x, 0) + y
-        if on_round is not None:
-            on_round(kc, i, len(rounds))
-        dist.barrier(group=group)   # the peers are done reading this round's partition buffers
-    out, ni_g, nd_g = merge_sparse_spectra(spec, ni, nd, world, dev, group)
-    if timings is not None:
-        timings["path"] = "partition-first/rounds/" + path
-        timings["n_rounds"] = len(rounds)
-        timings["prefix_bits"] = int(P)
-        timings["level0_rounds"] = [tuple(r) for r in rounds]
-        timings["bucket_ranges"] = ranges
-    return out, ni_g, nd_g
+        uid = KmerGroup.unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
+        t = torch.from_numpy(uid.copy())
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(t, src=src, group=group)
+        grp = KmerGroup.join(kc, t.cpu().numpy(), rank, world)
+    kc._group = grp
+    return grp
 
 
 def merge_sparse_spectra(spec, ni, nd, world, dev, group=None):
@@ -364,105 +139,6 @@ def merge_sparse_spectra(spec, ni, nd, world, dev, group=None):
     for x, y in far.items():
         out[x] = y
     return out, int(dense[DENSE]), int(dense[DENSE + 1])
-
-
-def _open_peers(kc, rank, world, handles):
-    """Device pointers of every rank's partition buffer (None for this rank's own), mapping the peers'
-    IPC handles once and again only when a peer reallocated.  None if a handle cannot be mapped."""
-    from .kmers import ApgkError
-
-    cache = getattr(kc, "_peer_map", None)
-    if cache is None:
-        cache = kc._peer_map = {}
-    ptrs = []
-    for s in range(world):
-        if s == rank:
-            ptrs.append(None)
-            continue
-        key = handles[s].tobytes()
-        ent = cache.get(s)
-        if ent is None or ent[0] != key:
-            try:
-                if ent is not None:
-                    kc.peer_close(ent[1])
-                    del cache[s]
-                ptr = kc.peer_open(np.frombuffer(key, dtype=np.uint8))
-            except ApgkError:
-                return None
-            cache[s] = (key, ptr)
-        ptrs.append(cache[s][1])
-    return ptrs
-
-
-def _reduce_results(kc, dev, group):
-    """sum the dense spectra (and the totals, in the same all-reduce) on the device; the library then
-    reloads its host copy of the spectrum"""
-    ptr, n = kc.spectrum_device()
-    spec = _wrap(ptr, n, "<i8", dev)
-    ni, nd = kc.totals()
-    both = torch.cat([spec, torch.tensor([ni, nd], dtype=torch.int64, device=dev)])
-    dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
-    spec.copy_(both[:n])
-    tot = both[n:].cpu()
-    kc.spectrum_reload()
-    return kc.spectrum(), int(tot[0]), int(tot[1])
-
-
-def exchange_plan(send_counts, world, group=None, device=None):
-    """All ranks learn how many k-mers they receive from every peer.
-    send_counts: uint64[world] (k-mers this rank sends to each owner) -> recv_counts int64[world]."""
-    t_send = torch.as_tensor(np.asarray(send_counts, dtype=np.int64), device=device)
-    t_recv = torch.empty(world, dtype=torch.int64, device=device)
-    dist.all_to_all_single(t_recv, t_send, group=group)
-    return t_recv.cpu().numpy()
-
-
-def sharded_count_hash(kc, rank, world, group=None, timings=None):
-    """Hash-owner form of the sharded pipeline (see the module docstring); same contract as sharded_count."""
-    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-    W = kc.W
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    e0, e1, e2 = ev(), ev(), ev()
-    e0.record()
-    send_counts = kc.owner_plan(world)
-    n_send = int(send_counts.sum())
-    # send buffer = the library's own level-0 key buffer (it is rewritten by the count below anyway);
-    # receive buffer = one torch tensor kept on the counter and reused from step to step
-    send = _wrap_u64(kc.key_buffer(n_send), max(n_send, 1) * W, dev)
-    kc.owner_scatter(send.data_ptr())  # synchronous: the library's stream is drained on return
-    recv_counts = exchange_plan(send_counts, world, group, dev)
-    n_recv = int(recv_counts.sum())
-    recv = getattr(kc, "_recv_buf", None)
-    if recv is None or recv.numel() < n_recv * W:
-        kc._recv_buf = None
-        del recv
-        torch.cuda.empty_cache()
-        recv = torch.empty(int(max(n_recv, 1) * W * 1.02) + 1024, dtype=torch.int64, device=dev)
-        kc._recv_buf = recv
-    e1.record()
-    dist.all_to_all_single(recv[: n_recv * W], send[: n_send * W],
-                           output_split_sizes=[int(c) * W for c in recv_counts],
-                           input_split_sizes=[int(c) * W for c in send_counts], group=group)
-    e2.record()
-    torch.cuda.current_stream().synchronize()
-    del send
-    kc.finish_keys_device(recv.data_ptr(), n_recv)
-    # sum the dense spectra in place on the device, then reload on the host side of the library
-    ptr, n = kc.spectrum_device()
-    spec = _wrap_u64(ptr, n, dev)
-    dist.all_reduce(spec, op=dist.ReduceOp.SUM, group=group)
-    torch.cuda.current_stream().synchronize()
-    kc.spectrum_reload()
-    ni, nd = kc.totals()
-    tot = torch.tensor([ni, nd], dtype=torch.int64, device=dev)
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    if timings is not None:
-        timings.setdefault("path", "hash")
-        timings["owner_ms"] = e0.elapsed_time(e1)
-        timings["all_to_all_ms"] = e1.elapsed_time(e2)
-        timings["sent_kmers"] = n_send
-        timings["recv_kmers"] = n_recv
-    return kc.spectrum(), int(tot[0].item()), int(tot[1].item())
 
 
 class _CudaArray:

@@ -342,6 +342,95 @@ class KmerCounter:
                     n_rounds=g[7])
 
 
+class KmerGroup:
+    """A group of ranks counting one read set sharded by canonical k-mer (include/apgk.h "a GROUP of ranks").
+    `KmerGroup.local([kc0, kc1, ...])`: one process drives all the contexts; `KmerGroup.join(kc, uid, rank, world)`:
+    one process per GPU, uid = KmerGroup.unique_id() made on rank 0 and handed to every rank by the caller."""
+
+    def __init__(self, handle, counters):
+        self._L = _lib.lib()
+        self._h = handle
+        self.counters = list(counters)
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        rc = _lib.lib().apgk_group_unique_id(buf.ctypes.data)
+        if rc != 0:
+            raise ApgkError(rc, "apgk_group_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf
+
+    @classmethod
+    def join(cls, kc, uid, rank, world):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert uid.size == 128
+        h = C.c_void_p()
+        rc = _lib.lib().apgk_group_join(kc._h, uid.ctypes.data, rank, world, C.byref(h))
+        if rc != 0:
+            raise ApgkError(rc, kc._L.apgk_last_error(kc._h).decode())
+        return cls(h, [kc])
+
+    @classmethod
+    def local(cls, counters):
+        arr = (C.c_void_p * len(counters))(*[kc._h for kc in counters])
+        h = C.c_void_p()
+        rc = _lib.lib().apgk_group_local(arr, len(counters), C.byref(h))
+        if rc != 0:
+            raise ApgkError(rc, counters[0]._L.apgk_last_error(counters[0]._h).decode())
+        return cls(h, counters)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise ApgkError(rc, self._L.apgk_group_last_error(self._h).decode())
+
+    def count(self):
+        """The sharded hot path over the read stores the contexts hold now (collective)."""
+        self._ck(self._L.apgk_group_count(self._h))
+        return self
+
+    def totals(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.apgk_group_totals(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def spectrum_sparse(self):
+        f, m, n = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)(), C.c_uint64()
+        self._ck(self._L.apgk_group_spectrum_sparse(self._h, C.byref(f), C.byref(m), C.byref(n)))
+        k = n.value
+        if not k:
+            return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+        return (np.ctypeslib.as_array(f, shape=(k,)).copy(), np.ctypeslib.as_array(m, shape=(k,)).copy())
+
+    def spectrum(self):
+        """dense global spectrum: index = frequency"""
+        f, m = self.spectrum_sparse()
+        out = np.zeros(int(f[-1]) + 1 if len(f) else 1, dtype=np.uint64)
+        out[f.astype(np.int64)] = m
+        return out
+
+    def stats(self):
+        st = _lib.GroupStats()
+        self._ck(self._L.apgk_group_stats_get(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.apgk_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def owner_of(K, kmers, n_ranks):
     q = np.ascontiguousarray(kmers, dtype=np.uint64)
     n = q.size // words_per_kmer(K)

@@ -403,16 +403,16 @@ def run_ours(args):
     # ---------------- roofline of the dominant kernel (algorithmic bytes)
     peak, peak_kind = measured_peaks()
     eb = geo["elem_bytes"]
+    n_part = READS_PER_GPU * (READ_LEN - K + 1)   # instances this rank partitions (n_local: instances of the shard it counts)
     alg_bytes = {
-        "hist0": n_local * 8.0 if world > 1 else total_bases * 0.375,
-        "scatter0": n_local * 16.0 if world > 1 else total_bases * 0.375 + n_local * 8.0,
-        "hist1": n_local * 8.0,
-        "scatter1": n_local * (8.0 + eb),
+        "hist0": total_bases * 0.375,
+        "scatter0": total_bases * 0.375 + n_part * 8.0,
+        "hist1": n_part * 8.0,
+        "scatter1": n_part * (8.0 + eb),
         "local": n_local * float(eb) + nd_local * 12.0,
         "table": nd_local * 24.0,
     }
-    kern_names = {"hist0": "k_hist_keys" if world > 1 else "k_hist_reads",
-                  "scatter0": "k_scatter_keys(level 0)" if world > 1 else "k_scatter_reads", "hist1": "k_hist_keys",
+    kern_names = {"hist0": "k_hist_reads", "scatter0": "k_scatter_reads", "hist1": "k_hist_keys",
                   "scatter1": "k_scatter_keys", "local": "k_local3", "table": "k_compact(+scan)"}
     dom = max(alg_bytes, key=lambda s: stage_ms.get(s, 0.0))
     dom_ms = stage_ms.get(dom, 0.0)

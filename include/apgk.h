@@ -249,8 +249,46 @@ int apgk_partition_export(apgk_ctx* ctx, uint8_t handle_out[64]);
 int apgk_peer_open(apgk_ctx* ctx, const uint8_t handle[64], void** d_ptr);
 int apgk_peer_close(apgk_ctx* ctx, void* d_ptr);
 
+/* ---- sharded counting behind the C ABI: a GROUP of ranks, one context (one GPU) each.
+ * This is SURVEY.md section 8(e) / BASELINE.json's "k-mers are partitioned by canonical k-mer ... each rank sorts and
+ * counts its own shard, and the per-rank spectra are summed" as ONE call: apgk_group_count runs, on every rank,
+ * levels 0 + 1 over the rank's read store, the all-gather of the bucket histograms, the balanced bucket ranges, the
+ * exchange fused into the gather kernel over NVLink peer memory, the per-bucket counting of the owned range and
+ * the spectrum all-reduce -- in k-mer-space rounds when a rank's k-mers do not fit its device at once (every
+ * round's shard table is appended, so each context ends up with the table of ALL the k-mers it owns).
+ * Two ways to form a group:
+ *   multi-process (one process per GPU, e.g. under mpirun / torchrun): rank 0 calls apgk_group_unique_id, the host
+ *     program hands the 128 bytes to every rank by its own means, every rank calls apgk_group_join.  The small
+ *     collectives use NCCL (libnccl.so.2 is loaded on first use); the partition buffers are mapped with CUDA IPC.
+ *   single process (one host thread drives all GPUs, as an ALLPATHS-LG module would): apgk_group_local over
+ *     contexts created on different devices (or, for tests, on one device); no NCCL is involved.
+ * All group calls are collective: every rank (every process of the multi-process form) must make them in the
+ * same order.  A group borrows its contexts: destroy the group first. */
+typedef struct apgk_group apgk_group;
+#define APGK_GROUP_ID_BYTES 128
+int apgk_group_unique_id(uint8_t id_out[APGK_GROUP_ID_BYTES]);
+int apgk_group_join(apgk_ctx* ctx, const uint8_t id[APGK_GROUP_ID_BYTES], int32_t rank, int32_t world, apgk_group** out);
+int apgk_group_local(apgk_ctx* const* ctxs, int32_t n, apgk_group** out);
+void apgk_group_destroy(apgk_group* g);
+const char* apgk_group_last_error(const apgk_group* g);
+/* The sharded hot path over the read stores the group's contexts hold now.  Afterwards every context answers
+ * apgk_totals / apgk_counts_* / apgk_lookup / apgk_prefix_range for the k-mers it owns, and the group the
+ * global results below (identical on every rank). */
+int apgk_group_count(apgk_group* g);
+int apgk_group_totals(const apgk_group* g, uint64_t* n_instances, uint64_t* n_distinct);
+/* Global spectrum, sparse form as apgk_spectrum_sparse (library-owned until the next apgk_group_count). */
+int apgk_group_spectrum_sparse(apgk_group* g, const uint64_t** freq, const uint64_t** n_kmers, uint64_t* n);
+typedef struct {
+  int32_t world, n_rounds, n_outer_rounds, prefix_bits, split_bits, peer_exchange; /* peer_exchange: 1 = gather over peer memory */
+  uint64_t shard_instances;   /* k-mer instances this rank (the group's first local context) counted */
+  uint64_t remote_bytes;      /* bytes its gather kernels read from the peers (NVLink) */
+  float gather_ms;            /* device time of those kernels */
+  float step_ms;              /* device time of the whole call on that context's stream */
+} apgk_group_stats;
+int apgk_group_stats_get(const apgk_group* g, apgk_group_stats* out);
+
 /* ---- instrumentation */
-#define APGK_N_STAGES 12
+#define APGK_N_STAGES 14
 /* Device milliseconds of the last finish, by stage; names via apgk_stage_name(i). */
 int apgk_stage_ms(const apgk_ctx* ctx, float* ms_out /* [APGK_N_STAGES] */);
 const char* apgk_stage_name(int i);
