@@ -54,6 +54,8 @@ SYMBOLS = {
     "apgk_spectrum_sparse": (C.c_int, [_vp, C.POINTER(_u64p), C.POINTER(_u64p), _u64p]),
     "apgk_counts_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
     "apgk_counts_copy": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "apgk_reserve_table": (C.c_int, [_vp, C.c_uint64]),
+    "apgk_release_temp": (C.c_int, [_vp]),
     "apgk_prefix_range": (C.c_int, [_vp, C.c_int32, C.c_uint64, _u64p, _u64p]),
     "apgk_lookup": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp]),
     "apgk_read_freqs": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),

@@ -2009,6 +2009,37 @@ int apgk_counts_copy(apgk_ctx* c, uint64_t first, uint64_t n, uint64_t* kmers_ou
   return APGK_OK;
 }
 
+int apgk_release_temp(apgk_ctx* c) {
+  if (!c) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  { int rc = wait_ingest(c); if (rc) return rc; }
+  CU(cudaStreamSynchronize(c->stream));
+  // B and sub_sizes stay: the peers of a group may have them mapped
+  DevBuf* tmp[] = {&c->A, &c->T, &c->C2, &c->TK, &c->scratch, &c->stacks, &c->chunksum, &c->chunksum0, &c->piece_off, &c->piece_tmp,
+                   &c->occ, &c->occ_pos, &c->occ_tmp, &c->staging};
+  for (DevBuf* b : tmp) b->release();
+  c->hp0_elems = ~0ull;            // the level-0 plan's chunk rows went with chunksum0
+  c->have_occ = false; c->n_occ = 0;
+  c->part_ready = false; c->part_n = 0;
+  c->tmp_keys_last = nullptr;
+  return APGK_OK;
+}
+
+int apgk_reserve_table(apgk_ctx* c, uint64_t n_records) {
+  if (!c) return APGK_E_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  const size_t kb = (size_t)c->W * 8;
+  if (c->out_keys.cap < n_records * kb || c->out_cnt.cap < n_records * 4) {
+    // the table's present contents are not kept: this is a sizing hint given before a count
+    c->out_keys.release(); c->out_cnt.release();
+    CU(c->out_keys.ensure(std::max<size_t>(n_records, 1) * kb));
+    CU(c->out_cnt.ensure(std::max<size_t>(n_records, 1) * 4));
+    c->have_table = false;
+  }
+  return APGK_OK;
+}
+
 int apgk_prefix_range(apgk_ctx* c, int32_t prefix_bits, uint64_t prefix, uint64_t* first, uint64_t* n) {
   if (!c || !first || !n) return APGK_E_ARG;
   if (!c->finished || !c->have_table) FAIL(APGK_E_STATE, "no table: finish with APGK_WANT_COUNTS first");

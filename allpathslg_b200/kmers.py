@@ -151,6 +151,12 @@ class KmerCounter:
         self._ck(self._L.apgk_counts_copy(self._h, first, n, k.ctypes.data, c.ctypes.data))
         return k[:n], c[:n]
 
+    def release_temp(self):
+        self._ck(self._L.apgk_release_temp(self._h))
+
+    def reserve_table(self, n_records):
+        self._ck(self._L.apgk_reserve_table(self._h, n_records))
+
     def prefix_range(self, prefix_bits, prefix):
         """(first, n): the table records whose k-mers start with the `prefix_bits`-bit value `prefix`."""
         a, b = C.c_uint64(), C.c_uint64()

@@ -46,6 +46,7 @@ CPU_SAMPLE_READS = int(os.environ.get("APGK_BENCH_CPU_READS", 10_000_000))
 # the CPU arm's sample keeps the workload's coverage (60x): 10 M reads of a 16.7 Mb genome, the same at every N
 CPU_SAMPLE_GENOME = max(READ_LEN, GENOME_PER_GPU * CPU_SAMPLE_READS // READS_PER_GPU)
 PARITY_PBITS, PARITY_PARTS = 8, (5, 77, 130, 201)   # sampled-partition oracle check: 4 of 256 leading-bit partitions
+WORKLOAD = "celegans"
 B_ALG_K25 = 136.0  # 8 * (2*7 + 3) bytes per instance for the 7-pass LSD model
 
 
@@ -187,10 +188,15 @@ def cpu_sample_text(n_inst):
 
 
 def workload_config(n_gpus):
-    return {"workload": "synthetic %d Mb genome, %d M x %d bp reads (%dx) per GPU, K=%d: spectrum to the host + sorted "
-                        "(k-mer, count) table resident on the device (what the frequency-table lookups read)"
-                        % (GENOME_PER_GPU // 1_000_000, READS_PER_GPU // 1_000_000, READ_LEN,
-                           READS_PER_GPU * READ_LEN // GENOME_PER_GPU, K),
+    if WORKLOAD == "human":
+        what = ("BASELINE configs[3]: synthetic human-size %.1f Gb genome at %dx, %d M x %d bp reads split over %d GPUs, K=%d"
+                % (GENOME_PER_GPU * n_gpus / 1e9, READS_PER_GPU * READ_LEN // GENOME_PER_GPU, READS_PER_GPU * n_gpus // 1_000_000,
+                   READ_LEN, n_gpus, K))
+    else:
+        what = ("synthetic %d Mb genome, %d M x %d bp reads (%dx) per GPU, K=%d"
+                % (GENOME_PER_GPU // 1_000_000, READS_PER_GPU // 1_000_000, READ_LEN, READS_PER_GPU * READ_LEN // GENOME_PER_GPU, K))
+    return {"workload": what + ": spectrum to the host + sorted (k-mer, count) table resident on the device "
+                        "(what the frequency-table lookups read)",
             "K": K, "reads_per_gpu": READS_PER_GPU, "read_len": READ_LEN, "genome_len": GENOME_PER_GPU * n_gpus,
             "sharding": ("canonical k-mer prefix ranges over %d ranks (balanced splitters), one exchange fused into "
                          "the gather kernel over NVLink peer memory" % n_gpus) if n_gpus > 1 else "single GPU",
@@ -282,6 +288,8 @@ def run_ours(args):
                      async_ingest=True)  # e2e: the level-0 histogram follows the H2D copy slice by slice
     kc.synth_reads(sp, rank * READS_PER_GPU, READS_PER_GPU)
     total_bases, _ = kc.read_store_info()
+    if WORKLOAD == "human":   # the shard table grows round by round: give it its room up front
+        kc.reserve_table(int(READS_PER_GPU * (READ_LEN - K + 1) * 0.21) + (1 << 20))
 
     def barrier():
         if dist is not None:
@@ -455,7 +463,7 @@ def run_ours(args):
         "timing": "host clock between barrier + cuda synchronize on both sides (max over ranks); device_ms_per_step and "
                   "roofline.stages are CUDA-event intervals on the library's own stream",
         "device_ms_per_step": round(stage_ms.get("total", 0.0), 3) if world == 1 else None,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if WORKLOAD == "human" else "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(n_gpus),
         "e2e": {"value": round(e2e_val, 3), "unit": "Gk-mers/s", "h2d_bytes_per_step": int(nbytes) * n_gpus,
                 "d2h_bytes_per_step": int(spec_bytes) * n_gpus, "steps": e2e_steps,
@@ -500,7 +508,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="celegans", choices=["celegans", "human"],
+                    help="celegans: BASELINE configs[2] per GPU (weak scaling, the default); human: configs[3], the 3 Gb x 45x "
+                         "read set split over the GPUs (k-mer-space rounds; meant for --gpus 8)")
     args = ap.parse_args()
+    if args.workload == "human":
+        global READS_PER_GPU, GENOME_PER_GPU, CPU_SAMPLE_GENOME, WORKLOAD
+        world = max(1, int(os.environ.get("WORLD_SIZE", args.gpus)))
+        WORKLOAD = "human"
+        READS_PER_GPU = (1_350_000_000 // world) // 8 * 8
+        GENOME_PER_GPU = 3_000_000_000 // world
+        CPU_SAMPLE_GENOME = max(READ_LEN, int(3_000_000_000 * (CPU_SAMPLE_READS / 1_350_000_000)))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -127,6 +127,14 @@ int apgk_counts_device(apgk_ctx* ctx, const uint64_t** d_kmers, const uint32_t**
 /* Copy records [first, first+n) of the table to host buffers (either may be NULL). */
 int apgk_counts_copy(apgk_ctx* ctx, uint64_t first, uint64_t n, uint64_t* kmers_out, uint32_t* counts_out);
 
+/* Give the scratch buffers of the pipeline back to the device (the k-mers of the partition levels, temp records,
+ * occurrence records): the read store, the result table with its index and the spectrum stay, so lookups keep
+ * working; the next count allocates again. */
+int apgk_release_temp(apgk_ctx* ctx);
+/* Sizing hint, before a count: room for n_records (k-mer, count) records, so that a table that grows round by
+ * round is never reallocated (a reallocation copies it and needs both copies for a moment).  Discards a
+ * smaller table. */
+int apgk_reserve_table(apgk_ctx* ctx, uint64_t n_records);
 /* Records [*first, *first + *n) of the sorted table are exactly the k-mers whose leading prefix_bits bits equal
  * `prefix` (one parcel of k-mer space; read off the table's prefix index).  prefix_bits <= D0 + D1 of
  * apgk_geometry.  On a shard context only the k-mers the shard owns are there. */
