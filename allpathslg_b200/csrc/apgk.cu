@@ -65,8 +65,10 @@ struct HostPlan {
 
 }  // namespace
 
+struct apgk_group;
 struct apgk_ctx {
   apgk_config cfg{};
+  apgk_group* group = nullptr;       // the group this context is a member of (include/apgk.h "a GROUP of ranks")
   int W = 1;
   int device = 0;
   int n_sm = 148;
@@ -864,8 +866,10 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
       { int rc = level1<W, ElemB>(c, (int)in[0], (int)in[1], n_in, a_src, 0); if (rc) return rc; }
       if (mode == RUN_PARTITION) { c->part_n = n_in; return APGK_OK; }
       c->count_src = c->B.p; c->bucket_lo = c->bucket_hi = 0;
+      if (!single) { c->bucket_lo = (uint32_t)in[0] * (uint32_t)bins1; c->bucket_hi = (uint32_t)in[1] * (uint32_t)bins1; }  // the others are empty
       // the temp records of the range's buckets go over the range's own level-0 keys: dead once level 1 has run
       { int rc = count_buckets<W, ElemB>(c, n_in, N, n_prev, a_src, single); if (rc) return rc; }
+      c->bucket_lo = c->bucket_hi = 0;
       off_a += n_in;
     }
   }
@@ -1637,6 +1641,7 @@ int apgk_create(const apgk_config* cfg, apgk_ctx** out) {
 
 void apgk_destroy(apgk_ctx* c) {
   if (!c) return;
+  if (c->group) group_detach(c->group, c);   // whichever of the two is destroyed first, nothing dangles
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->tot0_dev, &c->res, &c->bases, &c->starts, &c->staging, &c->off_dev, &c->A, &c->B, &c->T, &c->chunksum, &c->chunksum0, &c->plan0, &c->out_off_local,
@@ -2285,7 +2290,9 @@ int apgk_group_unique_id(uint8_t id_out[APGK_GROUP_ID_BYTES]) {
 }
 
 static int group_init_rank(apgk_group* g, RankState& r, apgk_ctx* c) {
+  if (c->group) GFAIL(APGK_E_STATE, "the context already belongs to a group");
   r.c = c;
+  c->group = g;
   GCU(cudaSetDevice(c->device));
   GCU(cudaEventCreateWithFlags(&r.ev_a, cudaEventDisableTiming));
   GCU(cudaEventCreateWithFlags(&r.ev_b, cudaEventDisableTiming));
@@ -2342,18 +2349,8 @@ int apgk_group_local(apgk_ctx* const* ctxs, int32_t n, apgk_group** out) {
 
 void apgk_group_destroy(apgk_group* g) {
   if (!g) return;
-  close_exports(g);
-  for (RankState& r : g->rs) {
-    if (!r.c) continue;
-    cudaSetDevice(r.c->device);
-    cudaStreamSynchronize(r.c->stream);
-    DevBuf* all[] = {&r.sizes32, &r.sizes_all, &r.tot32, &r.E_tot, &r.plan_dev, &r.ptrs_dev, &r.red_in, &r.red_out, &r.ovf_out,
-                     &r.ovf_all, &r.tot0_red, &r.meta_dev, &r.meta_all, &r.bar};
-    for (DevBuf* b : all) b->release();
-    if (r.host) cudaFreeHost(r.host);
-    if (r.ev_a) cudaEventDestroy(r.ev_a);
-    if (r.ev_b) cudaEventDestroy(r.ev_b);
-  }
+  for (size_t i = 0; i < g->rs.size(); i++)
+    if (g->rs[i].c) group_detach(g, g->rs[i].c);
   if (g->comm) g_nccl.CommDestroy(g->comm);
   delete g;
 }

@@ -96,6 +96,7 @@ struct apgk_group {
   uint64_t n_instances = 0, n_distinct = 0;
   apgk_group_stats stats{};
   bool counted = false;
+  bool dead = false;   // a member context was destroyed: the group can only be destroyed
 };
 
 namespace {
@@ -308,13 +309,28 @@ int refresh_exports(apgk_group* g, const std::vector<GroupMeta>& meta, const std
   return APGK_OK;
 }
 
-void close_exports(apgk_group* g) {
-  if (!g->use_nccl) return;
+// A context leaves its group (apgk_destroy of a context that is still a member, or apgk_group_destroy): its
+// mappings of the peers' buffers are closed, the group's per-rank buffers released.  The group stays valid for
+// destruction only.
+void group_detach(apgk_group* g, apgk_ctx* c) {
   for (RankState& r : g->rs) {
-    cudaSetDevice(r.c->device);
-    cudaStreamSynchronize(r.c->stream);
-    for (size_t s = 0; s < r.mapped.size(); s++)
-      if (r.mapped[s]) { cudaIpcCloseMemHandle(r.peer_B[s]); cudaIpcCloseMemHandle(r.peer_sub[s]); r.mapped[s] = false; }
+    if (r.c != c) continue;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (g->use_nccl)
+      for (size_t s = 0; s < r.mapped.size(); s++)
+        if (r.mapped[s]) { cudaIpcCloseMemHandle(r.peer_B[s]); cudaIpcCloseMemHandle(r.peer_sub[s]); r.mapped[s] = false; }
+    DevBuf* all[] = {&r.sizes32, &r.sizes_all, &r.tot32, &r.E_tot, &r.plan_dev, &r.ptrs_dev, &r.red_in, &r.red_out, &r.ovf_out,
+                     &r.ovf_all, &r.tot0_red, &r.meta_dev, &r.meta_all, &r.bar};
+    for (DevBuf* b : all) b->release();
+    if (r.host) cudaFreeHost(r.host);
+    r.host = nullptr; r.host_words = 0;
+    if (r.ev_a) cudaEventDestroy(r.ev_a);
+    if (r.ev_b) cudaEventDestroy(r.ev_b);
+    r.ev_a = r.ev_b = nullptr;
+    r.c = nullptr;
+    c->group = nullptr;
+    g->dead = true;
   }
 }
 
@@ -547,9 +563,14 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
         stage_end(c, ST_PLAN);
         if (r.host[hl.extra] & 1ull) GFAIL(APGK_E_RANGE, "a bucket piece holds 2^31 or more k-mers");
         if (r.host[hl.extra] & 2ull) GFAIL(APGK_E_RANGE, "a merged bucket holds 2^32 or more k-mers");
-        const uint32_t lo = (uint32_t)r.host[hl.plan + me], hi = (uint32_t)r.host[hl.plan + me + 1];
+        uint32_t lo = (uint32_t)r.host[hl.plan + me], hi = (uint32_t)r.host[hl.plan + me + 1];
         const uint64_t e_lo = r.host[hl.plan + world + 1 + me], e_hi = r.host[hl.plan + world + 1 + me + 1];
         const uint64_t Nr = e_hi - e_lo;
+        // only the round's level-0 buckets hold anything: the first and the last rank's ranges reach to the ends
+        // of the bucket space, and walking those empty buckets costs more than counting the full ones
+        lo = std::max<uint32_t>(lo, (uint32_t)s_lo * (uint32_t)bins1);
+        hi = std::min<uint32_t>(hi, (uint32_t)s_hi * (uint32_t)bins1);
+        if (hi < lo) hi = lo;
         // the gathered shard, the per-bucket records (over the dead level-0 keys when everything ran at once)
         GCU(c->C2.ensure(std::max<uint64_t>(Nr, 1) * sizeof(ElemB) + 16));
         Key<W>* tmp_keys;
@@ -567,8 +588,18 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
           ga.out = c->C2.as<ElemB>(); ga.bsize_fine = c->segtot.as<unsigned long long>(); ga.bofs_fine = c->bofs.as<unsigned long long>();
           ga.sub_sizes = nullptr;
           ga.sub_ptrs = d2 > 0 ? (const uint32_t* const*)(r.ptrs_dev.as<unsigned char>() + (size_t)world * 8) : nullptr;
-          const uint32_t grid = std::min<uint32_t>((hi - lo + 7) / 8, (uint32_t)c->n_sm * 8);  // one warp per bucket
-          k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(ga);
+          static const bool legacy = getenv("APGK_GATHER") && !strcmp(getenv("APGK_GATHER"), "legacy");
+          if (legacy) {   // the round-1 kernel: one 16-byte load in flight per lane
+            const uint32_t grid = std::min<uint32_t>((hi - lo + 7) / 8, (uint32_t)c->n_sm * 8);  // one warp per bucket
+            k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(ga);
+          } else {
+            auto kern = k_gather_split2<ElemB, 256>;
+            const size_t smg = (size_t)8 * 2 * GsChunk<ElemB>::N * sizeof(ElemB);
+            int occ = 1;
+            GCTX(c, kernel_setup(c, kern, 256, smg, &occ));
+            const uint32_t grid = std::min<uint32_t>((hi - lo + 7) / 8, (uint32_t)c->n_sm * (uint32_t)occ);
+            kern<<<grid, 256, smg, c->stream>>>(ga);
+          }
           c->launches++;
           GCU(cudaGetLastError());
         }
@@ -679,6 +710,7 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
 int group_count(apgk_group* g) {
   const int world = g->world, nl = g->n_local;
   g->counted = false;
+  if (g->dead) GFAIL(APGK_E_STATE, "a context of this group has been destroyed");
   // ---- what every rank tells the others
   std::vector<GroupMeta> mine(nl), meta(world);
   for (int i = 0; i < nl; i++) {

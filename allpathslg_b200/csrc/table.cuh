@@ -273,6 +273,131 @@ __global__ void __launch_bounds__(NT) k_gather_split(const GatherArgs<Elem> ga) 
   }
 }
 
+// ---------------------------------------------------------------- the gather, pipelined through shared memory
+// Same contract as k_gather_split (sub-bucket sizes known: d2 == 0, ga.sub_ptrs or ga.sub_sizes), but the pieces
+// reach the warp through cp.async (LDGSTS): every warp owns two stages of GS_CHUNK elements in shared memory and
+// always has the NEXT chunk of its bucket's piece stream -- piece after piece, source after source -- in flight
+// while it splits the current one.  In the round-1 kernel a lane had ONE 16-byte load outstanding and sat through
+// an NVLink round trip (2-3 us) per 512 bytes per warp: 0.46-0.55 of the link at 8 GPUs.  Here a warp keeps
+// 1-6 KB in flight without holding it in registers, the copies need no alignment (element-sized cp.async), and
+// loading overlaps the ballots and the stores.
+template <typename Elem> struct GsChunk { static constexpr int N = sizeof(Elem) == 4 ? 512 : 256; };   // elements per stage (2 KB+)
+__device__ __forceinline__ void cp_async_elem(uint32_t smem_dst, const uint32_t* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(src) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void cp_async_elem(uint32_t smem_dst, const Key<W>* src) {
+#pragma unroll
+  for (int i = 0; i < W; i++)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst + 8 * i), "l"(&src->w[i]) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename Elem, int NT>
+__global__ void __launch_bounds__(NT) k_gather_split2(const GatherArgs<Elem> ga) {
+  extern __shared__ __align__(16) unsigned char gs_raw[];
+  constexpr int U = 4;                 // elements per lane and ballot round
+  constexpr int GS_CHUNK = GsChunk<Elem>::N;
+  const int d2 = ga.d2, digit_pos = ga.digit_pos;
+  const uint32_t n_src = ga.n_src, nb = ga.nb, lo = ga.lo, hi = ga.hi;
+  const uint32_t nbins = 1u << d2, mask = nbins - 1u;
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = (blockIdx.x * NT + threadIdx.x) >> 5, nwarps = (gridDim.x * NT) >> 5;
+  Elem* stage = reinterpret_cast<Elem*>(gs_raw) + (size_t)wib * 2 * GS_CHUNK;   // this warp's two stages
+  const uint32_t stage_a = smem_u32(stage);
+  Elem* __restrict__ out = ga.out;
+  for (uint32_t b = lo + warp; b < hi; b += nwarps) {
+    // ---- sub-bucket sizes -> write cursors (lane j: sub-bucket j)
+    uint32_t mine = 0;
+    if (d2 == 0) {
+      for (uint32_t s = 0; s < n_src; s++) mine += ga.sizes_all[(size_t)s * nb + b];
+    } else if (ga.sub_ptrs) {
+      if (lane < nbins)
+        for (uint32_t s = 0; s < n_src; s++) mine += ga.sub_ptrs[s][((size_t)b << d2) + lane];
+    } else {
+      const size_t row = (size_t)(hi - lo) << d2;
+      if (lane < nbins)
+        for (uint32_t s = 0; s < n_src; s++) mine += ga.sub_sizes[(size_t)s * row + (((size_t)(b - lo)) << d2) + lane];
+    }
+    if (lane >= nbins) mine = 0;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += v;
+    }
+    uint32_t cur = incl - mine;
+    const unsigned long long base_b = ga.bofs_coarse[b] - ga.coarse_base;
+    if (lane < nbins) {
+      const size_t f = ((size_t)b << d2) | lane;
+      ga.bsize_fine[f] = mine;
+      ga.bofs_fine[f] = base_b + cur;
+    }
+    // ---- the bucket's piece stream: a load cursor one chunk ahead of the split
+    uint32_t ls = 0, loff = 0, ln = 0;
+    const Elem* lsrc = nullptr;
+    auto next_piece = [&]() {   // first non-empty piece from source ls on (warp-uniform)
+      while (ls < n_src) {
+        ln = ga.sizes_all[(size_t)ls * nb + b];
+        if (ln) { lsrc = ga.src_base[ls] + (ga.seg_off ? ga.seg_off[ls] : 0ull) + ga.piece_off[(size_t)ls * (nb + 1) + b]; return; }
+        ls++;
+      }
+    };
+    auto issue = [&](uint32_t st) -> uint32_t {   // start the copy of the next chunk into stage st; -> its length (0: stream over)
+      if (ls >= n_src) return 0u;
+      const uint32_t cnt = ln - loff < (uint32_t)GS_CHUNK ? ln - loff : (uint32_t)GS_CHUNK;
+      const Elem* src = lsrc + loff;
+      const uint32_t dst = stage_a + st * (uint32_t)(GS_CHUNK * sizeof(Elem));
+#pragma unroll
+      for (int u = 0; u < GS_CHUNK / 32; u++) {
+        const uint32_t i = u * 32 + lane;
+        if (i < cnt) cp_async_elem(dst + i * (uint32_t)sizeof(Elem), src + i);
+      }
+      cp_async_commit();
+      loff += cnt;
+      if (loff == ln) { ls++; loff = 0; next_piece(); }
+      return cnt;
+    };
+    next_piece();
+    uint32_t st = 0;
+    uint32_t cnt_cur = issue(0);
+    while (cnt_cur) {
+      const uint32_t cnt_next = issue(st ^ 1u);
+      if (cnt_next) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+      const Elem* sm = stage + (size_t)st * GS_CHUNK;
+      for (uint32_t i0 = 0; i0 < cnt_cur; i0 += 32 * U) {
+        Elem e[U];
+        uint32_t d[U], pos[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t i = i0 + u * 32 + lane;
+          d[u] = 0xFFFFFFFFu; pos[u] = 0;
+          if (i < cnt_cur) { e[u] = sm[i]; d[u] = split_digit(e[u], digit_pos, mask); } else e[u] = Elem{};
+        }
+        for (uint32_t j = 0; j < nbins; j++) {
+          uint32_t base = __shfl_sync(0xffffffffu, cur, j), tot = 0;
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, d[u] == j);
+            if (d[u] == j) pos[u] = base + tot + __popc(m & ((1u << lane) - 1u));
+            tot += __popc(m);
+          }
+          if (lane == j) cur += tot;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (d[u] != 0xFFFFFFFFu) out[base_b + pos[u]] = split_strip(e[u], digit_pos);
+      }
+      __syncwarp();   // every lane is done with stage st before a later copy lands in it
+      st ^= 1u;
+      cnt_cur = cnt_next;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- sharded counting: the plan of an exchange, on the device
 // u64 bucket sizes of this rank's partition -> u32 (what travels in the all-gather); flag |= 1 if one does not fit
 __global__ void k_sizes32(const unsigned long long* __restrict__ in, uint32_t nb, uint32_t* __restrict__ out,

@@ -65,6 +65,10 @@ class KmerCounter:
             raise ApgkError(rc, self._L.apgk_last_error(self._h).decode())
 
     def close(self):
+        grp = getattr(self, "_group", None)
+        if grp is not None:          # a group made for this counter by dist.sharded_count goes first
+            self._group = None
+            grp.close()
         if getattr(self, "_h", None):
             self._L.apgk_destroy(self._h)
             self._h = None

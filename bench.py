@@ -403,7 +403,15 @@ def run_ours(args):
         except Exception as e:
             parity = {"error": str(e)[:200]}
 
+    # leave the group in two steps: every rank unmaps the peers' partition buffers, then (after a barrier) frees its own
+    grp = getattr(kc, "_group", None)
+    if grp is not None:
+        kc._group = None
+        grp.close()
+    if dist is not None:
+        dist.barrier()
     if rank != 0:
+        kc.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
@@ -477,6 +485,7 @@ def run_ours(args):
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }
     emit(line)
+    kc.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -502,6 +511,9 @@ def emit(line):
 
 
 def main():
+    import faulthandler
+
+    faulthandler.enable()
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

@@ -68,6 +68,7 @@ for (K, G, L, n_per, rounds) in CASES:
                    tm["step_ms"]), flush=True)
         ok = ok and bool(f.item())
     kc._group.close()
+    dist.barrier()   # every rank has unmapped the peers' buffers before anyone frees its own
     kc.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -218,6 +218,7 @@ if rank == 0:
         with open(args.out, "w") as f:
             f.write(json.dumps(line, indent=1) + "\n")
 kc._group.close()
+dist.barrier()   # every rank has unmapped the peers' buffers before anyone frees its own
 kc.close()
 dist.barrier()
 dist.destroy_process_group()
