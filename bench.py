@@ -339,6 +339,16 @@ def run_ours(args):
         dt = float(t.item())
     if world == 1:
         n_inst_total = kc.totals()[0]
+    per_rank = None
+    if dist is not None:   # where the ranks differ: every rank's stage times (rank skew shows up as "reduce" on the fast ranks)
+        names = ["scatter0", "scatter1", "owner", "local", "table", "plan", "reduce", "total"]
+        mine = torch.tensor([stage_acc.get(n_, 0.0) / args.steps for n_ in names] + [float(kc.totals()[0]), float(kc.totals()[1])],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {n_: [round(float(t[i]), 2) for t in allr] for i, n_ in enumerate(names)}
+        per_rank["shard_instances"] = [int(t[len(names)]) for t in allr]
+        per_rank["shard_distinct"] = [int(t[len(names) + 1]) for t in allr]
     ms_step = 1e3 * dt / args.steps
     value = n_inst_total / (ms_step * 1e-3) / 1e9
     stage_ms = {k_: v / args.steps for k_, v in stage_acc.items()}
@@ -480,7 +490,7 @@ def run_ours(args):
         "cpu_baseline": {"value": round(cb_inst / cb_dt / 1e9, 4), "unit": "Gk-mers/s", "cores": cores, "kind": "port",
                          "sample": cpu_sample_text(cb_inst) + ", oracle port (not the reference's code: parity unpinned)"},
         "geometry": geo, "shard_ms": dict({k_: round(v / args.steps, 2) for k_, v in shard_acc.items()}, **{k_: (list(v) if isinstance(v, tuple) else v) for k_, v in shard_info.items()}) if shard_acc else None,
-        "records": records, "lookups": lookups, "parity_sample": parity,
+        "per_rank_ms": per_rank, "records": records, "lookups": lookups, "parity_sample": parity,
         "n_instances": int(n_inst_total), "n_distinct_rank0": int(nd_local),
         "invariant_sum_f_spectrum_eq_instances": bool(inv_ok),
     }
