@@ -614,6 +614,10 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
           c->bucket_lo = c->bucket_hi = 0;
         }
         r.shard_n += Nr;
+        // (measurement aid for the single-process form: one rank's shard-side kernels at a time, so that the stage
+        // times of contexts that share a device are each rank's own cost -- tools/skew_probe.py)
+        static const bool serial = getenv("APGK_GROUP_SERIAL") != nullptr;
+        if (serial && !g->use_nccl) GCU(cudaStreamSynchronize(c->stream));
         // bytes this rank's gather pulled from the peers: everything but its own piece
         const uint64_t own = r.host[hl.plan + 2 * (world + 1) + me + 1] - r.host[hl.plan + 2 * (world + 1) + me];
         r.remote_bytes += (Nr - own) * sizeof(ElemB);

@@ -12,6 +12,14 @@
 // fresh slot; a two-choice start slot that keeps most warps out of the probing loop; an L2 prefetch of
 // the next bucket.  Issue slots and the L1 data pipe both sit at ~60%: the kernel is bound by the
 // barrier-separated phases of small buckets, not by instruction count.)
+// (Round 2, profiles/r02_local3_experiments.txt: ncu shows 69 % issue-slot utilisation and 2.1 shared atomics per
+// key, yet neither a variant with ~40 % fewer instructions on the insert path -- 32-bit shared-window addressing,
+// compile-time table offsets, per-pass constants pinned in registers, rolled probe loop, predicate-free full
+// batches, branch-free 16-slot row ranking -- nor one that also halved the atomics -- look before CAS, so a
+// duplicate costs one RED; no occupancy bitmap -- moved the time (28.0 and 29.8 ms against 28.1).  What does move
+// it: the bucket size.  Per-rank timings of the sharded form give t = 4.3 ps x keys + 9.2 ns x buckets per GPU,
+// i.e. a bucket costs as much as ~2100 keys whatever it holds (six CTA-wide phases, one exposed global-load
+// latency), and larger buckets pay more per key for probing (P = 19: 39 ms).)
 // (A fully monotone slot hash was tried first: sequencing-error variants of a genomic
 // k-mer differ in their low bits, land on the same home slot and build clusters right
 // where the 45x-covered k-mer lives -- ncu showed 6.5 warp instructions per key in
