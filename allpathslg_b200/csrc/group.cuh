@@ -69,7 +69,7 @@ struct GroupMeta {   // what every rank tells the others before a step (all-gath
 
 struct RankState {   // per LOCAL context
   apgk_ctx* c = nullptr;
-  DevBuf sizes32, sizes_all, tot32, E_tot, plan_dev, ptrs_dev, red_in, red_out, ovf_out, ovf_all, tot0_red, meta_dev, meta_all, bar;
+  DevBuf sizes32, sizes_all, tot32, E_tot, cost32, E_cost, plan_dev, ptrs_dev, red_in, red_out, ovf_out, ovf_all, tot0_red, meta_dev, meta_all, bar;
   unsigned long long* host = nullptr;          // pinned: plan block | reduced spectrum | overflow lists (see offsets)
   size_t host_words = 0;
   std::vector<void*> peer_B, peer_sub;          // [world] device pointers valid on this rank's device (own slot: own buffer)
@@ -320,7 +320,7 @@ void group_detach(apgk_group* g, apgk_ctx* c) {
     if (g->use_nccl)
       for (size_t s = 0; s < r.mapped.size(); s++)
         if (r.mapped[s]) { cudaIpcCloseMemHandle(r.peer_B[s]); cudaIpcCloseMemHandle(r.peer_sub[s]); r.mapped[s] = false; }
-    DevBuf* all[] = {&r.sizes32, &r.sizes_all, &r.tot32, &r.E_tot, &r.plan_dev, &r.ptrs_dev, &r.red_in, &r.red_out, &r.ovf_out,
+    DevBuf* all[] = {&r.sizes32, &r.sizes_all, &r.tot32, &r.E_tot, &r.cost32, &r.E_cost, &r.plan_dev, &r.ptrs_dev, &r.red_in, &r.red_out, &r.ovf_out,
                      &r.ovf_all, &r.tot0_red, &r.meta_dev, &r.meta_all, &r.bar};
     for (DevBuf* b : all) b->release();
     if (r.host) cudaFreeHost(r.host);
@@ -362,6 +362,14 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
   if (std::is_same<ElemB, uint32_t>::value) {
     if (const char* e = getenv("APGK_LM")) { if (atoi(e) >= 256 && atoi(e) <= 12288) local_max = atoi(e); }
   }
+  // The ranges the ranks own are balanced by COST, not by instance count: canonical k-mers are twice as dense at the
+  // low end of k-mer space as on average and thin out to nothing at the high end, so with equal instance counts the
+  // last rank gets five times the buckets of the first -- and a bucket costs the per-bucket kernel as much as ~2100 keys
+  // whatever it holds (profiles/r02_local3_experiments.txt): at 8 ranks the last rank's counting took 1.6x the average
+  // and everybody waited for it in the final all-reduce.  cost(bucket) = keys + bucket_cost per fine bucket.
+  uint32_t bucket_cost = std::is_same<ElemB, uint32_t>::value ? 800u : 0u;   // ~9 ns per bucket over ~12 ps per key (gather + counting)
+  if (const char* e = getenv("APGK_BUCKET_COST")) bucket_cost = (uint32_t)std::max(0, atoi(e));
+  if (world == 1) bucket_cost = 0;
   const HostLayout hl(world, bins0);
   uint64_t N_sum = 0, N_max = 0;
   for (int s = 0; s < world; s++) { N_sum += meta[s].n_windows; N_max = std::max<uint64_t>(N_max, meta[s].n_windows); }
@@ -408,6 +416,7 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
     GCU(r.sizes_all.ensure((size_t)world * nb * 4));
     GCU(r.tot32.ensure((size_t)nb * 4));
     GCU(r.E_tot.ensure(((size_t)nb + 1) * 8));
+    if (bucket_cost) { GCU(r.cost32.ensure((size_t)nb * 4)); GCU(r.E_cost.ensure(((size_t)nb + 1) * 8)); }
     GCU(r.plan_dev.ensure(3 * ((size_t)world + 1) * 8));
     GCU(c->piece_off.ensure((size_t)world * ((size_t)nb + 1) * 8));
     GCU(r.ptrs_dev.ensure(3 * (size_t)world * 8));
@@ -539,13 +548,16 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
         const int me = g->rank0 + i;
         GCU(cudaSetDevice(c->device));
         unsigned long long* flags = c->res.as<unsigned long long>() + RES_XFLAGS;
-        k_total_sizes<<<(nb + 255) / 256, 256, 0, c->stream>>>(r.sizes_all.as<uint32_t>(), (uint32_t)world, nb, r.tot32.as<uint32_t>(), flags);
+        k_total_sizes<<<(nb + 255) / 256, 256, 0, c->stream>>>(r.sizes_all.as<uint32_t>(), (uint32_t)world, nb, r.tot32.as<uint32_t>(), flags,
+                                                             bucket_cost ? r.cost32.as<uint32_t>() : nullptr, bucket_cost << d2);
         c->launches++;
         GCTX(c, scan_u32(c, r.tot32.as<uint32_t>(), nb, r.E_tot.as<unsigned long long>(), nullptr));
+        if (bucket_cost) GCTX(c, scan_u32(c, r.cost32.as<uint32_t>(), nb, r.E_cost.as<unsigned long long>(), nullptr));
         for (int s = 0; s < world; s++)
           GCTX(c, scan_u32(c, r.sizes_all.as<uint32_t>() + (size_t)s * nb, nb,
                            c->piece_off.as<unsigned long long>() + (size_t)s * ((size_t)nb + 1), nullptr));
-        k_splitters<<<(world + 1 + 63) / 64, 64, 0, c->stream>>>(r.E_tot.as<unsigned long long>(), nb, (uint32_t)world,
+        k_splitters<<<(world + 1 + 63) / 64, 64, 0, c->stream>>>((bucket_cost ? r.E_cost : r.E_tot).as<unsigned long long>(),
+                                                              r.E_tot.as<unsigned long long>(), nb, (uint32_t)world,
                                                               c->piece_off.as<unsigned long long>() + (size_t)me * ((size_t)nb + 1),
                                                               r.plan_dev.as<unsigned long long>());
         c->launches++;
@@ -766,16 +778,19 @@ int group_count(apgk_group* g) {
   // ---- one round or several?  per instance: full key (A) + two level-1 copies (B, gathered shard) + temp count;
   // in rounds the per-bucket records need their own buffer (A keeps the outer round's keys)
   const uint64_t eA = 8ull * W, eB = u32 ? 4 : 8ull * W, eT = (meta[0].flags ? 4 : 0);
-  const double slack = 1.08;   // a shard may exceed the average by the balance granularity
+  // a shard may exceed the average: by the balance granularity, and because the ranges are balanced by cost (the
+  // rank at the dense end of k-mer space gets fewer, fuller buckets: ~1.2x the average instances at 8 ranks)
+  const double slack = world > 1 && u32 ? 1.25 : 1.08;
   bool single;
   uint64_t cap_outer = cap_o, cap_inner = cap_i;
   if (cap_o) {
     if (!cap_inner) cap_inner = cap_outer;
     single = N_max <= cap_outer && N_max <= cap_inner;
   } else {
-    single = (double)N_max * (double)(eA + 2 * eB + eT) * slack <= (double)budget;
+    // everything at once: the rank's own partition (B) + the shard's level-1 copy, records (over the dead level-0 keys) and counts
+    single = (double)N_max * ((double)eB + std::max((double)eA, slack * (double)eA) + slack * (double)(eB + eT)) <= (double)budget;
     if (!single) {
-      const double inner_bytes = (double)(2 * eB + eA + eT) * slack;
+      const double inner_bytes = (double)eB + slack * (double)(eB + eA + eT);
       if (cap_inner) cap_outer = (uint64_t)std::max(1.0, ((double)budget - (double)cap_inner * inner_bytes) / (double)eA);
       else { cap_outer = (uint64_t)((double)budget / ((double)eA + inner_bytes / 4.0)); cap_inner = std::max<uint64_t>(1, cap_outer / 4); }
       cap_outer = std::max<uint64_t>(cap_outer, 1);

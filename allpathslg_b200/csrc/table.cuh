@@ -408,25 +408,31 @@ __global__ void k_sizes32(const unsigned long long* __restrict__ in, uint32_t nb
   if (v >= (1ull << 31)) { atomicOr(flag, 1ull); out[b] = 0; }
   else out[b] = (uint32_t)v;
 }
-// merged size of every bucket over the sources; flag |= 2 if one reaches 2^32
+// merged size of every bucket over the sources; flag |= 2 if one reaches 2^32.  cost32 (may be null): what
+// counting the bucket costs, in key units -- its keys plus `bucket_cost` for being a bucket at all.
 __global__ void k_total_sizes(const uint32_t* __restrict__ sizes_all, uint32_t n_src, uint32_t nb, uint32_t* __restrict__ tot32,
-                              unsigned long long* __restrict__ flag) {
+                              unsigned long long* __restrict__ flag, uint32_t* __restrict__ cost32, uint32_t bucket_cost) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   unsigned long long t = 0;
   for (uint32_t s = 0; s < n_src; s++) t += sizes_all[(size_t)s * nb + b];
   if (t >= (1ull << 32)) { atomicOr(flag, 2ull); t = 0; }
   tot32[b] = (uint32_t)t;
+  if (cost32) {
+    const unsigned long long c = t ? t + bucket_cost : 0ull;
+    cost32[b] = c >= (1ull << 32) ? 0xFFFFFFFFu : (uint32_t)c;
+  }
 }
-// Balanced contiguous bucket ranges from the exclusive prefix E[nb + 1] of the merged sizes: range r ends after the
-// first bucket whose cumulative count exceeds total * (r + 1) / world (the rule of dist.balanced_splitters).
-// plan[0 .. world] = bounds, plan[world + 1 .. 2 world + 1] = E at the bounds.  One thread per bound.
-// plan[2 world + 2 ..] = own[] at the bounds (the calling rank's own prefix: how much of each range it holds itself).
-__global__ void k_splitters(const unsigned long long* __restrict__ E, uint32_t nb, uint32_t world,
+// Balanced contiguous bucket ranges from the exclusive prefix S[nb + 1] of the buckets' weights (their merged sizes,
+// or their costs): range r ends after the first bucket whose cumulative weight exceeds total * (r + 1) / world (the
+// rule of dist.balanced_splitters).  plan[0 .. world] = bounds, plan[world + 1 .. 2 world + 1] = E (the prefix of the
+// merged SIZES) at the bounds, plan[2 world + 2 ..] = own[] at the bounds (the calling rank's own prefix: how much of
+// each range it holds itself).  One thread per bound.
+__global__ void k_splitters(const unsigned long long* __restrict__ S, const unsigned long long* __restrict__ E, uint32_t nb, uint32_t world,
                             const unsigned long long* __restrict__ own, unsigned long long* __restrict__ plan) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > world) return;
-  const unsigned long long total = E[nb];
+  const unsigned long long total = S[nb];
   uint32_t bound;
   if (r == 0) bound = 0;
   else if (r == world) bound = nb;
@@ -437,7 +443,7 @@ __global__ void k_splitters(const unsigned long long* __restrict__ E, uint32_t n
     uint32_t lo = 0, hi = nb;
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
-      if (E[mid + 1] > target) hi = mid; else lo = mid + 1;
+      if (S[mid + 1] > target) hi = mid; else lo = mid + 1;
     }
     bound = lo;
   }

@@ -72,12 +72,17 @@ def _check_against_oracle(oracle, grp, kcs, p, o, K, sorted_by_rank):
     return ek, ec, en
 
 
+@pytest.mark.parametrize("bucket_cost", [None, 0])
 @pytest.mark.parametrize("K,world,n_reads,empty", [(25, 2, 30_000, None), (25, 5, 30_000, 2), (20, 3, 20_000, None),
                                                    (25, 8, 40_000, None), (31, 2, 12_000, None), (48, 3, 12_000, None),
                                                    (96, 2, 8_000, 0), (25, 1, 10_000, None)])
-def test_group_single_round(oracle, K, world, n_reads, empty):
+def test_group_single_round(oracle, K, world, n_reads, empty, bucket_cost, monkeypatch):
+    """bucket_cost None: the default balance of the owned ranges (by cost: keys + a charge per bucket); 0: by
+    instance count alone, which must then be even up to the bucket granularity."""
     from allpathslg_b200 import KmerGroup
 
+    if bucket_cost is not None:
+        monkeypatch.setenv("APGK_BUCKET_COST", str(bucket_cost))
     kcs, p, o = _make_ranks(oracle, K, world, n_reads, empty_rank=empty)
     with KmerGroup.local(kcs) as grp:
         grp.count()
@@ -85,7 +90,7 @@ def test_group_single_round(oracle, K, world, n_reads, empty):
         assert st["world"] == world and st["n_rounds"] == 1
         ek, ec, en = _check_against_oracle(oracle, grp, kcs, p, o, K, sorted_by_rank=True)
         per_rank = [kc.totals()[0] for kc in kcs]
-        if world > 1 and en > 10 * world:
+        if world > 1 and en > 10 * world and bucket_cost == 0:
             assert max(per_rank) < 1.25 * en / world + (en >> st["prefix_bits"]) * 64   # balanced up to bucket granularity
         # a second step over the same stores (steady state: buffers, mappings and the table's capacity are reused)
         grp.count()
