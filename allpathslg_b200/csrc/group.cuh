@@ -351,7 +351,8 @@ struct GRound { int lo, hi; std::vector<std::array<int, 2>> inner; };
 
 // ---------------------------------------------------------------- the step
 template <int W, typename ElemB>
-int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool single, uint64_t cap_outer, uint64_t cap_inner, int d2) {
+int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool single, uint64_t cap_outer, uint64_t cap_inner, int d2,
+                      uint64_t budget, double inner_bytes) {
   const int world = g->world, nl = g->n_local;
   apgk_ctx* c0 = g->rs[0].c;
   const KeyGeom gp = c0->geom;
@@ -464,6 +465,22 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
     for (int d = 0; d < bins0; d++) {
       tmax[d] = g->rs[0].host[hl.tot0 + bins0 + d];
       if (tmax[d] >= (1ull << 32)) GFAIL(APGK_E_RANGE, "level-0 bucket %d holds %llu k-mers on one rank (>= 2^32)", d, (unsigned long long)tmax[d]);
+    }
+    if (!cap_outer) {
+      // Sizes of the rounds from the memory budget: the fewest outer rounds (each is one more pass over the reads)
+      // whose level-0 keys leave room for inner rounds of at least a sixteenth of an outer round.
+      uint64_t tsum = 0;
+      for (int d = 0; d < bins0; d++) tsum += tmax[d];
+      const double eA = (double)sizeof(Key<W>);
+      for (uint64_t ro = 1;; ro++) {
+        const double per_outer = (double)tsum / (double)ro * 1.05 + (double)(tsum / (uint64_t)bins0) * 2.0;   // greedy cuts overshoot by a bucket
+        const double left = (double)budget - eA * per_outer;
+        if (left >= inner_bytes * per_outer / 16.0 || ro >= 64) {
+          cap_outer = (uint64_t)std::max(1.0, per_outer);
+          cap_inner = cap_inner ? cap_inner : (uint64_t)std::max(1.0, std::min(per_outer, left / inner_bytes));
+          break;
+        }
+      }
     }
     int lo = 0; uint64_t acc = 0;
     auto close_outer = [&](int hi) {
@@ -746,10 +763,11 @@ int group_count(apgk_group* g) {
       size_t fr = 0, tot = 0;
       GCU(cudaMemGetInfo(&fr, &tot));
       const size_t held = c->A.cap + c->B.cap + c->T.cap + c->C2.cap + c->TK.cap;
-      c->budget_bytes = (uint64_t)((double)(fr + held) * 0.60);
+      c->budget_bytes = (uint64_t)((double)(fr + held) * 0.70);
       c->budget_for = c->n_windows + 1;
     }
     m.budget = c->budget_bytes;
+    if (const char* e = getenv("APGK_BUDGET_BYTES")) { if (atoll(e) > 0) m.budget = (uint64_t)atoll(e); }   // tests: a small device
   }
   { int rc = coll_allgather_host(g, mine.data(), sizeof(GroupMeta), meta.data()); if (rc) return rc; }
   uint64_t N_max = 0, budget = ~0ull, cap_o = 0, cap_i = 0;
@@ -789,17 +807,14 @@ int group_count(apgk_group* g) {
   } else {
     // everything at once: the rank's own partition (B) + the shard's level-1 copy, records (over the dead level-0 keys) and counts
     single = (double)N_max * ((double)eB + std::max((double)eA, slack * (double)eA) + slack * (double)(eB + eT)) <= (double)budget;
-    if (!single) {
-      const double inner_bytes = (double)eB + slack * (double)(eB + eA + eT);
-      if (cap_inner) cap_outer = (uint64_t)std::max(1.0, ((double)budget - (double)cap_inner * inner_bytes) / (double)eA);
-      else { cap_outer = (uint64_t)((double)budget / ((double)eA + inner_bytes / 4.0)); cap_inner = std::max<uint64_t>(1, cap_outer / 4); }
-      cap_outer = std::max<uint64_t>(cap_outer, 1);
-    }
+    if (cap_i && N_max > cap_i) single = false;
+    cap_outer = 0;   // several rounds: sized in group_count_typed once the level-0 totals of all ranks are known
   }
-  if (W == 1) return u32 ? group_count_typed<1, uint32_t>(g, meta, single, cap_outer, cap_inner, d2)
-                         : group_count_typed<1, Key<1>>(g, meta, single, cap_outer, cap_inner, d2);
-  if (W == 2) return group_count_typed<2, Key<2>>(g, meta, single, cap_outer, cap_inner, d2);
-  return group_count_typed<3, Key<3>>(g, meta, single, cap_outer, cap_inner, d2);
+  const double inner_bytes = (double)eB + slack * (double)(eB + eA + eT);
+  if (W == 1) return u32 ? group_count_typed<1, uint32_t>(g, meta, single, cap_outer, cap_inner, d2, budget, inner_bytes)
+                         : group_count_typed<1, Key<1>>(g, meta, single, cap_outer, cap_inner, d2, budget, inner_bytes);
+  if (W == 2) return group_count_typed<2, Key<2>>(g, meta, single, cap_outer, cap_inner, d2, budget, inner_bytes);
+  return group_count_typed<3, Key<3>>(g, meta, single, cap_outer, cap_inner, d2, budget, inner_bytes);
 }
 
 }  // namespace

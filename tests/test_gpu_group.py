@@ -133,6 +133,23 @@ def test_group_rounds(oracle, K, world, n_reads, outer_div, inner_div):
         kc.close()
 
 
+@pytest.mark.parametrize("K,world,n_reads,budget_mb", [(25, 3, 60_000, 40), (25, 2, 60_000, 24), (48, 2, 20_000, 10)])
+def test_group_rounds_sized_from_the_memory_budget(oracle, K, world, n_reads, budget_mb, monkeypatch):
+    """No round sizes given: the group cuts outer and inner rounds from the device-memory budget of its tightest rank
+    (here a pretend budget, far below what the k-mers need at once)."""
+    from allpathslg_b200 import KmerGroup
+
+    monkeypatch.setenv("APGK_BUDGET_BYTES", str(budget_mb << 20))
+    kcs, p, o = _make_ranks(oracle, K, world, n_reads)
+    with KmerGroup.local(kcs) as grp:
+        grp.count()
+        st = grp.stats()
+        assert st["n_rounds"] >= 2
+        _check_against_oracle(oracle, grp, kcs, p, o, K, sorted_by_rank=False)
+    for kc in kcs:
+        kc.close()
+
+
 def test_group_counts_beyond_the_dense_spectrum(oracle):
     """A k-mer seen more than 65535 times lives in one rank's overflow list: the group's spectrum must carry it on
     every rank's behalf (sum f * spectrum[f] == instances)."""
