@@ -327,13 +327,15 @@ int ensure_store(apgk_ctx* c, uint64_t bases_needed) {
     DevBuf nb, ns;
     size_t grow = std::max(bbytes, c->bases.cap * 2);
     CU(cudaStreamSynchronize(c->stream));
-    CU(nb.ensure(grow, true));
-    CU(ns.ensure(grow / 2 + 256, true));
-    if (c->total_bases) {
-      CU(cudaMemcpyAsync(nb.p, c->bases.p, ((c->total_bases + 31) / 32) * 8 + 8, cudaMemcpyDeviceToDevice, c->stream));
-      CU(cudaMemcpyAsync(ns.p, c->starts.p, ((c->total_bases + 31) / 32) * 4 + 8, cudaMemcpyDeviceToDevice, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
+    cudaError_t e = nb.ensure(grow, true);
+    if (e == cudaSuccess) e = ns.ensure(grow / 2 + 256, true);
+    if (e == cudaSuccess && c->total_bases) {
+      e = cudaMemcpyAsync(nb.p, c->bases.p, ((c->total_bases + 31) / 32) * 8 + 8, cudaMemcpyDeviceToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ns.p, c->starts.p, ((c->total_bases + 31) / 32) * 4 + 8, cudaMemcpyDeviceToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     }
+    if (e != cudaSuccess) { nb.release(); ns.release(); }   // the old store stays in place
+    CU(e);
     c->bases.release(); c->starts.release();
     c->bases = nb; c->starts = ns;
   }
@@ -1109,7 +1111,8 @@ FreqTable<W> freq_table(const apgk_ctx* c) {
 template <int W>
 int lookup_impl(apgk_ctx* c, const uint64_t* kmers, uint64_t n, int canon, uint32_t* out) {
   if (!n) return APGK_OK;
-  DevBuf q, r;
+  struct Tmp { DevBuf b; ~Tmp() { b.release(); } } q_, r_;   // released on every path out
+  DevBuf& q = q_.b; DevBuf& r = r_.b;
   CU(q.ensure(n * sizeof(Key<W>)));
   CU(r.ensure(n * 4));
   CU(cudaMemcpyAsync(q.p, kmers, n * sizeof(Key<W>), cudaMemcpyHostToDevice, c->stream));
@@ -1119,7 +1122,6 @@ int lookup_impl(apgk_ctx* c, const uint64_t* kmers, uint64_t n, int canon, uint3
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, r.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  q.release(); r.release();
   CU(e);
   return APGK_OK;
 }
@@ -1128,7 +1130,8 @@ template <int W>
 int read_freqs_impl(apgk_ctx* c, uint64_t first, uint64_t n, uint32_t* out) {
   if (!n) return APGK_OK;
   { int rc = wait_ingest(c); if (rc) return rc; }
-  DevBuf r;
+  struct Tmp { DevBuf b; ~Tmp() { b.release(); } } r_;   // released on every path out
+  DevBuf& r = r_.b;
   CU(r.ensure(n * 4));
   constexpr int NT = 128;
   const uint64_t span = (first + n) - (first & ~15ull);
@@ -1139,7 +1142,6 @@ int read_freqs_impl(apgk_ctx* c, uint64_t first, uint64_t n, uint32_t* out) {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, r.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  r.release();
   CU(e);
   return APGK_OK;
 }
@@ -1817,6 +1819,13 @@ int apgk_finish(apgk_ctx* c) {
 int apgk_finish_keys_device(apgk_ctx* c, const uint64_t* d_keys, uint64_t n) {
   if (!c || (!d_keys && n)) return APGK_E_ARG;
   CU(cudaSetDevice(c->device));
+  {  // the level-0 scatter writes c->A: keys handed in through apgk_key_buffer would be read and overwritten at once
+    const unsigned char* k0 = (const unsigned char*)d_keys;
+    const unsigned char* a0 = (const unsigned char*)c->A.p;
+    if (n && a0 && k0 < a0 + c->A.cap && a0 < k0 + n * (size_t)c->W * 8)
+      FAIL(APGK_E_ARG, "apgk_finish_keys_device: d_keys overlaps the library's own key buffer (apgk_key_buffer): it is the "
+                       "scatter's destination -- receive into a buffer of your own");
+  }
   switch (c->W) {
     case 1: return finish_impl<1>(c, (const Key<1>*)d_keys, n);
     case 2: return finish_impl<2>(c, (const Key<2>*)d_keys, n);

@@ -185,8 +185,9 @@ int apgk_owner_plan(apgk_ctx* ctx, uint32_t n_ranks, uint64_t* counts_out);
  * buffer d_keys_out (sum(counts) * W words). */
 int apgk_owner_scatter(apgk_ctx* ctx, uint64_t* d_keys_out);
 /* The library's own level-0 key buffer, sized for n_keys k-mers: a caller may use it as the
- * d_keys_out of apgk_owner_scatter (and as the send buffer of its exchange) instead of allocating
- * another N*W words.  Its contents are overwritten by the next apgk_finish* call. */
+ * d_keys_out of apgk_owner_scatter (and as the SEND buffer of its exchange) instead of allocating
+ * another N*W words.  Its contents are overwritten by the next apgk_finish* call -- so it cannot be the
+ * d_keys of apgk_finish_keys_device (refused with APGK_E_ARG): receive into a buffer of your own. */
 int apgk_key_buffer(apgk_ctx* ctx, uint64_t n_keys, uint64_t** d_ptr);
 /* Owner hash of k-mers (host arrays), for tests. */
 int apgk_owner_of(int K, const uint64_t* kmers, uint64_t n, uint32_t n_ranks, uint32_t* owner_out);
