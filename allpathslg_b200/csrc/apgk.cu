@@ -91,6 +91,7 @@ struct apgk_ctx {
   HostPlan hp0;                      // level-0 plan: a function of the input size, kept from step to step
   uint64_t hp0_elems = ~0ull; uint32_t hp0_tile = 0;
   std::map<std::pair<const void*, size_t>, int> kattr;   // (kernel, dynamic smem) -> occupancy, attribute set
+  double table_scale = 1.0;          // rounds: instances of the whole run over instances counted so far (table growth hint)
   bool table_pending = false;        // single-round step: the table's size is read at the final synchronisation
   void* tmp_keys_last = nullptr;     // where the last count_buckets left its per-bucket records
   DevBuf A, B, T, chunksum, chunksum0, plan0, out_off_local, segtot, bstart32, bofs, plan, bstart64, nd, out_off, blocksum, big_list, stats,
@@ -505,7 +506,10 @@ int ensure_preserve(apgk_ctx* c, DevBuf& b, size_t bytes, size_t keep_bytes) {
   if (bytes <= b.cap) return APGK_OK;
   if (!keep_bytes || !b.p) { CU(b.ensure(bytes)); return APGK_OK; }
   DevBuf nb;
-  CU(nb.ensure(std::max(bytes, b.cap + b.cap / 2)));
+  if (nb.ensure(std::max(bytes, b.cap + b.cap / 2)) != cudaSuccess) {
+    cudaGetLastError();
+    CU(nb.ensure(bytes));   // no room for growth in steps: exactly what is needed
+  }
   CU(cudaMemcpyAsync(nb.p, b.p, keep_bytes, cudaMemcpyDeviceToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   b.release();
@@ -848,6 +852,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
   CU(c->out_off_local.ensure(((size_t)c->nb1 + 1) * 8));
   CU(c->stats.ensure(64));
   uint64_t n_prev = 0;  // records already in the result table
+  uint64_t n_counted = 0;  // instances of the rounds so far (the table's growth hint)
 
   for (const Round& r : rounds) {
     if (r.n == 0) {
@@ -862,6 +867,7 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
     { int rc = level0_scatter<W>(c, dev_keys, dg0, r.lo, r.hi, r.n); if (rc) return rc; }
     uint64_t off_a = 0;   // keys of the outer round before the current inner range
     for (const auto& in : r.inner) {
+      n_counted += in[2];
       const uint64_t n_in = in[2];
       if (n_in == 0) continue;
       Key<W>* a_src = c->A.as<Key<W>>() + off_a;
@@ -870,7 +876,9 @@ int run_levels(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mod
       c->count_src = c->B.p; c->bucket_lo = c->bucket_hi = 0;
       if (!single) { c->bucket_lo = (uint32_t)in[0] * (uint32_t)bins1; c->bucket_hi = (uint32_t)in[1] * (uint32_t)bins1; }  // the others are empty
       // the temp records of the range's buckets go over the range's own level-0 keys: dead once level 1 has run
+      c->table_scale = single ? 1.0 : std::max(1.0, (double)N / (double)std::max<uint64_t>(n_counted, 1));
       { int rc = count_buckets<W, ElemB>(c, n_in, N, n_prev, a_src, single); if (rc) return rc; }
+      c->table_scale = 1.0;
       c->bucket_lo = c->bucket_hi = 0;
       off_a += n_in;
     }
@@ -1046,7 +1054,12 @@ int count_buckets(apgk_ctx* c, uint64_t Nr, uint64_t N, uint64_t& n_prev, Key<W>
         CU(cudaMemcpyAsync(&total, c->blocksum.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         if (want_table) {
-          const size_t want = n_prev + total + (nosync ? (total >> 5) : 0);   // a little slack: the next step reuses the buffers
+          // a little slack when this is the whole table (the next step reuses the buffers); when it grows round by
+          // round, room for the rounds still to come (table_scale: all instances over those counted so far), so that
+          // it is allocated once, while it is small, and not copied again and again
+          size_t want = n_prev + total + (nosync ? (total >> 5) : 0);
+          if (!nosync && c->table_scale > 1.0 && (c->out_keys.cap < want * sizeof(Key<W>) || c->out_cnt.cap < want * 4))
+            want = (size_t)((double)want * c->table_scale * 1.12) + 1024;
           { int rc = ensure_preserve(c, c->out_keys, std::max<size_t>(want, 1) * sizeof(Key<W>), n_prev * sizeof(Key<W>)); if (rc) return rc; }
           { int rc = ensure_preserve(c, c->out_cnt, std::max<size_t>(want, 1) * 4, n_prev * 4); if (rc) return rc; }
           k_compact<W><<<c->n_sm * 8, 256, 0, c->stream>>>(tmp_keys, c->T.as<uint32_t>(), c->bofs.as<unsigned long long>(),

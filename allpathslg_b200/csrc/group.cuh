@@ -472,6 +472,7 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
       uint64_t tsum = 0;
       for (int d = 0; d < bins0; d++) tsum += tmax[d];
       const double eA = (double)sizeof(Key<W>);
+      budget = (uint64_t)((double)budget * (0.55 / 0.70));   // in rounds the table grows beside the temp buffers: leave it more room
       for (uint64_t ro = 1;; ro++) {
         const double per_outer = (double)tsum / (double)ro * 1.05 + (double)(tsum / (uint64_t)bins0) * 2.0;   // greedy cuts overshoot by a bucket
         const double left = (double)budget - eA * per_outer;
@@ -636,13 +637,15 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
         // -- count the shard: the context now describes the finer geometry (P + d2 prefix bits)
         c->geom = r.geom_shard; c->nb1 = nbf;
         c->n_rounds++;
+        r.shard_n += Nr;
         if (Nr && hi > lo) {
           c->count_src = c->C2.p;
           c->bucket_lo = lo << d2; c->bucket_hi = hi << d2;
+          c->table_scale = single ? 1.0 : std::max(1.0, (double)N_sum / (double)world / (double)r.shard_n);
           GCTX(c, (count_buckets<W, ElemB>(c, Nr, N_sum, r.n_prev, tmp_keys, single)));
+          c->table_scale = 1.0;
           c->bucket_lo = c->bucket_hi = 0;
         }
-        r.shard_n += Nr;
         // (measurement aid for the single-process form: one rank's shard-side kernels at a time, so that the stage
         // times of contexts that share a device are each rank's own cost -- tools/skew_probe.py)
         static const bool serial = getenv("APGK_GROUP_SERIAL") != nullptr;
