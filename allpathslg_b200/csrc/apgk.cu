@@ -711,11 +711,25 @@ int level1(apgk_ctx* c, int s_lo, int s_hi, uint64_t n_range, const Key<W>* a_sr
   CU(c->B.ensure(std::max<size_t>(n_range, 1) * sizeof(ElemB) + 16));
   stage_begin(c, ST_SCATTER1);
   {
-    auto kern = ScatterSel<ElemB, W>::kernel();
-    const size_t sm = scatter_smem_bytes<Key<W>>(tile, bins1);
-    { int rc = kernel_setup(c, kern, Geo<W>::NT1, sm, nullptr); if (rc) return rc; }
-    kern<<<chunks_bound, Geo<W>::NT1, sm, c->stream>>>(a_src, lp, dg1, c->chunksum.as<uint32_t>(), nullptr, g.pad, g.REM,
-                                                       c->B.as<ElemB>());
+    // APGK_BULK=1: the TMA bulk write-out (k_scatter_keys_bulk) for 32-bit remainders.  Off by default: measured
+    // slower than the register write-out (profiles/r02_bulk_scatter.txt: 23.3 against 19.7 ms) -- the element-wise
+    // write-out doubles as the work that hides the next tile's load latency, and a tile's 1 024 copies of ~64 bytes
+    // do not buy back what that costs.  Kept (and tested) as the measured alternative.
+    const char* eb = getenv("APGK_BULK");
+    const bool bulk = eb && !strcmp(eb, "1");
+    const size_t smb = scatter_bulk_smem_bytes<ElemB>(tile, bins1);
+    if (bulk && sizeof(ElemB) == 4 && smb <= 200 * 1024 && bins1 <= Geo<W>::NT1) {
+      auto kern = k_scatter_keys_bulk<Key<W>, ElemB, Geo<W>::NT1, DIGIT_BITS, false>;
+      { int rc = kernel_setup(c, kern, Geo<W>::NT1, smb, nullptr); if (rc) return rc; }
+      kern<<<chunks_bound, Geo<W>::NT1, smb, c->stream>>>(a_src, lp, dg1, c->chunksum.as<uint32_t>(), nullptr, g.pad, g.REM,
+                                                          c->B.as<ElemB>());
+    } else {
+      auto kern = ScatterSel<ElemB, W>::kernel();
+      const size_t sm = scatter_smem_bytes<Key<W>>(tile, bins1);
+      { int rc = kernel_setup(c, kern, Geo<W>::NT1, sm, nullptr); if (rc) return rc; }
+      kern<<<chunks_bound, Geo<W>::NT1, sm, c->stream>>>(a_src, lp, dg1, c->chunksum.as<uint32_t>(), nullptr, g.pad, g.REM,
+                                                         c->B.as<ElemB>());
+    }
     LAUNCHED();
   }
   stage_end(c, ST_SCATTER1);

@@ -196,6 +196,26 @@ def test_kmer_space_rounds(oracle, K):
         kc.close()
 
 
+@pytest.mark.parametrize("K,n_reads", [(25, 40_000), (20, 30_000), (26, 3_000)])
+def test_bulk_write_out_scatter(oracle, K, n_reads, monkeypatch):
+    """APGK_BULK=1: the level-1 scatter whose runs leave the shared-memory stage as TMA bulk copies
+    (cp.async.bulk.global.shared::cta, per-bin carry of the incomplete 16-byte granule) -- the measured alternative
+    to the default register write-out must give the same table, also over several k-mer-space rounds."""
+    from allpathslg_b200 import KmerCounter
+
+    monkeypatch.setenv("APGK_BULK", "1")
+    sp = oracle.synth_params(300_000, 100)
+    p, o = oracle.synth_reads(sp, 0, n_reads)
+    ek, ec, en = oracle.count(p, o, K)
+    for budget in (0, en // 3 + 1):
+        kc = KmerCounter(K, max_round_keys=budget)
+        kc.add_reads_uniform(p, n_reads, 100)
+        kc.finish()
+        assert kc.geometry()["elem_bytes"] == 4
+        _assert_equal_to_oracle(oracle, kc, p, o, K)
+        kc.close()
+
+
 def test_empty_and_short_inputs(oracle):
     from allpathslg_b200 import KmerCounter
 
