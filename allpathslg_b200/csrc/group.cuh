@@ -618,8 +618,13 @@ int group_count_typed(apgk_group* g, const std::vector<GroupMeta>& meta, bool si
           ga.out = c->C2.as<ElemB>(); ga.bsize_fine = c->segtot.as<unsigned long long>(); ga.bofs_fine = c->bofs.as<unsigned long long>();
           ga.sub_sizes = nullptr;
           ga.sub_ptrs = d2 > 0 ? (const uint32_t* const*)(r.ptrs_dev.as<unsigned char>() + (size_t)world * 8) : nullptr;
-          static const bool legacy = getenv("APGK_GATHER") && !strcmp(getenv("APGK_GATHER"), "legacy");
-          if (legacy) {   // the round-1 kernel: one 16-byte load in flight per lane
+          // Two gather kernels, both tested: the direct one (16-byte loads straight from the peers, one in flight per
+          // lane) and the one pipelined through shared memory with cp.async (APGK_GATHER=pipelined).  Measured at 8
+          // GPUs (profiles/r02_final_bench_n8*.json): 476 against 440 GB/s of remote reads -- with 40+ warps per SM the
+          // direct loads already keep the link busy, and the staging costs an extra trip through shared memory.
+          const char* eg = getenv("APGK_GATHER");
+          const bool direct = !(eg && !strcmp(eg, "pipelined"));
+          if (direct) {
             const uint32_t grid = std::min<uint32_t>((hi - lo + 7) / 8, (uint32_t)c->n_sm * 8);  // one warp per bucket
             k_gather_split<ElemB, 256><<<grid, 256, 0, c->stream>>>(ga);
           } else {

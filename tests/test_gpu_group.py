@@ -99,13 +99,16 @@ def test_group_single_round(oracle, K, world, n_reads, empty, bucket_cost, monke
         kc.close()
 
 
+@pytest.mark.parametrize("gather", ["direct", "pipelined"])
 @pytest.mark.parametrize("K,world,n_reads,outer_div,inner_div", [(25, 3, 30_000, 2, 5), (25, 2, 30_000, 1, 3), (48, 2, 12_000, 2, 4),
                                                                  (20, 4, 20_000, 3, 3), (96, 2, 6_000, 2, 2)])
-def test_group_rounds(oracle, K, world, n_reads, outer_div, inner_div):
+def test_group_rounds(oracle, K, world, n_reads, outer_div, inner_div, gather, monkeypatch):
     """K-mer-space rounds of the sharded form: outer rounds (one filtered extraction each) cut into inner rounds
     (level 1 + exchange + counting); every round's shard table is appended, so the contexts end up with all the
-    k-mers they own."""
+    k-mers they own.  Both gather kernels (direct peer loads; cp.async-pipelined through shared memory)."""
     from allpathslg_b200 import KmerGroup
+
+    monkeypatch.setenv("APGK_GATHER", gather)
 
     L = 100
     per_rank = (n_reads // world) * (L - K + 1)
