@@ -2,7 +2,7 @@
 
 `sharded_count` is a thin caller of the library's group API (include/apgk.h, csrc/group.cuh): every rank runs
 levels 0 and 1 of the single-GPU pipeline on ITS reads, the ranks all-gather the bucket histogram, cut the bucket
-space into `world` contiguous ranges of (nearly) equal instance counts, every rank gathers the ranges it owns
+space into `world` contiguous ranges of (nearly) equal cost (keys + a charge per bucket), every rank gathers the ranges it owns
 straight from the peers' partition buffers over NVLink peer memory (the exchange is fused into the gather kernel)
 and sorts + counts them; the per-rank spectra -- disjoint sets of k-mers, so plain integer sums -- are all-reduced.
 A k-mer's owner depends on the canonical k-mer alone, so counts are final without a merge.
@@ -10,12 +10,10 @@ When a rank's k-mers do not fit its device at once the library runs the same pip
 torch.distributed is used for one thing only: handing rank 0's group id to the other ranks.
 
 The rest of this module is the HOST mirror of the exchange (numpy + gloo/nccl all_to_all), which the CPU test-suite
-runs at world size 2 and 3: the same ownership rule (`balanced_splitters`) and the same round planning
-(`plan_rounds`) as the device code, so the host logic of the N-rank path is covered without a GPU.
+runs at world size 2 and 3: the splitter rule (`balanced_splitters`: the rule of the device's k_splitters, here on
+instance counts), the round planning (`plan_rounds`) and the sparse-spectrum merge, so the host logic of the N-rank
+path is covered without a GPU.
 """
-import os
-import time
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -139,21 +137,6 @@ def merge_sparse_spectra(spec, ni, nd, world, dev, group=None):
     for x, y in far.items():
         out[x] = y
     return out, int(dense[DENSE]), int(dense[DENSE + 1])
-
-
-class _CudaArray:
-    """Minimal __cuda_array_interface__ holder so torch can view library-owned device memory."""
-
-    def __init__(self, ptr, n, typestr="<i8"):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
-def _wrap(ptr, n, typestr, dev):
-    return torch.as_tensor(_CudaArray(ptr, n, typestr), device=dev)
-
-
-def _wrap_u64(ptr, n, dev):
-    return _wrap(ptr, n, "<i8", dev)
 
 
 # ---------------------------------------------------------------------------
