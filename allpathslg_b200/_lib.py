@@ -108,6 +108,7 @@ SYMBOLS = {
     "apgk_debug_host_topdigits": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_int, _vp]),
     "apgk_debug_host_canonical": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
     "apgk_debug_host_table_find": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_int, _vp, C.c_uint64, _vp]),
+    "apgk_debug_host_splitters": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "apgk_debug_host_synth": (C.c_int, [C.POINTER(SynthParams), C.c_uint64, C.c_uint64, _vp]),
 }
 

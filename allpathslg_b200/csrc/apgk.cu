@@ -2483,6 +2483,15 @@ int apgk_debug_host_table_find(int K, const uint64_t* sorted_kmers, uint64_t n, 
   return APGK_OK;
 }
 
+int apgk_debug_host_splitters(const uint32_t* bucket_sizes, uint32_t n_buckets, uint32_t world, uint32_t bucket_cost, uint32_t* bounds_out) {
+  if (!bucket_sizes || !bounds_out || !world) return APGK_E_ARG;
+  // what k_total_sizes (cost column) + the scan + k_splitters do on the device, here on the host
+  std::vector<unsigned long long> S((size_t)n_buckets + 1, 0);
+  for (uint32_t b = 0; b < n_buckets; b++) S[b + 1] = S[b] + (bucket_sizes[b] ? (unsigned long long)bucket_sizes[b] + bucket_cost : 0ull);
+  for (uint32_t r = 0; r <= world; r++) bounds_out[r] = splitter_bound(S.data(), n_buckets, world, r);
+  return APGK_OK;
+}
+
 int apgk_debug_host_synth(const apgk_synth_params* p, uint64_t r0, uint64_t n_reads, uint8_t* packed_out) {
   if (!p || !packed_out) return APGK_E_ARG;
   SynthParams sp{p->genome_len, p->seed_g, p->seed_p, p->seed_q, p->seed_r, p->seed_e, p->read_len, p->err_per_200};

@@ -428,25 +428,25 @@ __global__ void k_total_sizes(const uint32_t* __restrict__ sizes_all, uint32_t n
 // rule of dist.balanced_splitters).  plan[0 .. world] = bounds, plan[world + 1 .. 2 world + 1] = E (the prefix of the
 // merged SIZES) at the bounds, plan[2 world + 2 ..] = own[] at the bounds (the calling rank's own prefix: how much of
 // each range it holds itself).  One thread per bound.
+// bound r of `world` ranges over nb buckets with weight prefix S[nb + 1]  (host-callable: the CPU suite checks the rule)
+APGK_HD uint32_t splitter_bound(const unsigned long long* S, uint32_t nb, uint32_t world, uint32_t r) {
+  if (r == 0) return 0;
+  if (r >= world) return nb;
+  const unsigned long long total = S[nb];
+  const unsigned long long target = (unsigned long long)(((unsigned __int128)total * r) / world);
+  // smallest b in [0, nb] with S[b + 1] > target  (S[nb + 1] := infinity)
+  uint32_t lo = 0, hi = nb;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (S[mid + 1] > target) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
 __global__ void k_splitters(const unsigned long long* __restrict__ S, const unsigned long long* __restrict__ E, uint32_t nb, uint32_t world,
                             const unsigned long long* __restrict__ own, unsigned long long* __restrict__ plan) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > world) return;
-  const unsigned long long total = S[nb];
-  uint32_t bound;
-  if (r == 0) bound = 0;
-  else if (r == world) bound = nb;
-  else {
-    // multiply in 128 bits: total * r may exceed 2^64 only beyond 2^60 instances; plain division order keeps it exact enough
-    const unsigned long long target = (unsigned long long)(((unsigned __int128)total * r) / world);
-    // smallest b in [0, nb] with E[b + 1] > target  (E[nb + 1] := infinity)
-    uint32_t lo = 0, hi = nb;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (S[mid + 1] > target) hi = mid; else lo = mid + 1;
-    }
-    bound = lo;
-  }
+  const uint32_t bound = splitter_bound(S, nb, world, r);
   plan[r] = bound;
   plan[world + 1 + r] = E[bound];
   plan[2 * (world + 1) + r] = own[bound];

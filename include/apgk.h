@@ -333,6 +333,11 @@ int apgk_debug_host_topdigits(const uint8_t* packed, const uint64_t* off, uint64
 int apgk_debug_host_table_find(int K, const uint64_t* sorted_kmers, uint64_t n, int prefix_bits, const uint64_t* queries,
                                uint64_t n_q, uint64_t* idx_out);
 int apgk_debug_host_synth(const apgk_synth_params* p, uint64_t r0, uint64_t n_reads, uint8_t* packed_out);
+/* The sharded form's ownership rule on the HOST: bounds_out[world + 1] = the contiguous bucket ranges of equal cost
+ * (cost of a non-empty bucket = its size + bucket_cost; bucket_cost 0 = equal instance counts) that the device's
+ * k_total_sizes -> scan -> k_splitters derive from the all-gathered bucket sizes. */
+int apgk_debug_host_splitters(const uint32_t* bucket_sizes, uint32_t n_buckets, uint32_t world, uint32_t bucket_cost,
+                              uint32_t* bounds_out);
 
 #ifdef __cplusplus
 }

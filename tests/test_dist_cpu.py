@@ -185,3 +185,38 @@ def test_rounds_spectrum_merge_gloo(tmp_path):
     spec, ni, nd = outs[0][:-2], int(outs[0][-2]), int(outs[0][-1])
     assert len(spec) == 80001 and spec[1] == 12 and spec[2] == 3 and spec[70000] == 3 and spec[80000] == 1
     assert int(spec.sum()) == 19 and (ni, nd) == (600, 60)
+
+
+def test_device_splitter_rule_on_the_host(apgk_lib):
+    """The ownership rule of the sharded form (k_total_sizes -> scan -> k_splitters), run on the host through the
+    library's test hook: with no per-bucket charge it is dist.balanced_splitters; with one, the ranges have equal COST
+    up to one bucket, stay contiguous and cover the bucket space, whatever the skew."""
+    from allpathslg_b200.dist import balanced_splitters
+
+    rnd = np.random.RandomState(5)
+    for nb, world, skew in [(1 << 12, 8, "canonical"), (1 << 10, 3, "uniform"), (1 << 12, 5, "spiky"), (64, 8, "sparse"), (16, 4, "empty")]:
+        if skew == "canonical":      # density 2(1 - x): what canonical k-mers look like over their leading bits
+            sizes = (8000 * (1 - np.arange(nb) / nb) + rnd.randint(0, 50, nb)).astype(np.uint32)
+        elif skew == "uniform":
+            sizes = rnd.randint(3000, 5000, nb).astype(np.uint32)
+        elif skew == "spiky":
+            sizes = rnd.randint(0, 100, nb).astype(np.uint32)
+            sizes[rnd.randint(0, nb, 20)] = 500_000
+        elif skew == "sparse":
+            sizes = np.zeros(nb, dtype=np.uint32)
+            sizes[[3, 40]] = [10, 7]
+        else:
+            sizes = np.zeros(nb, dtype=np.uint32)
+        for cost in (0, 800, 5000):
+            bounds = np.zeros(world + 1, dtype=np.uint32)
+            assert apgk_lib.apgk_debug_host_splitters(sizes.ctypes.data, nb, world, cost, bounds.ctypes.data) == 0
+            b = bounds.astype(np.int64)
+            assert b[0] == 0 and b[-1] == nb and (np.diff(b) >= 0).all()
+            w = np.where(sizes > 0, sizes.astype(np.int64) + cost, 0)
+            if cost == 0:
+                assert b.tolist() == balanced_splitters(sizes.astype(np.int64), world)
+            tot = int(w.sum())
+            per = [int(w[b[r]:b[r + 1]].sum()) for r in range(world)]
+            assert sum(per) == tot
+            if tot:
+                assert max(per) <= tot / world + int(w.max()) + 1     # equal cost up to one bucket
