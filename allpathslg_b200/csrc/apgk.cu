@@ -478,7 +478,13 @@ int finish_impl(apgk_ctx* c, const Key<W>* dev_keys, uint64_t n_keys, RunMode mo
   } else {
     rc = run_levels<W, Key<W>>(c, dev_keys, n_keys, mode);
   }
-  if (rc) { cudaStreamSynchronize(c->stream); c->n_ivs = 0; c->table_pending = false; return rc; }
+  if (rc) {   // leave the context in a state the next call can start from: nothing in flight, no half-recorded intervals
+    if (c->n_slices && c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    c->n_slices = 0;
+    cudaStreamSynchronize(c->stream);
+    c->n_ivs = 0; c->table_pending = false;
+    return rc;
+  }
   stage_end(c, ST_TOTAL);
   c->n_deferred = 0;
   if (mode == RUN_FULL && c->deferred.p && c->n_instances)
