@@ -194,3 +194,29 @@ def test_table_search_on_host(apgk_lib, K, P):
         d = {tuple(k): i for i, k in enumerate(keys.tolist())}
         exp = np.array([d.get(tuple(x), 2 ** 64 - 1) for x in qs.tolist()], dtype=np.uint64)
         assert (out == exp).all(), (K, P, n)
+
+
+def test_group_api_without_a_gpu(apgk_lib):
+    """The group entry points answer without a device: NCCL is loaded on first use and gives an id (the bootstrap
+    needs no GPU), null arguments are refused -- and nothing falls back to the CPU: a context cannot be made, so a
+    group cannot be formed."""
+    import ctypes as C
+
+    import torch
+
+    from allpathslg_b200 import _lib
+
+    buf = np.zeros(128, dtype=np.uint8)
+    rc = apgk_lib.apgk_group_unique_id(buf.ctypes.data)
+    assert rc in (0, _lib.E_CUDA)          # E_CUDA only where libnccl.so.2 cannot be loaded at all
+    if rc == 0:
+        assert buf.any()
+    h = C.c_void_p()
+    assert apgk_lib.apgk_group_local(None, 0, C.byref(h)) == _lib.E_ARG
+    assert apgk_lib.apgk_group_count(None) == _lib.E_ARG
+    assert apgk_lib.apgk_group_totals(None, None, None) == _lib.E_ARG
+    apgk_lib.apgk_group_destroy(None)      # a no-op
+    if not torch.cuda.is_available():
+        cfg = _lib.Config(K=25, device=0, flags=_lib.WANT_COUNTS)
+        ctx = C.c_void_p()
+        assert apgk_lib.apgk_create(C.byref(cfg), C.byref(ctx)) == _lib.E_CUDA   # no CPU fallback
